@@ -1,0 +1,81 @@
+// FP64 scalar math used inside the UDE kernels (sm_100a).
+//
+// The MLP activation of every shipped constructor of the reference is tanh
+// (/root/reference/src/ProcessModels.jl:379,427; src/NeuralNetworkConstructors.jl:20-22), which Lux
+// lowers to NNlib.tanh_fast.  tanh dominates the FP64 issue budget of the hot
+// path (one per hidden unit per RK stage), so it is hand-written: an expm1-style evaluation
+//      tanh|x| = E / (E + 2),   E = expm1(2|x|) = 2^n (1 + p(r)) - 1,   2|x| = n ln2 + r
+// with no cancellation anywhere (relative accuracy ~1 ulp-ish for all x, exact odd symmetry),
+// a MUFU.RCP64H seeded Newton reciprocal instead of the IEEE division sequence, and no branches.
+#pragma once
+#include <cuda_runtime.h>
+
+#ifndef UDE_RCP_NR
+#define UDE_RCP_NR 2
+#endif
+
+// reciprocal of a normal double d (|d| in [2^-500, 2^500]); relative error ~1e-16 after the Newton steps
+__device__ __forceinline__ double ude_rcp(double d) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));      // MUFU.RCP64H: ~2^-20 relative
+#pragma unroll
+  for (int i = 0; i < UDE_RCP_NR; ++i) {
+    double e = fma(-d, y, 1.0);
+    y = fma(y, e, y);
+  }
+  return y;
+}
+
+// num/den for den >= 1 (normal): one residual correction on top of ude_rcp
+__device__ __forceinline__ double ude_div(double num, double den) {
+  double y = ude_rcp(den);
+  double q = num * y;
+  double rem = fma(-q, den, num);
+  return fma(rem, y, q);
+}
+
+__device__ __forceinline__ double ude_tanh(double x) {
+  const double LOG2E  = 1.4426950408889634;
+  const double LN2_HI = 6.93147180369123816490e-01;   // fdlibm split of ln 2
+  const double LN2_LO = 1.90821492927058770002e-10;
+  const double SHIFT  = 6755399441055744.0;           // 1.5 * 2^52: round-to-nearest-integer trick
+  double t = fabs(x);
+  t = t + t;
+  t = fmin(t, 40.0);                                  // tanh(20) == 1.0 in double
+  double kf = fma(t, LOG2E, SHIFT);
+  int n = __double2loint(kf);
+  kf -= SHIFT;
+  double r = fma(kf, -LN2_HI, t);
+  r = fma(kf, -LN2_LO, r);
+  // p = expm1(r), |r| <= ln2/2: r + r^2 (1/2! + r/3! + ... + r^11/13!)
+  double q = 1.6059043836821613e-10;                  // 1/13!
+  q = fma(q, r, 2.08767569878681e-09);                // 1/12!
+  q = fma(q, r, 2.505210838544172e-08);               // 1/11!
+  q = fma(q, r, 2.755731922398589e-07);               // 1/10!
+  q = fma(q, r, 2.7557319223985893e-06);              // 1/9!
+  q = fma(q, r, 2.48015873015873e-05);                // 1/8!
+  q = fma(q, r, 1.984126984126984e-04);               // 1/7!
+  q = fma(q, r, 1.388888888888889e-03);               // 1/6!
+  q = fma(q, r, 8.333333333333333e-03);               // 1/5!
+  q = fma(q, r, 4.1666666666666664e-02);              // 1/4!
+  q = fma(q, r, 1.6666666666666666e-01);              // 1/3!
+  q = fma(q, r, 0.5);                                 // 1/2!
+  double p = fma(q * r, r, r);
+  double s = __hiloint2double((1023 + n) << 20, 0);   // 2^n, 0 <= n <= 58
+  double em1 = fma(s, p, s - 1.0);                    // 2^n (1+p) - 1
+  double y = ude_div(em1, em1 + 2.0);
+  return copysign(y, x);
+}
+
+// single-precision twin for the optional FP32 mode (1e-4 parity bar): hardware tanh is too coarse
+// (2^-11), so use the same E/(E+2) form with ex2.approx; ~1e-6 relative.
+__device__ __forceinline__ float ude_tanhf(float x) {
+  float t = fminf(fabsf(x) * 2.0f, 20.0f);
+  float e = __expf(t);
+  float y = __fdividef(e - 1.0f, e + 1.0f);
+  // small-|x| branch-free fix: for t < 2^-5 use the odd Taylor polynomial (avoids e-1 cancellation)
+  float x2 = x * x;
+  float ys = fabsf(x) * (1.0f + x2 * (-0.33333334f + x2 * 0.13333334f));
+  y = (t < 0.0625f) ? ys : y;
+  return copysignf(y, x);
+}
