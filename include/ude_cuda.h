@@ -1,0 +1,153 @@
+/* ude_cuda.h -- C ABI of libude_cuda.so, the B200 (sm_100a) loss-and-gradient engine for
+ * UniversalDiffEq-style universal differential equations.
+ *
+ * The reference (Jack-H-Buckner/UniversalDiffEq.jl) has NO foreign-function boundary on this path: the
+ * loss is a Julia closure  loss(theta::ComponentVector)::Float64  built by
+ *     conditional_likelihood / multiple_shooting_loss / shooting_loss / derivative_matching_loss
+ *     (src/LossFunctionConstructors.jl:17-98, :261-305, :639-708, :196-232, :545-601, :175-192, :500-540)
+ *     init_loss / init_multi_loss_function (src/helpers.jl:16-76, src/MultipleTimeSeries.jl:121-157)
+ * and differentiated by Zygote through  Optimization.OptimizationFunction(target, AutoZygote())
+ * (src/Optimizers.jl:473-478, :658-663).  The entry points below are what a `ccall` from those two places
+ * binds instead (INTEGRATION.md shows the Julia stub): the handle captures what the closure captured
+ * (data, times, covariates, loss options, solver), and ude_loss_grad is the closure + its pullback.
+ *
+ * Conventions: plain C, host pointers unless the name ends in _device, FP64 arrays, column-major matrices
+ * exactly as Julia stores them, 0-based series offsets (the Julia stub subtracts 1 from `starts`,
+ * src/helpers.jl:516-526).  Every call returns UDE_OK (0) or a negative ude_status; the message is
+ * available from ude_last_error.  Nothing throws across the boundary.  Handles are independent: different
+ * handles may be used from different host threads concurrently (src/CrossValidation.jl:30, :259 call the
+ * optimiser from Threads.@threads); one handle is not re-entrant.
+ */
+#ifndef UDE_CUDA_H
+#define UDE_CUDA_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UDE_ABI_VERSION 1
+#define UDE_MAX_SCALARS 8
+#define UDE_MAX_D 8
+
+typedef enum ude_status {
+  UDE_OK = 0,
+  UDE_ERR_INVALID = -1,      /* bad argument / inconsistent description */
+  UDE_ERR_UNSUPPORTED = -2,  /* shape or RHS kind with no compiled sm_100a kernel */
+  UDE_ERR_CUDA = -3,         /* CUDA runtime error (message has the cudaError string) */
+  UDE_ERR_NO_DEVICE = -4,    /* no usable sm_100 device: there is NO CPU fallback */
+  UDE_ERR_STATE = -5,        /* call order (e.g. loss_grad before set_data) */
+  UDE_ERR_NCCL = -6,
+  UDE_NONFINITE = -7         /* loss or gradient is not finite; outputs are still written (loss = Inf/NaN as computed) */
+} ude_status;
+
+/* solver: fixed-step explicit RK replacing OrdinaryDiffEq.solve(..., Tsit5(), abstol=1e-6, reltol=1e-6)
+ * (src/ProcessModels.jl:82-83); `substeps` steps per observation interval. */
+enum { UDE_RK4 = 0, UDE_TSIT5 = 1 };
+enum { UDE_F64 = 0, UDE_F32 = 1 };
+/* loss kinds */
+enum {
+  UDE_LOSS_STATE_SPACE = 0, /* conditional likelihood (LFC.jl:17-98, :347-404) and the default MSE loss (helpers.jl:16-76) */
+  UDE_LOSS_MULTI_SHOOT = 1, /* LFC.jl:261-305, :639-708 */
+  UDE_LOSS_SHOOT = 2,       /* LFC.jl:196-232, :545-601 */
+  UDE_LOSS_DERIV_MATCH = 3  /* LFC.jl:175-192, :500-540 */
+};
+/* right-hand-side catalog: the shapes users of NODE / MultiNODE / CustomDerivatives write */
+enum {
+  UDE_RHS_NODE = 0,          /* du = NN([u; X(t)])                      src/ProcessModels.jl:387-390, :434-437 */
+  UDE_RHS_NODE_TIME = 1,     /* du[1:nn_out] = NN([u; X(t); a t + b]); du[j>nn_out] = -s_j u_j   docs/src/examples.md:44-49 */
+  UDE_RHS_LV_UDE = 2,        /* du1 = r u1 - NN(u); du2 = theta NN(u) - m u2 (+ beta_i X1)        test/UDETests.jl:20-28, :82-86 */
+  UDE_RHS_LV_UDE_ABS = 3,    /* README.md:52-62 (abs on NN and parameters, logistic prey growth) */
+  UDE_RHS_FISHERY = 4,       /* docs/src/examples.md:163-166 */
+  UDE_RHS_NN_DECAY = 5,      /* du = NN(u) - m u                         test/MultiUDE.jl:17-19 */
+  UDE_RHS_SERIES_GROWTH = 6  /* du = r[series] u NN(u)[1]                docs/src/MultipleTimeSeries.md:51-55 */
+};
+
+typedef struct ude_handle ude_handle;
+
+/* Everything the reference's loss closure captures that is not an array. Offsets are in doubles, relative
+ * to the start of `process_model` inside one model's theta = [uhat (d x n_cols_of_model, column-major) |
+ * process_model | nothing else] (src/helpers.jl:3-11; the other ComponentArray groups are empty). */
+typedef struct ude_desc {
+  int32_t abi_version;        /* UDE_ABI_VERSION */
+  int32_t struct_bytes;       /* sizeof(ude_desc) */
+  int32_t device;             /* CUDA ordinal */
+  int32_t dtype;              /* UDE_F64 (UDE_F32: arithmetic in FP32, reductions in FP64) */
+  int32_t solver, substeps;
+  int32_t rhs_kind, d, n_cov, nn_in, nn_hidden, nn_out, n_scalars, has_series_param;
+  int64_t off_w1, off_b1, off_w2, off_b2;           /* Lux Dense leaves: weight (out x in, column-major), bias */
+  int64_t off_scalar[UDE_MAX_SCALARS];
+  int64_t off_series_param;                         /* vector indexed by the series' position inside its model */
+  int64_t n_pm;                                     /* length of process_model */
+  double time_scale, time_shift;                    /* UDE_RHS_NODE_TIME input feature a*t + b */
+  int32_t loss_kind, pred_length, proc_inv_dt, shoot_from_theta, shoot_first_scored, remove_ends;
+  double preroll_eps;                               /* LFC.jl:268: tspan starts 1e-6 before the block (single-series only) */
+  double A[UDE_MAX_D * UDE_MAX_D];                  /* observation weight, d x d column-major (Sigma_obs^-1) */
+  double B[UDE_MAX_D * UDE_MAX_D];                  /* process weight (Sigma_proc^-1) */
+  int32_t lanes_per_segment;  /* 0 = choose; else force the sub-warp group size G (tuning / tests) */
+  int32_t hidden_per_lane;    /* 0 = choose */
+  int32_t reserved[6];
+} ude_desc;
+
+int ude_abi_version(void);
+int ude_device_count(void);
+
+/* Allocates a handle bound to desc->device. Fails with UDE_ERR_NO_DEVICE when no GPU is present. */
+int ude_create(const ude_desc* desc, ude_handle** out);
+int ude_destroy(ude_handle* h);
+/* Message of the last failure on this handle (h == NULL: last failure of a create on this thread). */
+const char* ude_last_error(const ude_handle* h);
+
+/* data d x n_cols column-major, times n_cols, both sorted by (series, time) as process_multi_data does
+ * (src/helpers.jl:529-556); series s owns columns [starts[s], starts[s]+lengths[s]).  model_of_series
+ * (NULL = one model) lets one handle hold many independent theta vectors (CV folds x ensemble members,
+ * src/CrossValidation.jl:17-45): theta_all = concat over models of [uhat_m | process_model_m]. */
+int ude_set_data(ude_handle* h, int64_t n_series, const int64_t* starts, const int64_t* lengths,
+                 const int64_t* model_of_series, int64_t n_cols, const double* times, const double* data);
+/* per-model loss weights, each n_models long (NULL = ones / zeros for reg_weight):
+ *   obs_scale*A and proc_scale*B(/dt if proc_inv_dt) weight the state-space loss (src/LossFunctions.jl:17-28),
+ *   shoot_weight scales the shooting loss, reg_weight*(|W1|^2+|W2|^2) is added (src/Regularization.jl:97-105). */
+int ude_set_model_weights(ude_handle* h, const double* obs_scale, const double* proc_scale,
+                          const double* shoot_weight, const double* reg_weight);
+/* piecewise-linear covariates with flat extrapolation (src/covariates.jl:16-19, :45-48):
+ * knots of (series s, variable v) are [knot_off[s*n_cov+v], knot_off[s*n_cov+v+1]) */
+int ude_set_covariates(ude_handle* h, const int64_t* knot_off, const double* knot_t, const double* knot_x);
+/* derivative matching inputs: smoothed states and their time derivatives (LFC.jl:161-171), d x n_cols */
+int ude_set_targets(ude_handle* h, const double* smoothed_states, const double* dudt);
+/* skip_mask[c] != 0: the process term of the interval ENDING at column c is left out (t_skip, LFC.jl:82) */
+int ude_set_skip(ude_handle* h, const uint8_t* skip_mask);
+
+int64_t ude_n_theta(const ude_handle* h);
+int64_t ude_n_models(const ude_handle* h);
+/* RK steps one loss evaluation integrates (unit of the throughput metric) and kernels launched per call */
+int64_t ude_steps_per_eval(const ude_handle* h);
+int32_t ude_launches_per_eval(const ude_handle* h);
+
+/* loss[n_models] and grad[n_theta] (grad may be NULL: loss only). Synchronous, host buffers:
+ * H2D(theta) -> kernels (-> allreduce) -> D2H(loss, grad). */
+int ude_loss_grad(ude_handle* h, const double* theta, int64_t n_theta, double* loss, double* grad);
+/* Same with device-resident theta / loss / grad on `stream` (a cudaStream_t; NULL = the handle's stream).
+ * Asynchronous: returns after enqueueing. No nonfinite check. */
+int ude_loss_grad_device(ude_handle* h, const double* d_theta, double* d_loss, double* d_grad, void* stream);
+/* Forward-only trajectories at every column (shooting_states / multiple_shooting_states / predictions,
+ * LFC.jl:237-258, :310-341, :604-631, :711-756; src/ModelTesting.jl:181-195): out is d x n_cols. */
+int ude_forward(ude_handle* h, const double* theta, int64_t n_theta, double* out);
+
+/* Multi-GPU (one handle per GPU, one rank per process or per host thread): after ude_comm_init every
+ * ude_loss_grad* call sum-allreduces [grad of process_model (minus the per-series vector) | loss] across
+ * ranks with one NCCL call on the handle's stream. id_bytes is an ncclUniqueId (128 B). */
+int ude_comm_unique_id(void* id_bytes, int32_t n_bytes);
+int ude_comm_init(ude_handle* h, const void* id_bytes, int32_t n_bytes, int32_t n_ranks, int32_t rank);
+
+/* Device-resident Adam (Optimisers.jl semantics: beta=(0.9,0.999), eps=1e-8, bias-corrected), SURVEY.md 8f row 1.
+ * Runs n_iter iterations of loss_grad + update without leaving the device; theta is read and written back.
+ * loss_trace (n_iter doubles per model, may be NULL) receives the loss before each update. */
+int ude_adam(ude_handle* h, double* theta, int64_t n_theta, double step_size, int32_t n_iter, double* loss_trace);
+
+/* Measured FP64 FMA throughput of the device (TFLOP/s): the roofline denominator bench.py reports against. */
+int ude_measure_fp64_peak(int32_t device, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,133 @@
+"""Parity of the CUDA hot path (through the C ABI, host buffers) against the CPU oracle on identical inputs.
+
+Bar (BASELINE.json north_star): loss and gradient within 1e-10 relative in FP64.  The oracle and the kernels share
+the discretisation (fixed-step RK4 / Tsit5, `substeps` per observation interval) but no code; they differ in
+summation order, FMA contraction, the tanh implementation (libm vs ude_tanh_tab, <= 2 ulp apart) and the covariate
+interpolation (division vs precomputed reciprocal), all O(1e-16) effects.
+"""
+import numpy as np
+import pytest
+
+import cases
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-10   # relative, FP64 (north_star)
+
+
+def _check(prob, theta, ude, **kw):
+    L_ref, g_ref = oracle.loss_grad(prob, theta)
+    with ude.Engine(prob, **kw) as eng:
+        L, g = eng.loss_grad(theta)
+        L2, _ = eng.loss_grad(theta, want_grad=False)
+        assert eng.steps_per_eval() == prob.count_steps() == oracle.count_steps(prob)
+    assert np.all(np.isfinite(L)) and np.all(np.isfinite(g))
+    assert np.max(np.abs(L - L_ref) / np.abs(L_ref)) < TOL, (L, L_ref)
+    assert np.max(np.abs(L2 - L_ref) / np.abs(L_ref)) < TOL, (L2, L_ref)
+    # gradient: norm-wise per model block (entries that are structurally zero must be exactly zero)
+    for m in range(prob.n_models):
+        lo = int(prob.theta_base[m]); hi = int(prob.theta_base[m + 1]) if m + 1 < prob.n_models else prob.n_theta
+        assert cases.relerr(g[lo:hi], g_ref[lo:hi]) < TOL, (m, cases.relerr(g[lo:hi], g_ref[lo:hi]))
+    assert np.all(g[g_ref == 0.0] == 0.0)
+
+
+@pytest.mark.parametrize("solver", [0, 1], ids=["rk4", "tsit5"])
+@pytest.mark.parametrize("loss", cases.LOSSES)
+@pytest.mark.parametrize("rhs", list(cases.RHS_SPECS))
+def test_parity_all_kinds(ude, rhs, loss, solver):
+    prob, theta = cases.make_case(rhs, loss, solver, skip=(loss in ("cond_lik", "mse")))
+    _check(prob, theta, ude)
+
+
+@pytest.mark.parametrize("loss", ["cond_lik", "mse", "multi_shoot", "shoot_theta", "deriv_match"])
+def test_parity_many_models(ude, loss):
+    """CV folds x ensemble members: independent theta vectors in one handle (src/CrossValidation.jl:17-45)."""
+    prob, theta = cases.make_case("node_time_d3", loss, 0, lengths=(9, 8, 7, 6, 5, 4, 11, 3), n_models=8)
+    _check(prob, theta, ude)
+    prob, theta = cases.make_case("node_d2", loss, 1, lengths=(9, 3, 7, 6, 5, 4), n_models=3)
+    _check(prob, theta, ude)
+
+
+@pytest.mark.parametrize("g_hpl", [(4, 3), (16, 2)])
+def test_parity_group_shapes_node2(ude, g_hpl):
+    prob, theta = cases.make_case("node_d2", "multi_shoot", 0, hidden=10, lengths=(23, 11, 6, 31, 5, 1, 2, 16))
+    _check(prob, theta, ude, lanes_per_segment=g_hpl[0], hidden_per_lane=g_hpl[1])
+
+
+@pytest.mark.parametrize("g_hpl,hidden", [((4, 3), 12), ((16, 2), 32), ((8, 4), 32), ((16, 2), 20), ((8, 4), 7)])
+@pytest.mark.parametrize("loss", ["multi_shoot", "mse"])
+def test_parity_group_shapes_c3(ude, g_hpl, hidden, loss):
+    prob, theta = cases.make_case("node_d4x1", loss, 0, hidden=hidden, lengths=(30, 30, 7, 12, 1, 30, 26, 3), substeps=4)
+    _check(prob, theta, ude, lanes_per_segment=g_hpl[0], hidden_per_lane=g_hpl[1])
+
+
+def test_parity_wide_node(ude):
+    prob, theta = cases.make_case("node_d8", "cond_lik", 0, hidden=128, lengths=(2,) * 9 + (5,), substeps=4)
+    _check(prob, theta, ude)
+    prob, theta = cases.make_case("node_d8", "multi_shoot", 1, hidden=100, lengths=(7, 6, 3), substeps=2)
+    _check(prob, theta, ude)
+
+
+@pytest.mark.parametrize("name,kw", [("c1", {}), ("c2", dict(n_series=40)), ("c3", dict(n_series=25)),
+                                     ("c3", dict(n_series=25, loss="mse")), ("c4", dict(n_members=3, n_folds=4, n_pts=30)),
+                                     ("c5", dict(n_segments=70))])
+def test_parity_baseline_configs_reduced(ude, name, kw):
+    """The five BASELINE.json configs at sizes the oracle finishes in seconds."""
+    for solver in (0, 1):
+        prob, theta = ude.synthetic.CONFIGS[name](solver=solver, **kw)
+        rng = np.random.default_rng(7)
+        theta = theta + 0.01 * rng.normal(size=theta.shape)
+        _check(prob, theta, ude)
+
+
+def test_forward_states(ude):
+    """shooting_states / multiple_shooting_states / one-step predictions (LFC.jl:237-258, :310-341; ModelTesting.jl:181-195)."""
+    for loss in ("multi_shoot", "multi_shoot_preroll", "shoot_theta", "shoot_data", "cond_lik"):
+        prob, theta = cases.make_case("node_d2x1", loss, 0, lengths=(11, 1, 6, 16), skip=False)
+        ref = oracle.forward(prob, theta)
+        with ude.Engine(prob) as eng:
+            out = eng.forward(theta)
+        assert cases.relerr(out, ref) < TOL, loss
+
+
+def test_repeatable_bitwise(ude):
+    """Single-model reductions have a fixed order: two evaluations give bit-identical process-model gradients."""
+    prob, theta = ude.synthetic.config_c3(n_series=300)
+    with ude.Engine(prob) as eng:
+        L1, g1 = eng.loss_grad(theta)
+        L2, g2 = eng.loss_grad(theta)
+    pmb = prob.pm_base(0)
+    assert L1[0] == L2[0]
+    assert np.array_equal(g1[pmb:], g2[pmb:])
+    assert np.array_equal(g1[:pmb], g2[:pmb])     # <= 2 atomic contributions per uhat entry: order-independent
+
+
+def test_error_paths(ude):
+    prob, theta = cases.make_case("node_d2", "cond_lik", 0)
+    with ude.Engine(prob) as eng:
+        with pytest.raises(ude.UdeError):
+            eng.loss_grad(theta[:-1])
+    bad, _ = cases.make_case("node_d2", "cond_lik", 0, hidden=300)       # no compiled kernel that wide for d = 2
+    with pytest.raises(ude.UdeError) as ei:
+        with ude.Engine(bad) as eng:
+            eng.loss_grad(np.zeros(bad.n_theta))
+    assert ei.value.code == -2
+    th = theta.copy(); th[prob.pm_base(0)] = np.inf
+    with ude.Engine(prob) as eng:
+        L, g = eng.loss_grad(th)
+    assert not np.isfinite(L[0])
+
+
+def test_adam_matches_host_loop(ude):
+    """Device-resident Adam == the same update applied on the host with oracle gradients."""
+    prob, theta = cases.make_case("lv_ude", "cond_lik", 0, lengths=(12, 9))
+    with ude.Engine(prob) as eng:
+        th_dev, trace = eng.adam(theta, 0.01, 5)
+    th = theta.copy(); m = np.zeros_like(th); v = np.zeros_like(th)
+    for it in range(1, 6):
+        L, g = oracle.loss_grad(prob, th)
+        assert abs(trace[it - 1, 0] - L[0]) / abs(L[0]) < 1e-9
+        m = 0.9 * m + 0.1 * g; v = 0.999 * v + 0.001 * g * g
+        th = th - 0.01 * (m / (1 - 0.9 ** it)) / (np.sqrt(v / (1 - 0.999 ** it)) + 1e-8)
+    assert cases.relerr(th_dev, th) < 1e-9

@@ -6,3 +6,4 @@ The directory name carries a dot, so import it through the repo-root shim:  ``im
 """
 from . import problem, synthetic  # noqa: F401
 from .problem import Problem  # noqa: F401
+from ._capi import Engine, UdeError, device_count, measure_fp64_peak, get_unique_id, load_library, LIB_PATH  # noqa: F401,E402

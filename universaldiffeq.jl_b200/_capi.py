@@ -1,0 +1,270 @@
+"""ctypes binding of libude_cuda.so (include/ude_cuda.h) and the ``Engine`` wrapper that feeds it a Problem.
+
+This is the Python counterpart of the `ccall` stub INTEGRATION.md gives for Julia: the same entry points, the same
+argument order, no torch types.  There is no CPU fallback anywhere in this module: if the shared library is missing
+or no sm_100 device is present, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+
+from .problem import MAX_SCALARS, Problem
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libude_cuda.so")
+ABI_VERSION = 1
+MAX_D = 8
+
+UDE_OK = 0
+STATUS = {0: "UDE_OK", -1: "UDE_ERR_INVALID", -2: "UDE_ERR_UNSUPPORTED", -3: "UDE_ERR_CUDA", -4: "UDE_ERR_NO_DEVICE",
+          -5: "UDE_ERR_STATE", -6: "UDE_ERR_NCCL", -7: "UDE_NONFINITE"}
+UDE_NONFINITE = -7
+
+EXPORTS = ["ude_abi_version", "ude_device_count", "ude_create", "ude_destroy", "ude_last_error", "ude_set_data",
+           "ude_set_model_weights", "ude_set_covariates", "ude_set_targets", "ude_set_skip", "ude_n_theta",
+           "ude_n_models", "ude_steps_per_eval", "ude_launches_per_eval", "ude_loss_grad", "ude_loss_grad_device",
+           "ude_forward", "ude_comm_unique_id", "ude_comm_init", "ude_adam", "ude_measure_fp64_peak"]
+
+
+class UdeDesc(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32), ("struct_bytes", C.c_int32), ("device", C.c_int32), ("dtype", C.c_int32),
+        ("solver", C.c_int32), ("substeps", C.c_int32),
+        ("rhs_kind", C.c_int32), ("d", C.c_int32), ("n_cov", C.c_int32), ("nn_in", C.c_int32), ("nn_hidden", C.c_int32),
+        ("nn_out", C.c_int32), ("n_scalars", C.c_int32), ("has_series_param", C.c_int32),
+        ("off_w1", C.c_int64), ("off_b1", C.c_int64), ("off_w2", C.c_int64), ("off_b2", C.c_int64),
+        ("off_scalar", C.c_int64 * MAX_SCALARS), ("off_series_param", C.c_int64), ("n_pm", C.c_int64),
+        ("time_scale", C.c_double), ("time_shift", C.c_double),
+        ("loss_kind", C.c_int32), ("pred_length", C.c_int32), ("proc_inv_dt", C.c_int32), ("shoot_from_theta", C.c_int32),
+        ("shoot_first_scored", C.c_int32), ("remove_ends", C.c_int32),
+        ("preroll_eps", C.c_double),
+        ("A", C.c_double * (MAX_D * MAX_D)), ("B", C.c_double * (MAX_D * MAX_D)),
+        ("lanes_per_segment", C.c_int32), ("hidden_per_lane", C.c_int32), ("reserved", C.c_int32 * 6),
+    ]
+
+
+class UdeError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"{STATUS.get(code, code)}: {msg}")
+        self.code = code
+
+
+_LIB = None
+
+
+def load_library():
+    """Loads libude_cuda.so; raises (never falls back) when it has not been built."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise FileNotFoundError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                                "(the CUDA library is the only implementation; there is no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64, dp = C.c_void_p, C.c_int32, C.c_int64, C.c_void_p
+    lib.ude_abi_version.restype = C.c_int
+    lib.ude_device_count.restype = C.c_int
+    lib.ude_create.restype = C.c_int
+    lib.ude_create.argtypes = [C.POINTER(UdeDesc), C.POINTER(vp)]
+    lib.ude_destroy.restype = C.c_int
+    lib.ude_destroy.argtypes = [vp]
+    lib.ude_last_error.restype = C.c_char_p
+    lib.ude_last_error.argtypes = [vp]
+    lib.ude_set_data.restype = C.c_int
+    lib.ude_set_data.argtypes = [vp, i64, dp, dp, dp, i64, dp, dp]
+    lib.ude_set_model_weights.restype = C.c_int
+    lib.ude_set_model_weights.argtypes = [vp, dp, dp, dp, dp]
+    lib.ude_set_covariates.restype = C.c_int
+    lib.ude_set_covariates.argtypes = [vp, dp, dp, dp]
+    lib.ude_set_targets.restype = C.c_int
+    lib.ude_set_targets.argtypes = [vp, dp, dp]
+    lib.ude_set_skip.restype = C.c_int
+    lib.ude_set_skip.argtypes = [vp, dp]
+    lib.ude_n_theta.restype = i64
+    lib.ude_n_theta.argtypes = [vp]
+    lib.ude_n_models.restype = i64
+    lib.ude_n_models.argtypes = [vp]
+    lib.ude_steps_per_eval.restype = i64
+    lib.ude_steps_per_eval.argtypes = [vp]
+    lib.ude_launches_per_eval.restype = i32
+    lib.ude_launches_per_eval.argtypes = [vp]
+    lib.ude_loss_grad.restype = C.c_int
+    lib.ude_loss_grad.argtypes = [vp, dp, i64, dp, dp]
+    lib.ude_loss_grad_device.restype = C.c_int
+    lib.ude_loss_grad_device.argtypes = [vp, vp, vp, vp, vp]
+    lib.ude_forward.restype = C.c_int
+    lib.ude_forward.argtypes = [vp, dp, i64, dp]
+    lib.ude_comm_unique_id.restype = C.c_int
+    lib.ude_comm_unique_id.argtypes = [vp, i32]
+    lib.ude_comm_init.restype = C.c_int
+    lib.ude_comm_init.argtypes = [vp, vp, i32, i32, i32]
+    lib.ude_adam.restype = C.c_int
+    lib.ude_adam.argtypes = [vp, dp, i64, C.c_double, i32, dp]
+    lib.ude_measure_fp64_peak.restype = C.c_int
+    lib.ude_measure_fp64_peak.argtypes = [i32, C.POINTER(C.c_double)]
+    if lib.ude_abi_version() != ABI_VERSION:
+        raise RuntimeError("libude_cuda ABI version mismatch")
+    _LIB = lib
+    return lib
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def make_desc(p: Problem, device: int = 0, lanes_per_segment: int = 0, hidden_per_lane: int = 0) -> UdeDesc:
+    d = UdeDesc()
+    d.abi_version = ABI_VERSION
+    d.struct_bytes = C.sizeof(UdeDesc)
+    d.device = device
+    d.dtype = 0
+    for name in ("solver", "substeps", "rhs_kind", "d", "n_cov", "nn_in", "nn_hidden", "nn_out", "n_scalars",
+                 "off_w1", "off_b1", "off_w2", "off_b2", "n_pm", "time_scale", "time_shift", "loss_kind", "pred_length",
+                 "shoot_first_scored", "remove_ends", "preroll_eps"):
+        setattr(d, name, getattr(p, name))
+    d.has_series_param = int(p.has_series_param)
+    d.proc_inv_dt = int(p.proc_inv_dt)
+    d.shoot_from_theta = int(p.shoot_from_theta)
+    d.off_series_param = int(p.off_series_param)
+    for k, o in enumerate(p.off_scalar):
+        d.off_scalar[k] = int(o)
+    A = np.asfortranarray(p.A).reshape(-1, order="F")
+    B = np.asfortranarray(p.B).reshape(-1, order="F")
+    for k in range(p.d * p.d):
+        d.A[k] = A[k]
+        d.B[k] = B[k]
+    d.lanes_per_segment = lanes_per_segment
+    d.hidden_per_lane = hidden_per_lane
+    return d
+
+
+def device_count() -> int:
+    return int(load_library().ude_device_count())
+
+
+def get_unique_id() -> bytes:
+    lib = load_library()
+    buf = C.create_string_buffer(128)
+    rc = lib.ude_comm_unique_id(buf, 128)
+    if rc != UDE_OK:
+        raise UdeError(rc, lib.ude_last_error(None).decode())
+    return buf.raw
+
+
+def measure_fp64_peak(device: int = 0) -> float:
+    lib = load_library()
+    out = C.c_double(0.0)
+    rc = lib.ude_measure_fp64_peak(device, C.byref(out))
+    if rc != UDE_OK:
+        raise UdeError(rc, lib.ude_last_error(None).decode())
+    return float(out.value)
+
+
+class Engine:
+    """One ude_handle: the batched loss-and-gradient evaluator of a finalized Problem on one GPU."""
+
+    def __init__(self, p: Problem, device: int = 0, lanes_per_segment: int = 0, hidden_per_lane: int = 0):
+        self.lib = load_library()
+        self.problem = p
+        self.handle = C.c_void_p()
+        desc = make_desc(p, device, lanes_per_segment, hidden_per_lane)
+        rc = self.lib.ude_create(C.byref(desc), C.byref(self.handle))
+        if rc != UDE_OK:
+            raise UdeError(rc, self.lib.ude_last_error(None).decode())
+        try:
+            mos = p.model_of_series if p.n_models > 1 else None
+            self._check(self.lib.ude_set_data(self.handle, p.n_series, _ptr(p.starts), _ptr(p.lengths), _ptr(mos),
+                                              p.n_cols, _ptr(p.times), _ptr(p.data)))
+            self._check(self.lib.ude_set_model_weights(self.handle, _ptr(p.obs_scale), _ptr(p.proc_scale),
+                                                       _ptr(p.shoot_weight), _ptr(p.reg_weight)))
+            if p.n_cov > 0:
+                self._check(self.lib.ude_set_covariates(self.handle, _ptr(p.knot_off), _ptr(p.knot_t), _ptr(p.knot_x)))
+            if p.dm_u is not None:
+                self._check(self.lib.ude_set_targets(self.handle, _ptr(p.dm_u), _ptr(p.dm_dudt)))
+            if p.skip_mask is not None:
+                self._check(self.lib.ude_set_skip(self.handle, _ptr(p.skip_mask)))
+            n = int(self.lib.ude_n_theta(self.handle))
+            if n != p.n_theta:
+                raise RuntimeError(f"theta layout mismatch: library {n}, host {p.n_theta}")
+        except Exception:
+            self.close()
+            raise
+
+    # -- plumbing --------------------------------------------------------------------------------
+    def _check(self, rc, allow_nonfinite=False):
+        if rc == UDE_OK or (allow_nonfinite and rc == UDE_NONFINITE):
+            return rc
+        raise UdeError(rc, self.lib.ude_last_error(self.handle).decode())
+
+    def close(self):
+        if getattr(self, "handle", None) is not None and self.handle.value:
+            self.lib.ude_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- the hot path ----------------------------------------------------------------------------
+    @property
+    def n_theta(self) -> int:
+        return int(self.lib.ude_n_theta(self.handle))
+
+    @property
+    def n_models(self) -> int:
+        return int(self.lib.ude_n_models(self.handle))
+
+    def steps_per_eval(self) -> int:
+        n = int(self.lib.ude_steps_per_eval(self.handle))
+        if n < 0:
+            raise UdeError(-1, self.lib.ude_last_error(self.handle).decode())
+        return n
+
+    def launches_per_eval(self) -> int:
+        return int(self.lib.ude_launches_per_eval(self.handle))
+
+    def loss_grad(self, theta: np.ndarray, want_grad: bool = True, loss_out=None, grad_out=None):
+        """(loss[n_models], grad[n_theta] | None) through host buffers: H2D(theta) -> kernels -> D2H(loss, grad)."""
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        loss = np.empty(self.problem.n_models) if loss_out is None else loss_out
+        grad = (np.empty(theta.shape[0]) if grad_out is None else grad_out) if want_grad else None
+        self._check(self.lib.ude_loss_grad(self.handle, _ptr(theta), theta.shape[0], _ptr(loss), _ptr(grad)),
+                    allow_nonfinite=True)
+        return loss, grad
+
+    def loss_grad_ptr(self, theta_ptr: int, n_theta: int, loss_ptr: int, grad_ptr: int):
+        """Same call on raw HOST addresses (e.g. pinned torch tensors' data_ptr())."""
+        return self._check(self.lib.ude_loss_grad(self.handle, theta_ptr, n_theta, loss_ptr, grad_ptr), allow_nonfinite=True)
+
+    def loss_grad_device(self, d_theta: int, d_loss: int, d_grad: int, stream: int = 0):
+        """Device-resident variant (raw device addresses); asynchronous on `stream` (0 = the handle's stream)."""
+        return self._check(self.lib.ude_loss_grad_device(self.handle, d_theta, d_loss, d_grad or None, stream or None))
+
+    def forward(self, theta: np.ndarray) -> np.ndarray:
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        out = np.zeros((self.problem.d, self.problem.n_cols), order="F")
+        self._check(self.lib.ude_forward(self.handle, _ptr(theta), theta.shape[0], _ptr(out)))
+        return out
+
+    def adam(self, theta: np.ndarray, step_size: float, n_iter: int):
+        """Device-resident Adam; returns (theta_new, loss_trace[n_iter, n_models])."""
+        theta = np.array(theta, dtype=np.float64, order="C", copy=True)
+        trace = np.zeros((max(n_iter, 1), self.problem.n_models))
+        self._check(self.lib.ude_adam(self.handle, _ptr(theta), theta.shape[0], float(step_size), int(n_iter), _ptr(trace)))
+        return theta, trace[:n_iter]
+
+    def comm_init(self, unique_id: bytes, n_ranks: int, rank: int):
+        buf = C.create_string_buffer(unique_id, 128)
+        self._check(self.lib.ude_comm_init(self.handle, buf, 128, n_ranks, rank))

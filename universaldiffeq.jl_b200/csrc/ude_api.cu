@@ -1,0 +1,721 @@
+// libude_cuda.so -- C ABI (include/ude_cuda.h) over the sm_100a kernels.  There is no CPU fallback: every entry
+// point that computes fails with UDE_ERR_NO_DEVICE / UDE_ERR_CUDA when no Blackwell GPU is usable.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/ude_cuda.h"
+#include "ude_device.cuh"
+#include "ude_registry.h"
+
+namespace ude {
+std::vector<KernelEntry>& kernel_registry() {
+  static std::vector<KernelEntry> r;
+  return r;
+}
+}  // namespace ude
+
+using ude::DevProblem;
+using ude::KernelEntry;
+using ude::Seg;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  ~DevBuf() { release(); }
+  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  cudaError_t reserve(size_t count) {
+    if (count <= n && p) return cudaSuccess;
+    release();
+    if (count == 0) count = 1;
+    cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+    if (e == cudaSuccess) n = count;
+    return e;
+  }
+  cudaError_t upload(const T* src, size_t count, cudaStream_t s) {
+    cudaError_t e = reserve(count);
+    if (e != cudaSuccess) return e;
+    if (count == 0) return cudaSuccess;
+    return cudaMemcpyAsync(p, src, count * sizeof(T), cudaMemcpyHostToDevice, s);
+  }
+};
+
+// ---- NCCL through dlopen: the single-GPU path has no NCCL dependency --------------------------------------------
+struct Id128 { char b[128]; };   // ncclUniqueId, passed BY VALUE to ncclCommInitRank
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, Id128, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+
+bool nccl_load(std::string& err) {
+  if (g_nccl.lib) return true;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* nm : names) { g_nccl.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (g_nccl.lib) break; }
+  if (!g_nccl.lib) { err = std::string("dlopen(libnccl.so.2) failed: ") + dlerror(); return false; }
+  g_nccl.GetUniqueId = (int (*)(void*))dlsym(g_nccl.lib, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (int (*)(void**, int, Id128, int))dlsym(g_nccl.lib, "ncclCommInitRank");
+  g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(g_nccl.lib, "ncclAllReduce");
+  g_nccl.CommDestroy = (int (*)(void*))dlsym(g_nccl.lib, "ncclCommDestroy");
+  g_nccl.GetErrorString = (const char* (*)(int))dlsym(g_nccl.lib, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce) { err = "NCCL symbols missing"; return false; }
+  return true;
+}
+
+}  // namespace
+
+struct ude_handle {
+  ude_desc desc{};
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  mutable std::string err;
+  // host copies of the index arrays
+  int64_t n_series = 0, n_cols = 0, n_models = 1, n_theta = 0;
+  std::vector<int64_t> starts, lengths, model_of_series, theta_base, model_col0, model_series0;
+  std::vector<uint8_t> skip;
+  std::vector<double> obs_scale, proc_scale, shoot_weight, reg_weight;
+  bool have_data = false, have_cov = false, have_targets = false, dirty = true;
+  // device buffers
+  DevBuf<long long> d_starts, d_lengths, d_theta_base, d_model_col0, d_model_series0, d_knot_off;
+  DevBuf<double> d_times, d_data, d_obs_scale, d_proc_scale, d_shoot_weight, d_reg_weight;
+  DevBuf<double> d_knot_t, d_knot_x, d_knot_inv, d_dm_u, d_dm_dudt;
+  DevBuf<Seg> d_segs;
+  DevBuf<double> d_theta, d_grad, d_loss, d_block_part, d_model_loss, d_stash, d_traj, d_red, d_adam_m, d_adam_v;
+  // launch plan
+  const KernelEntry* k_grad = nullptr;
+  const KernelEntry* k_fwd = nullptr;
+  int64_t n_tasks = 0, steps_per_eval = 0, max_steps_per_task = 0;
+  int grid_grad = 0, grid_fwd = 0;
+  long long stash_rows_per_warp = 0;
+  size_t smem_bytes = 0;
+  // multi-GPU
+  void* comm = nullptr;
+  int n_ranks = 1, rank = 0;
+};
+
+namespace {
+
+int fail(const ude_handle* h, int code, const std::string& msg) {
+  if (h) h->err = msg; else g_create_error = msg;
+  return code;
+}
+#define UDE_CUDA_TRY(h, expr)                                                                         \
+  do { cudaError_t e_ = (expr);                                                                       \
+    if (e_ != cudaSuccess) return fail((h), UDE_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); } while (0)
+
+// ---- reductions that follow the segment kernel --------------------------------------------------------------------
+// single model: out[k] = sum_b block_part[b][k] (+ L2 regulariser); loss likewise.  Fixed summation order.
+__global__ void ude_finalize_single(const double* __restrict__ block_part, int n_blocks, long long n_pm,
+                                    const double* __restrict__ pm, long long off_w1, long long n_w1, long long off_w2,
+                                    long long n_w2, long long series_lo, long long series_hi, const double* __restrict__ reg_weight,
+                                    double* __restrict__ grad_pm, double* __restrict__ loss_out, int accumulate_series) {
+  __shared__ double sh[8][33];
+  const int x = threadIdx.x, y = threadIdx.y;
+  const long long k = (long long)blockIdx.x * 32 + x;
+  const double rw = reg_weight ? reg_weight[0] : 0.0;
+  double acc = 0.0;
+  if (k <= n_pm) {
+    for (int b = y; b < n_blocks; b += 8) acc += block_part[(long long)b * (n_pm + 1) + k];
+    if (k == n_pm && rw != 0.0) {   // the loss slot: add rw * (|W1|^2 + |W2|^2), partitioned over y
+      double r = 0.0;
+      for (long long i = y; i < n_w1; i += 8) { double v = pm[off_w1 + i]; r = fma(v, v, r); }
+      for (long long i = y; i < n_w2; i += 8) { double v = pm[off_w2 + i]; r = fma(v, v, r); }
+      acc = fma(rw, r, acc);
+    }
+  }
+  sh[y][x] = acc;
+  __syncthreads();
+  if (y == 0 && k <= n_pm) {
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += sh[i][x];
+    if (k == n_pm) { loss_out[0] = s; }
+    else {
+      const bool isw = (k >= off_w1 && k < off_w1 + n_w1) || (k >= off_w2 && k < off_w2 + n_w2);
+      if (isw && rw != 0.0) s = fma(2.0 * rw, pm[k], s);
+      if (k >= series_lo && k < series_hi) { if (accumulate_series) grad_pm[k] += s; }   // written by atomics in the segment kernel
+      else grad_pm[k] = s;
+    }
+  }
+}
+
+// many models: loss[m] = model_loss[m] + reg; grad_pm += 2 rw W.  One block per model.
+__global__ void ude_finalize_multi(const double* __restrict__ theta, double* __restrict__ grad, const double* __restrict__ model_loss,
+                                   const long long* __restrict__ theta_base, const long long* __restrict__ model_col0, int d,
+                                   long long off_w1, long long n_w1, long long off_w2, long long n_w2,
+                                   const double* __restrict__ reg_weight, double* __restrict__ loss_out) {
+  const int m = blockIdx.x;
+  const long long base = theta_base[m] + (long long)d * (model_col0[m + 1] - model_col0[m]);
+  const double rw = reg_weight ? reg_weight[m] : 0.0;
+  double r = 0.0;
+  if (rw != 0.0) {
+    for (long long i = threadIdx.x; i < n_w1 + n_w2; i += blockDim.x) {
+      const long long k = i < n_w1 ? off_w1 + i : off_w2 + (i - n_w1);
+      const double v = theta[base + k];
+      r = fma(v, v, r);
+      if (grad) grad[base + k] = fma(2.0 * rw, v, grad[base + k]);
+    }
+  }
+  __shared__ double sh[128];
+  sh[threadIdx.x] = r;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) { if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s]; __syncthreads(); }
+  if (threadIdx.x == 0) loss_out[m] = fma(rw, sh[0], model_loss[m]);
+}
+
+__global__ void ude_scatter_reduced(const double* __restrict__ red, long long n_pm, long long series_lo, long long series_hi,
+                                    double* __restrict__ grad_pm, double* __restrict__ loss_out) {
+  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n_pm) { if (!(k >= series_lo && k < series_hi)) grad_pm[k] = red[k]; }
+  else if (k == n_pm) loss_out[0] = red[n_pm];
+}
+
+// Optimisers.jl Adam: m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2; theta -= eta * (m/(1-b1^t)) / (sqrt(v/(1-b2^t)) + eps)
+__global__ void ude_adam_update(double* __restrict__ theta, double* __restrict__ m, double* __restrict__ v,
+                                const double* __restrict__ g, long long n, double eta, double c1, double c2) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const double gi = g[i];
+    const double mi = 0.9 * m[i] + 0.1 * gi;
+    const double vi = 0.999 * v[i] + 0.001 * gi * gi;
+    m[i] = mi; v[i] = vi;
+    theta[i] -= eta * (mi / c1) / (sqrt(vi / c2) + 1e-8);
+  }
+}
+
+__global__ void ude_dfma_peak(double* out, int iters, double a, double b) {
+  double acc[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) acc[c] = threadIdx.x * 1e-3 + c;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[c] = fma(acc[c], a, b);
+  }
+  double s = 0;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) s += acc[c];
+  if (s == 123.456) out[0] = s;
+}
+
+// ---- segment table -------------------------------------------------------------------------------------------------
+int build_plan(ude_handle* h) {
+  const ude_desc& D = h->desc;
+  if (!h->have_data) return fail(h, UDE_ERR_STATE, "ude_set_data has not been called");
+  if (D.n_cov > 0 && !h->have_cov) return fail(h, UDE_ERR_STATE, "model has covariates but ude_set_covariates has not been called");
+  if (D.loss_kind == UDE_LOSS_DERIV_MATCH && !h->have_targets) return fail(h, UDE_ERR_STATE, "derivative matching needs ude_set_targets");
+  // choose the kernel specialisation
+  const KernelEntry* best_g = nullptr; const KernelEntry* best_f = nullptr;
+  for (const KernelEntry& e : ude::kernel_registry()) {
+    if (e.rhs_kind != D.rhs_kind || e.d != D.d || e.n_cov != D.n_cov || e.nn_in != D.nn_in || e.nn_out != D.nn_out) continue;
+    if (e.solver != D.solver || e.G * e.HPL < D.nn_hidden) continue;
+    if (D.lanes_per_segment > 0 && e.G != D.lanes_per_segment) continue;
+    if (D.hidden_per_lane > 0 && e.HPL != D.hidden_per_lane) continue;
+    const KernelEntry*& slot = e.grad ? best_g : best_f;
+    auto key = [](const KernelEntry* k) { return (long long)k->G * k->HPL * 1000 + k->priority; };
+    if (!slot || key(&e) < key(slot)) slot = &e;
+  }
+  if (!best_g || !best_f) {
+    char buf[320];
+    snprintf(buf, sizeof buf, "no compiled sm_100a kernel for rhs_kind=%d d=%d n_cov=%d nn=%d->%d->%d solver=%d (G=%d HPL=%d); "
+             "add an instantiation in csrc/ude_inst_*.cu", D.rhs_kind, D.d, D.n_cov, D.nn_in, D.nn_hidden, D.nn_out, D.solver,
+             D.lanes_per_segment, D.hidden_per_lane);
+    return fail(h, UDE_ERR_UNSUPPORTED, buf);
+  }
+  h->k_grad = best_g; h->k_fwd = best_f;
+  const int G = best_g->G, SPW = 32 / G;
+  const int S = D.substeps, pre = (D.loss_kind == UDE_LOSS_MULTI_SHOOT && D.preroll_eps > 0.0) ? 1 : 0;
+
+  std::vector<Seg> segs;
+  segs.reserve((size_t)h->n_cols + 64);
+  int64_t steps = 0, max_steps = 0;
+  std::vector<int64_t> task_steps;
+  auto pad_model = [&]() {
+    while (segs.size() % SPW) { Seg z = segs.back(); z.flags |= ude::SEG_NULL; z.L = 0; segs.push_back(z); }
+  };
+  int64_t cur_model = -1;
+  for (int64_t s = 0; s < h->n_series; ++s) {
+    const int64_t m = h->model_of_series[s], c0 = h->starts[s], len = h->lengths[s];
+    if (m != cur_model) { if (!segs.empty()) pad_model(); cur_model = m; }
+    auto push = [&](int64_t col, int64_t L, uint16_t flags) {
+      Seg z; z.col = (int32_t)col; z.series = (int32_t)s; z.L = (int16_t)L; z.flags = flags; z.model = (int32_t)m;
+      segs.push_back(z);
+    };
+    switch (D.loss_kind) {
+      case UDE_LOSS_STATE_SPACE:
+        if (len == 1) push(c0, 0, ude::SEG_SKIP_PROC);
+        for (int64_t t = 1; t < len; ++t) {
+          uint16_t f = (t == 1) ? ude::SEG_OBS_FIRST : 0;
+          if (!h->skip.empty() && h->skip[c0 + t]) f |= ude::SEG_SKIP_PROC; else steps += S;
+          push(c0 + t, 1, f);
+        }
+        break;
+      case UDE_LOSS_MULTI_SHOOT:
+        for (int64_t t = 0; t < len; t += D.pred_length) {
+          const int64_t L = (len - 1 - t >= D.pred_length) ? D.pred_length : (len - 1 - t);
+          push(c0 + t, L, 0);
+          steps += pre + L * S;
+        }
+        break;
+      case UDE_LOSS_SHOOT:
+        if (len - 1 > 32767) return fail(h, UDE_ERR_INVALID, "shooting: series longer than 32768 points");
+        push(c0, len - 1, 0);
+        steps += (len - 1) * S;
+        break;
+      case UDE_LOSS_DERIV_MATCH:
+        for (int64_t t = D.remove_ends; t < len - D.remove_ends; ++t) push(c0 + t, 0, 0);
+        break;
+      default: return fail(h, UDE_ERR_INVALID, "unknown loss_kind");
+    }
+  }
+  if (segs.empty()) return fail(h, UDE_ERR_INVALID, "no segments (empty data)");
+  pad_model();
+  h->n_tasks = (int64_t)segs.size() / SPW;
+  for (int64_t t = 0; t < h->n_tasks; ++t) {
+    int64_t mx = 0;
+    for (int q = 0; q < SPW; ++q) {
+      const Seg& z = segs[t * SPW + q];
+      int64_t st = (D.loss_kind == UDE_LOSS_STATE_SPACE) ? S : (D.loss_kind == UDE_LOSS_DERIV_MATCH ? 0 : pre + (int64_t)z.L * S);
+      mx = std::max(mx, st);
+    }
+    max_steps = std::max(max_steps, mx);
+  }
+  h->steps_per_eval = steps;
+  h->max_steps_per_task = max_steps;
+  UDE_CUDA_TRY(h, h->d_segs.upload(segs.data(), segs.size(), h->stream));
+
+  // launch geometry: persistent grid, a multiple of the SM count
+  const int stages = D.solver == UDE_TSIT5 ? 6 : 4;
+  h->smem_bytes = (h->n_models == 1) ? (size_t)(D.n_pm + 1) * sizeof(double) : 0;
+  for (const KernelEntry* k : {h->k_grad, h->k_fwd}) {
+    if (h->smem_bytes > 40 * 1024)
+      UDE_CUDA_TRY(h, cudaFuncSetAttribute(k->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+  }
+  int occ_g = 0, occ_f = 0;
+  UDE_CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessorWithFlags(&occ_g, h->k_grad->fn, ude::kBlockThreads, h->smem_bytes, 0));
+  UDE_CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessorWithFlags(&occ_f, h->k_fwd->fn, ude::kBlockThreads, h->smem_bytes, 0));
+  if (occ_g < 1 || occ_f < 1) return fail(h, UDE_ERR_CUDA, "kernel does not fit on an SM");
+  const int wpb = ude::kBlockThreads / 32;
+  const int64_t need_blocks = (h->n_tasks + wpb - 1) / wpb;
+  const char* env_occ = getenv("UDE_MAX_BLOCKS_PER_SM");
+  if (env_occ && atoi(env_occ) > 0) { occ_g = std::min(occ_g, atoi(env_occ)); occ_f = std::min(occ_f, atoi(env_occ)); }
+  h->grid_grad = (int)std::min<int64_t>(need_blocks, (int64_t)occ_g * h->sm_count);
+  h->grid_fwd = (int)std::min<int64_t>(need_blocks, (int64_t)occ_f * h->sm_count);
+  h->stash_rows_per_warp = (long long)max_steps * stages * h->k_grad->rows_per_stage;
+  // the stash must fit: shrink the grid (whole multiples of the SM count) if a long shooting problem would not
+  size_t free_b = 0, total_b = 0;
+  UDE_CUDA_TRY(h, cudaMemGetInfo(&free_b, &total_b));
+  while (h->grid_grad > h->sm_count &&
+         (double)h->grid_grad * wpb * h->stash_rows_per_warp * 256.0 > 0.5 * (double)free_b)
+    h->grid_grad -= h->sm_count;
+  const size_t stash_doubles = (size_t)h->grid_grad * wpb * (size_t)h->stash_rows_per_warp * 32;
+  if ((double)stash_doubles * 8.0 > 0.8 * (double)free_b) return fail(h, UDE_ERR_CUDA, "reverse-sweep stash does not fit in device memory");
+  UDE_CUDA_TRY(h, h->d_stash.reserve(stash_doubles));
+  UDE_CUDA_TRY(h, h->d_block_part.reserve((size_t)std::max(h->grid_grad, h->grid_fwd) * (size_t)(D.n_pm + 1)));
+  UDE_CUDA_TRY(h, h->d_model_loss.reserve((size_t)h->n_models));
+  UDE_CUDA_TRY(h, h->d_red.reserve((size_t)D.n_pm + 1));
+  UDE_CUDA_TRY(h, cudaStreamSynchronize(h->stream));   // segs came from a local vector
+  h->dirty = false;
+  return UDE_OK;
+}
+
+DevProblem make_dev_problem(const ude_handle* h, const double* d_theta, double* d_grad, double* d_traj) {
+  const ude_desc& D = h->desc;
+  DevProblem P{};
+  P.d = D.d; P.n_cov = D.n_cov; P.nn_in = D.nn_in; P.H = D.nn_hidden; P.nn_out = D.nn_out; P.n_scalars = D.n_scalars;
+  P.has_series_param = D.has_series_param; P.substeps = D.substeps;
+  P.off_w1 = D.off_w1; P.off_b1 = D.off_b1; P.off_w2 = D.off_w2; P.off_b2 = D.off_b2;
+  for (int k = 0; k < 8; ++k) P.off_scalar[k] = D.off_scalar[k];
+  P.off_series_param = D.off_series_param; P.n_pm = D.n_pm;
+  P.time_scale = D.time_scale; P.time_shift = D.time_shift;
+  P.loss_kind = D.loss_kind; P.pred_length = D.pred_length; P.proc_inv_dt = D.proc_inv_dt;
+  P.shoot_from_theta = D.shoot_from_theta; P.shoot_first_scored = D.shoot_first_scored; P.remove_ends = D.remove_ends;
+  P.preroll_eps = D.preroll_eps;
+  const int d = D.d;
+  for (int a = 0; a < d; ++a)
+    for (int b = 0; b < d; ++b) {
+      P.A[a + d * b] = D.A[a + d * b]; P.Asym[a + d * b] = D.A[a + d * b] + D.A[b + d * a];
+      P.B[a + d * b] = D.B[a + d * b]; P.Bsym[a + d * b] = D.B[a + d * b] + D.B[b + d * a];
+    }
+  P.starts = h->d_starts.p; P.lengths = h->d_lengths.p; P.theta_base = h->d_theta_base.p;
+  P.model_col0 = h->d_model_col0.p; P.model_series0 = h->d_model_series0.p;
+  P.times = h->d_times.p; P.data = h->d_data.p;
+  P.obs_scale = h->d_obs_scale.p; P.proc_scale = h->d_proc_scale.p; P.shoot_weight = h->d_shoot_weight.p;
+  P.knot_off = h->d_knot_off.p; P.knot_t = h->d_knot_t.p; P.knot_x = h->d_knot_x.p; P.knot_inv = h->d_knot_inv.p;
+  P.dm_u = h->d_dm_u.p; P.dm_dudt = h->d_dm_dudt.p;
+  P.segs = h->d_segs.p; P.n_tasks = h->n_tasks; P.n_models = (int)h->n_models;
+  P.theta = d_theta; P.grad = d_grad; P.traj_out = d_traj;
+  P.block_part = h->d_block_part.p; P.model_loss = h->d_model_loss.p;
+  P.stash = h->d_stash.p; P.stash_rows_per_warp = h->stash_rows_per_warp;
+  return P;
+}
+
+// enqueue one loss(+grad) evaluation on `s`; all pointers are device pointers
+int enqueue_eval(ude_handle* h, const double* d_theta, double* d_loss, double* d_grad, double* d_traj, cudaStream_t s) {
+  if (h->dirty) { int rc = build_plan(h); if (rc != UDE_OK) return rc; }
+  const ude_desc& D = h->desc;
+  const bool want_grad = d_grad != nullptr;
+  const KernelEntry* k = want_grad ? h->k_grad : h->k_fwd;
+  const int grid = want_grad ? h->grid_grad : h->grid_fwd;
+  DevProblem P = make_dev_problem(h, d_theta, d_grad, d_traj);
+  if (want_grad) UDE_CUDA_TRY(h, cudaMemsetAsync(d_grad, 0, (size_t)h->n_theta * sizeof(double), s));
+  if (h->n_models > 1) UDE_CUDA_TRY(h, cudaMemsetAsync(h->d_model_loss.p, 0, (size_t)h->n_models * sizeof(double), s));
+  void* args[] = {&P};
+  UDE_CUDA_TRY(h, cudaLaunchKernel(k->fn, dim3(grid), dim3(ude::kBlockThreads), args, h->smem_bytes, s));
+  const long long n_w1 = (long long)D.nn_hidden * D.nn_in, n_w2 = (long long)D.nn_out * D.nn_hidden;
+  if (h->n_models == 1) {
+    const long long pmb = (long long)D.d * h->n_cols;
+    const long long slo = D.has_series_param ? D.off_series_param : -1, shi = D.has_series_param ? slo + h->n_series : -1;
+    const bool use_comm = h->comm != nullptr;
+    double* gp = use_comm ? h->d_red.p : (want_grad ? d_grad + pmb : h->d_red.p);
+    double* lp = use_comm ? h->d_red.p + D.n_pm : d_loss;
+    const int nb = (int)((D.n_pm + 1 + 31) / 32);
+    // rank r > 0 must not add the regulariser again: only rank 0 carries it (host passes reg_weight = 0 elsewhere)
+    ude_finalize_single<<<nb, dim3(32, 8), 0, s>>>(h->d_block_part.p, grid, D.n_pm, d_theta + pmb, D.off_w1, n_w1, D.off_w2, n_w2,
+                                                   slo, shi, h->d_reg_weight.p, gp, lp, 0);
+    UDE_CUDA_TRY(h, cudaGetLastError());
+    if (use_comm) {
+      int rc = g_nccl.AllReduce(h->d_red.p, h->d_red.p, (size_t)D.n_pm + 1, /*ncclFloat64*/ 8, /*ncclSum*/ 0, h->comm, s);
+      if (rc != 0) return fail(h, UDE_ERR_NCCL, std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
+      const int nb2 = (int)((D.n_pm + 1 + 255) / 256);
+      ude_scatter_reduced<<<nb2, 256, 0, s>>>(h->d_red.p, D.n_pm, slo, shi, want_grad ? d_grad + pmb : h->d_red.p, d_loss);
+      UDE_CUDA_TRY(h, cudaGetLastError());
+    }
+  } else {
+    ude_finalize_multi<<<(int)h->n_models, 128, 0, s>>>(d_theta, d_grad, h->d_model_loss.p, h->d_theta_base.p, h->d_model_col0.p, D.d,
+                                                        D.off_w1, n_w1, D.off_w2, n_w2, h->d_reg_weight.p, d_loss);
+    UDE_CUDA_TRY(h, cudaGetLastError());
+  }
+  return UDE_OK;
+}
+
+}  // namespace
+
+// ==================================================================================================================
+#pragma GCC visibility push(default)
+extern "C" {
+
+int ude_abi_version(void) { return UDE_ABI_VERSION; }
+
+int ude_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+const char* ude_last_error(const ude_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int ude_create(const ude_desc* desc, ude_handle** out) {
+  if (!desc || !out) return fail(nullptr, UDE_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (desc->abi_version != UDE_ABI_VERSION || desc->struct_bytes != (int32_t)sizeof(ude_desc))
+    return fail(nullptr, UDE_ERR_INVALID, "ude_desc ABI mismatch (abi_version / struct_bytes)");
+  if (desc->d < 1 || desc->d > UDE_MAX_D || desc->nn_out < 1 || desc->nn_out > UDE_MAX_D || desc->nn_hidden < 1 ||
+      desc->substeps < 1 || desc->n_scalars < 0 || desc->n_scalars > UDE_MAX_SCALARS || desc->n_cov < 0)
+    return fail(nullptr, UDE_ERR_INVALID, "bad model dimensions");
+  if (desc->dtype != UDE_F64) return fail(nullptr, UDE_ERR_UNSUPPORTED, "only UDE_F64 is compiled in this build");
+  if (desc->solver != UDE_RK4 && desc->solver != UDE_TSIT5) return fail(nullptr, UDE_ERR_INVALID, "bad solver");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return fail(nullptr, UDE_ERR_NO_DEVICE, std::string("no CUDA device (libude_cuda has no CPU fallback): ") + cudaGetErrorString(e));
+  }
+  if (desc->device < 0 || desc->device >= n) return fail(nullptr, UDE_ERR_INVALID, "device ordinal out of range");
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, desc->device)) != cudaSuccess) return fail(nullptr, UDE_ERR_CUDA, cudaGetErrorString(e));
+  if (prop.major != 10) {
+    char buf[160];
+    snprintf(buf, sizeof buf, "device %d is sm_%d%d; libude_cuda is built for sm_100a only", desc->device, prop.major, prop.minor);
+    return fail(nullptr, UDE_ERR_NO_DEVICE, buf);
+  }
+  ude_handle* h = new ude_handle();
+  h->desc = *desc; h->device = desc->device; h->sm_count = prop.multiProcessorCount;
+  if ((e = cudaSetDevice(h->device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+    std::string m = cudaGetErrorString(e); delete h; return fail(nullptr, UDE_ERR_CUDA, m);
+  }
+  *out = h;
+  return UDE_OK;
+}
+
+int ude_destroy(ude_handle* h) {
+  if (!h) return UDE_OK;
+  cudaSetDevice(h->device);
+  if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+  delete h;
+  return UDE_OK;
+}
+
+int ude_set_data(ude_handle* h, int64_t n_series, const int64_t* starts, const int64_t* lengths, const int64_t* model_of_series,
+                 int64_t n_cols, const double* times, const double* data) {
+  if (!h) return UDE_ERR_INVALID;
+  if (n_series < 1 || n_cols < 1 || !starts || !lengths || !times || !data) return fail(h, UDE_ERR_INVALID, "empty or null data");
+  if (n_cols > 2000000000LL) return fail(h, UDE_ERR_INVALID, "more than 2^31 columns per handle: shard the series");
+  UDE_CUDA_TRY(h, cudaSetDevice(h->device));
+  const int d = h->desc.d;
+  h->starts.assign(starts, starts + n_series);
+  h->lengths.assign(lengths, lengths + n_series);
+  h->model_of_series.assign(n_series, 0);
+  if (model_of_series) h->model_of_series.assign(model_of_series, model_of_series + n_series);
+  int64_t expect = 0;
+  for (int64_t s = 0; s < n_series; ++s) {
+    if (starts[s] != expect || lengths[s] < 1) return fail(h, UDE_ERR_INVALID, "series must tile the columns contiguously, each with >= 1 point");
+    expect += lengths[s];
+    const int64_t m = h->model_of_series[s], prev = s ? h->model_of_series[s - 1] : 0;
+    if ((s == 0 && m != 0) || m < prev || m > prev + 1) return fail(h, UDE_ERR_INVALID, "model_of_series must be sorted, dense, 0-based");
+  }
+  if (expect != n_cols) return fail(h, UDE_ERR_INVALID, "sum(lengths) != n_cols");
+  const int64_t M = h->model_of_series.back() + 1;
+  h->n_series = n_series; h->n_cols = n_cols; h->n_models = M;
+  h->model_col0.assign(M + 1, 0); h->model_series0.assign(M + 1, 0); h->theta_base.assign(M, 0);
+  for (int64_t s = n_series - 1; s >= 0; --s) { h->model_col0[h->model_of_series[s]] = starts[s]; h->model_series0[h->model_of_series[s]] = s; }
+  h->model_col0[M] = n_cols; h->model_series0[M] = n_series;
+  int64_t off = 0;
+  for (int64_t m = 0; m < M; ++m) { h->theta_base[m] = off; off += (int64_t)d * (h->model_col0[m + 1] - h->model_col0[m]) + h->desc.n_pm; }
+  h->n_theta = off;
+  if (h->desc.has_series_param) {
+    for (int64_t m = 0; m < M; ++m)
+      if (h->desc.off_series_param + (h->model_series0[m + 1] - h->model_series0[m]) > h->desc.n_pm)
+        return fail(h, UDE_ERR_INVALID, "per-series parameter vector does not fit inside process_model");
+  }
+  cudaStream_t s = h->stream;
+  UDE_CUDA_TRY(h, h->d_starts.upload((const long long*)h->starts.data(), n_series, s));
+  UDE_CUDA_TRY(h, h->d_lengths.upload((const long long*)h->lengths.data(), n_series, s));
+  UDE_CUDA_TRY(h, h->d_theta_base.upload((const long long*)h->theta_base.data(), M, s));
+  UDE_CUDA_TRY(h, h->d_model_col0.upload((const long long*)h->model_col0.data(), M + 1, s));
+  UDE_CUDA_TRY(h, h->d_model_series0.upload((const long long*)h->model_series0.data(), M + 1, s));
+  UDE_CUDA_TRY(h, h->d_times.upload(times, n_cols, s));
+  UDE_CUDA_TRY(h, h->d_data.upload(data, (size_t)d * n_cols, s));
+  UDE_CUDA_TRY(h, h->d_theta.reserve((size_t)h->n_theta));
+  UDE_CUDA_TRY(h, h->d_grad.reserve((size_t)h->n_theta));
+  UDE_CUDA_TRY(h, h->d_loss.reserve((size_t)M));
+  h->have_data = true; h->dirty = true;
+  h->skip.clear();
+  int rc = ude_set_model_weights(h, nullptr, nullptr, nullptr, nullptr);
+  if (rc != UDE_OK) return rc;
+  UDE_CUDA_TRY(h, cudaStreamSynchronize(s));
+  return UDE_OK;
+}
+
+int ude_set_model_weights(ude_handle* h, const double* obs_scale, const double* proc_scale, const double* shoot_weight,
+                          const double* reg_weight) {
+  if (!h) return UDE_ERR_INVALID;
+  if (!h->have_data) return fail(h, UDE_ERR_STATE, "ude_set_data first");
+  UDE_CUDA_TRY(h, cudaSetDevice(h->device));
+  const size_t M = (size_t)h->n_models;
+  auto fill = [&](std::vector<double>& v, const double* src, double dflt) { v.assign(M, dflt); if (src) v.assign(src, src + M); };
+  fill(h->obs_scale, obs_scale, 1.0); fill(h->proc_scale, proc_scale, 1.0);
+  fill(h->shoot_weight, shoot_weight, 1.0); fill(h->reg_weight, reg_weight, 0.0);
+  UDE_CUDA_TRY(h, h->d_obs_scale.upload(h->obs_scale.data(), M, h->stream));
+  UDE_CUDA_TRY(h, h->d_proc_scale.upload(h->proc_scale.data(), M, h->stream));
+  UDE_CUDA_TRY(h, h->d_shoot_weight.upload(h->shoot_weight.data(), M, h->stream));
+  UDE_CUDA_TRY(h, h->d_reg_weight.upload(h->reg_weight.data(), M, h->stream));
+  UDE_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return UDE_OK;
+}
+
+int ude_set_covariates(ude_handle* h, const int64_t* knot_off, const double* knot_t, const double* knot_x) {
+  if (!h) return UDE_ERR_INVALID;
+  if (!h->have_data) return fail(h, UDE_ERR_STATE, "ude_set_data first");
+  if (h->desc.n_cov < 1) return fail(h, UDE_ERR_INVALID, "model has no covariates");
+  if (!knot_off || !knot_t || !knot_x) return fail(h, UDE_ERR_INVALID, "null covariate arrays");
+  UDE_CUDA_TRY(h, cudaSetDevice(h->device));
+  const size_t n_off = (size_t)h->n_series * h->desc.n_cov + 1;
+  const size_t nk = (size_t)knot_off[n_off - 1];
+  std::vector<double> inv(nk ? nk : 1, 0.0);
+  for (size_t i = 0; i + 1 < n_off; ++i) {
+    if (knot_off[i + 1] < knot_off[i]) return fail(h, UDE_ERR_INVALID, "knot_off must be non-decreasing");
+    for (int64_t k = knot_off[i]; k + 1 < knot_off[i + 1]; ++k) {
+      const double dt = knot_t[k + 1] - knot_t[k];
+      if (!(dt > 0.0)) return fail(h, UDE_ERR_INVALID, "covariate knot times must be strictly increasing");
+      inv[k] = 1.0 / dt;
+    }
+  }
+  UDE_CUDA_TRY(h, h->d_knot_off.upload((const long long*)knot_off, n_off, h->stream));
+  UDE_CUDA_TRY(h, h->d_knot_t.upload(knot_t, nk, h->stream));
+  UDE_CUDA_TRY(h, h->d_knot_x.upload(knot_x, nk, h->stream));
+  UDE_CUDA_TRY(h, h->d_knot_inv.upload(inv.data(), nk, h->stream));
+  UDE_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  h->have_cov = true;
+  return UDE_OK;
+}
+
+int ude_set_targets(ude_handle* h, const double* smoothed_states, const double* dudt) {
+  if (!h) return UDE_ERR_INVALID;
+  if (!h->have_data) return fail(h, UDE_ERR_STATE, "ude_set_data first");
+  if (!smoothed_states || !dudt) return fail(h, UDE_ERR_INVALID, "null targets");
+  UDE_CUDA_TRY(h, cudaSetDevice(h->device));
+  const size_t n = (size_t)h->desc.d * h->n_cols;
+  UDE_CUDA_TRY(h, h->d_dm_u.upload(smoothed_states, n, h->stream));
+  UDE_CUDA_TRY(h, h->d_dm_dudt.upload(dudt, n, h->stream));
+  UDE_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  h->have_targets = true;
+  return UDE_OK;
+}
+
+int ude_set_skip(ude_handle* h, const uint8_t* skip_mask) {
+  if (!h) return UDE_ERR_INVALID;
+  if (!h->have_data) return fail(h, UDE_ERR_STATE, "ude_set_data first");
+  if (skip_mask) h->skip.assign(skip_mask, skip_mask + h->n_cols); else h->skip.clear();
+  h->dirty = true;
+  return UDE_OK;
+}
+
+int64_t ude_n_theta(const ude_handle* h) { return h ? h->n_theta : 0; }
+int64_t ude_n_models(const ude_handle* h) { return h ? h->n_models : 0; }
+int64_t ude_steps_per_eval(const ude_handle* h) {
+  if (!h) return 0;
+  if (h->dirty && build_plan(const_cast<ude_handle*>(h)) != UDE_OK) return -1;
+  return h->steps_per_eval;
+}
+int32_t ude_launches_per_eval(const ude_handle* h) {
+  if (!h) return 0;
+  return (h->n_models == 1) ? (h->comm ? 3 : 2) : 2;     // segment kernel + finalize (+ scatter after the allreduce)
+}
+
+int ude_loss_grad_device(ude_handle* h, const double* d_theta, double* d_loss, double* d_grad, void* stream) {
+  if (!h) return UDE_ERR_INVALID;
+  if (!d_theta || !d_loss) return fail(h, UDE_ERR_INVALID, "null device pointer");
+  UDE_CUDA_TRY(h, cudaSetDevice(h->device));
+  return enqueue_eval(h, d_theta, d_loss, d_grad, nullptr, stream ? (cudaStream_t)stream : h->stream);
+}
+
+int ude_loss_grad(ude_handle* h, const double* theta, int64_t n_theta, double* loss, double* grad) {
+  if (!h) return UDE_ERR_INVALID;
+  if (!theta || !loss) return fail(h, UDE_ERR_INVALID, "null argument");
+  if (!h->have_data) return fail(h, UDE_ERR_STATE, "ude_set_data has not been called");
+  if (n_theta != h->n_theta) {
+    char buf[128]; snprintf(buf, sizeof buf, "n_theta = %lld, expected %lld", (long long)n_theta, (long long)h->n_theta);
+    return fail(h, UDE_ERR_INVALID, buf);
+  }
+  UDE_CUDA_TRY(h, cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  UDE_CUDA_TRY(h, cudaMemcpyAsync(h->d_theta.p, theta, (size_t)n_theta * sizeof(double), cudaMemcpyHostToDevice, s));
+  int rc = enqueue_eval(h, h->d_theta.p, h->d_loss.p, grad ? h->d_grad.p : nullptr, nullptr, s);
+  if (rc != UDE_OK) return rc;
+  UDE_CUDA_TRY(h, cudaMemcpyAsync(loss, h->d_loss.p, (size_t)h->n_models * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (grad) UDE_CUDA_TRY(h, cudaMemcpyAsync(grad, h->d_grad.p, (size_t)n_theta * sizeof(double), cudaMemcpyDeviceToHost, s));
+  UDE_CUDA_TRY(h, cudaStreamSynchronize(s));
+  for (int64_t m = 0; m < h->n_models; ++m)
+    if (!std::isfinite(loss[m])) return fail(h, UDE_NONFINITE, "loss is not finite (diverged trajectory?)");
+  return UDE_OK;
+}
+
+int ude_forward(ude_handle* h, const double* theta, int64_t n_theta, double* out) {
+  if (!h) return UDE_ERR_INVALID;
+  if (!theta || !out) return fail(h, UDE_ERR_INVALID, "null argument");
+  if (!h->have_data) return fail(h, UDE_ERR_STATE, "ude_set_data has not been called");
+  if (n_theta != h->n_theta) return fail(h, UDE_ERR_INVALID, "n_theta mismatch");
+  if (h->desc.loss_kind == UDE_LOSS_DERIV_MATCH) return fail(h, UDE_ERR_INVALID, "derivative matching has no trajectories");
+  UDE_CUDA_TRY(h, cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  const size_t n = (size_t)h->desc.d * h->n_cols;
+  UDE_CUDA_TRY(h, h->d_traj.reserve(n));
+  UDE_CUDA_TRY(h, cudaMemsetAsync(h->d_traj.p, 0, n * sizeof(double), s));
+  UDE_CUDA_TRY(h, cudaMemcpyAsync(h->d_theta.p, theta, (size_t)n_theta * sizeof(double), cudaMemcpyHostToDevice, s));
+  int rc = enqueue_eval(h, h->d_theta.p, h->d_loss.p, nullptr, h->d_traj.p, s);
+  if (rc != UDE_OK) return rc;
+  UDE_CUDA_TRY(h, cudaMemcpyAsync(out, h->d_traj.p, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+  UDE_CUDA_TRY(h, cudaStreamSynchronize(s));
+  return UDE_OK;
+}
+
+int ude_comm_unique_id(void* id_bytes, int32_t n_bytes) {
+  std::string err;
+  if (!id_bytes || n_bytes < 128) return fail(nullptr, UDE_ERR_INVALID, "id buffer must hold 128 bytes");
+  if (!nccl_load(err)) return fail(nullptr, UDE_ERR_NCCL, err);
+  Id128 id; memset(&id, 0, sizeof id);
+  int rc = g_nccl.GetUniqueId(&id);
+  if (rc != 0) return fail(nullptr, UDE_ERR_NCCL, "ncclGetUniqueId failed");
+  memcpy(id_bytes, &id, 128);
+  return UDE_OK;
+}
+
+int ude_comm_init(ude_handle* h, const void* id_bytes, int32_t n_bytes, int32_t n_ranks, int32_t rank) {
+  if (!h) return UDE_ERR_INVALID;
+  if (!id_bytes || n_bytes < 128 || n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(h, UDE_ERR_INVALID, "bad communicator arguments");
+  if (n_ranks == 1) { h->n_ranks = 1; h->rank = 0; return UDE_OK; }
+  std::string err;
+  if (!nccl_load(err)) return fail(h, UDE_ERR_NCCL, err);
+  UDE_CUDA_TRY(h, cudaSetDevice(h->device));
+  Id128 id; memcpy(&id, id_bytes, 128);
+  int rc = g_nccl.CommInitRank(&h->comm, n_ranks, id, rank);
+  if (rc != 0) return fail(h, UDE_ERR_NCCL, std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
+  h->n_ranks = n_ranks; h->rank = rank;
+  return UDE_OK;
+}
+
+int ude_adam(ude_handle* h, double* theta, int64_t n_theta, double step_size, int32_t n_iter, double* loss_trace) {
+  if (!h) return UDE_ERR_INVALID;
+  if (!theta || n_iter < 0) return fail(h, UDE_ERR_INVALID, "bad argument");
+  if (!h->have_data) return fail(h, UDE_ERR_STATE, "ude_set_data has not been called");
+  if (n_theta != h->n_theta) return fail(h, UDE_ERR_INVALID, "n_theta mismatch");
+  UDE_CUDA_TRY(h, cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  const size_t n = (size_t)n_theta, M = (size_t)h->n_models;
+  UDE_CUDA_TRY(h, h->d_adam_m.reserve(n));
+  UDE_CUDA_TRY(h, h->d_adam_v.reserve(n));
+  UDE_CUDA_TRY(h, cudaMemsetAsync(h->d_adam_m.p, 0, n * sizeof(double), s));
+  UDE_CUDA_TRY(h, cudaMemsetAsync(h->d_adam_v.p, 0, n * sizeof(double), s));
+  DevBuf<double> d_trace;
+  UDE_CUDA_TRY(h, d_trace.reserve(M * (size_t)std::max(n_iter, 1)));
+  UDE_CUDA_TRY(h, cudaMemcpyAsync(h->d_theta.p, theta, n * sizeof(double), cudaMemcpyHostToDevice, s));
+  double b1t = 1.0, b2t = 1.0;
+  const int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)h->sm_count * 8);
+  for (int it = 0; it < n_iter; ++it) {
+    int rc = enqueue_eval(h, h->d_theta.p, d_trace.p + (size_t)it * M, h->d_grad.p, nullptr, s);
+    if (rc != UDE_OK) return rc;
+    b1t *= 0.9; b2t *= 0.999;
+    ude_adam_update<<<blocks, 256, 0, s>>>(h->d_theta.p, h->d_adam_m.p, h->d_adam_v.p, h->d_grad.p, (long long)n, step_size, 1.0 - b1t, 1.0 - b2t);
+    UDE_CUDA_TRY(h, cudaGetLastError());
+  }
+  UDE_CUDA_TRY(h, cudaMemcpyAsync(theta, h->d_theta.p, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (loss_trace && n_iter > 0) UDE_CUDA_TRY(h, cudaMemcpyAsync(loss_trace, d_trace.p, M * (size_t)n_iter * sizeof(double), cudaMemcpyDeviceToHost, s));
+  UDE_CUDA_TRY(h, cudaStreamSynchronize(s));
+  return UDE_OK;
+}
+
+int ude_measure_fp64_peak(int32_t device, double* tflops) {
+  if (!tflops) return UDE_ERR_INVALID;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) { cudaGetLastError(); return fail(nullptr, UDE_ERR_NO_DEVICE, "no such CUDA device"); }
+  cudaError_t e;
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return fail(nullptr, UDE_ERR_CUDA, cudaGetErrorString(e));
+  cudaDeviceProp prop; cudaGetDeviceProperties(&prop, device);
+  double* d_out = nullptr; cudaMalloc((void**)&d_out, 64);
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 14;
+  float best = 1e30f;
+  for (int r = 0; r < 6; ++r) {
+    cudaEventRecord(e0);
+    ude_dfma_peak<<<blocks, threads>>>(d_out, iters, 1.0000001, 1e-9);
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+    if (r > 0 && ms < best) best = ms;
+  }
+  e = cudaGetLastError();
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d_out);
+  if (e != cudaSuccess) return fail(nullptr, UDE_ERR_CUDA, cudaGetErrorString(e));
+  *tflops = 2.0 * 8 * (double)iters * blocks * threads / (best * 1e-3) * 1e-12;
+  return UDE_OK;
+}
+
+}  // extern "C"
+#pragma GCC visibility pop

@@ -1,0 +1,151 @@
+// Device-side problem description, segment table entry, RK tableaux and sub-warp group collectives.
+//
+// Layout in HBM (DESIGN.md "Data layout"):
+//   times[n_cols], data[d x n_cols] column-major, theta = concat_m [uhat_m | pm_m], grad same shape,
+//   covariate knots CSR (knot_off, knot_t, knot_x, knot_inv = 1/(t[i+1]-t[i])),
+//   segs[n_tasks * SPW]: 16-byte work items sorted by (model, series, time), padded per model so that one
+//   warp-task (SPW = 32/G consecutive segments) never mixes models,
+//   stash[total_warps][rows][32]: per-warp scratch for the reverse sweep, one 256-byte row = one double per lane.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace ude {
+
+constexpr int kMaxD = 8;
+constexpr int kBlockThreads = 128;
+
+enum : uint16_t { SEG_NULL = 1, SEG_OBS_FIRST = 2, SEG_SKIP_PROC = 4 };
+
+struct Seg {
+  int32_t col;      // STATE_SPACE: END column of the interval; otherwise first column of the block
+  int32_t series;   // global series index
+  int16_t L;        // intervals in the block (trajectory kinds)
+  uint16_t flags;
+  int32_t model;
+};
+static_assert(sizeof(Seg) == 16, "Seg must stay 16 bytes");
+
+struct DevProblem {
+  // model
+  int d, n_cov, nn_in, H, nn_out, n_scalars, has_series_param, substeps;
+  long long off_w1, off_b1, off_w2, off_b2, off_scalar[8], off_series_param, n_pm;
+  double time_scale, time_shift;
+  // loss
+  int loss_kind, pred_length, proc_inv_dt, shoot_from_theta, shoot_first_scored, remove_ends;
+  double preroll_eps;
+  double A[kMaxD * kMaxD], Asym[kMaxD * kMaxD], B[kMaxD * kMaxD], Bsym[kMaxD * kMaxD];
+  // data (device pointers)
+  const long long* starts; const long long* lengths;
+  const long long* theta_base; const long long* model_col0; const long long* model_series0;
+  const double* times; const double* data;
+  const double* obs_scale; const double* proc_scale; const double* shoot_weight;
+  const long long* knot_off; const double* knot_t; const double* knot_x; const double* knot_inv;
+  const double* dm_u; const double* dm_dudt;
+  // work
+  const Seg* segs; long long n_tasks; int n_models;
+  // io
+  const double* theta; double* grad; double* traj_out;
+  double* block_part;   // [grid][n_pm + 1]: per-block gradient of process_model and loss (n_models == 1)
+  double* model_loss;   // [n_models], atomics                                       (n_models  > 1)
+  double* stash; long long stash_rows_per_warp;
+};
+
+// ------------------------------------------------------------------------------------------------
+// Butcher tableaux as constexpr functions so zero coefficients vanish at compile time.
+template <int SOLVER> struct Tab;
+template <> struct Tab<0> {   // classic RK4
+  static constexpr int S = 4;
+  __host__ __device__ static constexpr double c(int i) { constexpr double v[4] = {0.0, 0.5, 0.5, 1.0}; return v[i]; }
+  __host__ __device__ static constexpr double b(int i) { constexpr double v[4] = {1.0 / 6.0, 1.0 / 3.0, 1.0 / 3.0, 1.0 / 6.0}; return v[i]; }
+  __host__ __device__ static constexpr double a(int i, int j) {
+    constexpr double v[4][4] = {{0, 0, 0, 0}, {0.5, 0, 0, 0}, {0, 0.5, 0, 0}, {0, 0, 1.0, 0}};
+    return v[i][j];
+  }
+};
+template <> struct Tab<1> {   // Tsit5 stages 1..6 (OrdinaryDiffEq Tsit5ConstantCache; b = row 7 of a, b7 = 0)
+  static constexpr int S = 6;
+  __host__ __device__ static constexpr double c(int i) {
+    constexpr double v[6] = {0.0, 0.161, 0.327, 0.9, 0.9800255409045097, 1.0}; return v[i];
+  }
+  __host__ __device__ static constexpr double b(int i) {
+    constexpr double v[6] = {0.09646076681806523, 0.01, 0.4798896504144996, 1.379008574103742, -3.290069515436081, 2.324710524099774};
+    return v[i];
+  }
+  __host__ __device__ static constexpr double a(int i, int j) {
+    constexpr double v[6][6] = {
+        {0, 0, 0, 0, 0, 0},
+        {0.161, 0, 0, 0, 0, 0},
+        {-0.008480655492356989, 0.335480655492357, 0, 0, 0, 0},
+        {2.8971530571054935, -6.359448489975075, 4.3622954328695815, 0, 0, 0},
+        {5.325864828439257, -11.748883564062828, 7.4955393428898365, -0.09249506636175525, 0, 0},
+        {5.86145544294642, -12.92096931784711, 8.159367898576159, -0.071584973281401, -0.028269050394068383, 0}};
+    return v[i][j];
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// All-reduce of N doubles over the G lanes of a sub-warp group (G a power of two, groups aligned).
+// Reduce-scatter (halving the payload each butterfly step) followed by an all-gather: for N = 4, G = 16
+// this is 8 double shuffles instead of the 16 of a per-value butterfly.  SHFL issues at 1 warp-instruction
+// per clock per SM on B200 (profiles/microbench_r01.json), i.e. one double shuffle costs as much pipe
+// time as four DFMAs, so shuffle count is what this routine minimises.  Every lane of the warp must call
+// it (full mask); all lanes of a group end with bit-identical sums.
+__host__ __device__ constexpr int next_pow2(int n) { int p = 1; while (p < n) p <<= 1; return p; }
+__host__ __device__ constexpr int ilog2(int n) { int l = 0; while (n > 1) { n >>= 1; ++l; } return l; }
+
+template <int G, int N>
+__device__ __forceinline__ void group_allreduce(double (&v)[N], int lane) {
+  if constexpr (G == 1) { return; }
+  else {
+    constexpr int NP = next_pow2(N);
+    double w[NP];
+#pragma unroll
+    for (int i = 0; i < NP; ++i) w[i] = (i < N) ? v[i] : 0.0;
+    // reduce-scatter
+    int cnt = NP;
+#pragma unroll
+    for (int off = G / 2; off >= 1; off >>= 1) {
+      if (cnt > 1) {
+        const int half = cnt / 2;
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < NP / 2; ++i) {
+          if (i < half) {
+            double send = up ? w[i] : w[i + half];
+            double keep = up ? w[i + half] : w[i];
+            w[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+          }
+        }
+        cnt = half;
+      } else {
+        w[0] += __shfl_xor_sync(0xffffffffu, w[0], off);
+      }
+    }
+    // all-gather: undo the splits in reverse order.  Splits happened at off = G/2, G/4, ... (ns of them).
+    constexpr int cnt_final = (NP / G) > 1 ? (NP / G) : 1;
+    constexpr int ns = ilog2(NP / cnt_final);
+    int c = cnt_final;
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
+      if (s < ns) {
+        const int off = G >> (ns - s);       // last split first
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < NP / 2; ++i) {
+          if (i < c) {
+            double recv = __shfl_xor_sync(0xffffffffu, w[i], off);
+            double lo = up ? recv : w[i];
+            double hi = up ? w[i] : recv;
+            w[i] = lo; w[i + c] = hi;
+          }
+        }
+        c *= 2;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = w[i];
+  }
+}
+
+}  // namespace ude

@@ -67,6 +67,45 @@ __device__ __forceinline__ double ude_tanh(double x) {
   return copysign(y, x);
 }
 
+// 2^(j/64) table (512 B).  Kernels copy it to shared memory once per block; the lookup is one LDS on the
+// otherwise idle LSU pipe and shortens the exp polynomial from degree 13 to 5, i.e. ~19 FP64-pipe
+// instructions per tanh instead of ~33 (measured: tools/microbench.cu, profiles/microbench_r01.json).
+__constant__ double c_ude_exp2_tab[64] = {
+#include "ude_exp2_table.inc"
+};
+
+__device__ __forceinline__ void ude_load_exp2_tab(double* s_tab /* shared, 64 doubles */) {
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) s_tab[i] = c_ude_exp2_tab[i];
+}
+
+// tanh via E = expm1(2|x|) = 2^n T_j (1 + p(r)) - 1 with 2|x| = (64 n + j) ln2/64 + r, |r| <= ln2/128.
+// |error| <= ~1.5e-16 absolute everywhere (relative ~1e-16 except for |x| in [0.003, 0.3] where E = T(1+p)-1
+// cancels mildly: still <= 2^-52 absolute).  Branch-free; the clamp to |x| <= 20 is done on the high word
+// in the integer pipe.
+__device__ __forceinline__ double ude_tanh_tab(double x, const double* __restrict__ s_tab) {
+  const double INV   = 184.6649652337873;              // 128 / ln 2
+  const double C_HI  = 0x1.62e42fee00000p-7;           // (ln 2)/64, high part (21 trailing zero bits)
+  const double C_LO  = 0x1.a39ef35793c76p-39;
+  const double SHIFT = 6755399441055744.0;
+  int hi = __double2hiint(x) & 0x7fffffff;
+  hi = min(hi, 0x40340000);                            // |x| <= 20 (+ < 2e-6 when the low word is kept)
+  double ax = __hiloint2double(hi, __double2loint(x));
+  double kf = fma(ax, INV, SHIFT);
+  int N = __double2loint(kf);
+  kf -= SHIFT;
+  double r = fma(kf, -C_HI, ax + ax);
+  r = fma(kf, -C_LO, r);
+  double q = fma(r, 8.333333333333333e-03, 4.1666666666666664e-02);
+  q = fma(q, r, 1.6666666666666666e-01);
+  q = fma(q, r, 0.5);
+  double p = fma(q, r * r, r);                         // expm1(r)
+  double T = s_tab[N & 63];
+  double s = __hiloint2double(__double2hiint(T) + ((N >> 6) << 20), __double2loint(T));   // 2^n T_j
+  double em1 = fma(s, p, s - 1.0);
+  double y = ude_div(em1, em1 + 2.0);
+  return copysign(y, x);
+}
+
 // single-precision twin for the optional FP32 mode (1e-4 parity bar): hardware tanh is too coarse
 // (2^-11), so use the same E/(E+2) form with ex2.approx; ~1e-6 relative.
 __device__ __forceinline__ float ude_tanhf(float x) {

@@ -1,0 +1,24 @@
+// Host-side registry of the compiled sm_100a specialisations of ude_seg_kernel.
+// Each ude_inst_*.cu translation unit registers its kernels at load time; ude_create picks one by
+// (rhs_kind, d, n_cov, nn_in, nn_out) and the smallest padded hidden width G*HPL >= nn_hidden.
+#pragma once
+#include <vector>
+
+namespace ude {
+
+struct KernelEntry {
+  int rhs_kind, d, n_cov, nn_in, nn_out;
+  int G, HPL, solver, grad;
+  int rows_per_stage;      // stash rows (256 B each) per RK stage
+  int priority;            // lower = preferred when several (G, HPL) fit
+  const void* fn;
+  const char* name;
+};
+
+std::vector<KernelEntry>& kernel_registry();
+
+struct RegisterKernels {
+  explicit RegisterKernels(void (*fn)()) { fn(); }
+};
+
+}  // namespace ude
