@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""bench.py -- RK trajectory-steps/sec (loss + adjoint gradient, FP64) of the UDE hot path on N B200s.
+
+Contract (driver): `python bench.py --gpus N --steps K --warmup W` (N > 1 under torchrun, one rank per GPU) prints ONE
+JSON line.  A "step" is one loss+gradient evaluation of the workload BASELINE.json's metric is quoted on: config C3,
+MultiNODE with one covariate, d = 4, hidden 32, 10^5 synthetic series x 30 points per GPU, multiple-shooting loss
+(pred_length 5), RK4 with 4 substeps per observation interval => 1.16e7 RK steps per evaluation per GPU.
+Weak scaling: every rank holds its own 10^5 series; the process-model gradient (+ loss) is sum-allreduced over
+NCCL by the library on the launching stream once per step.
+
+  value     : whole-job steps/s, theta and all inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e       : same metric through the public host-buffer C-ABI call (ude_loss_grad): pinned host theta -> H2D ->
+              kernels -> D2H(loss, grad) inside the timed region
+  roofline  : the segment kernel against the MEASURED FP64 FMA peak (ude_measure_fp64_peak, run live; MEASURED_PEAKS.json
+              has no FP64 entry) -- the path is FP64-issue bound, not HBM bound; HBM figures are added
+  cpu_baseline : the CPU oracle (a port: the Julia reference cannot run here) on a bounded sample, all host cores
+`--impl reference` times that CPU oracle alone (rank 0 only under torchrun).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "RK trajectory-steps/sec (loss+adjoint grad, FP64)"
+UNIT = "steps/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c3", choices=["c2", "c3", "c3mse", "c4", "c5"])
+    ap.add_argument("--series", type=int, default=0, help="series (c2/c3), members (c4) or segments (c5) PER GPU; 0 = BASELINE size")
+    ap.add_argument("--solver", default="rk4", choices=["rk4", "tsit5"])
+    ap.add_argument("--substeps", type=int, default=4)
+    ap.add_argument("--lanes", type=int, default=0)
+    ap.add_argument("--hpl", type=int, default=0)
+    ap.add_argument("--cpu-sample", type=int, default=0, help="series in the CPU-oracle sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def build_problem(ude, args, rank, n_override=None):
+    P = ude.problem
+    solver = P.RK4 if args.solver == "rk4" else P.TSIT5
+    seed = 1000 + rank
+    cfg = args.config
+    n = n_override if n_override else args.series
+    if cfg == "c2":
+        prob, th = ude.synthetic.config_c2(n_series=n or 10_000, seed=seed, solver=solver, substeps=args.substeps)
+        name = "C2 NODE d=2 H=10, multiple shooting pl=5, %d LV series x 60 pts" % prob.n_series
+    elif cfg in ("c3", "c3mse"):
+        prob, th = ude.synthetic.config_c3(n_series=n or 100_000, seed=seed, solver=solver, substeps=args.substeps,
+                                           loss="multiple shooting" if cfg == "c3" else "mse")
+        name = "C3 MultiNODE+1 covariate d=4 NN 5->32->4, %s, %d series x 30 pts per GPU" % (
+            "multiple shooting pl=5" if cfg == "c3" else "default MSE state-space loss", prob.n_series)
+    elif cfg == "c4":
+        prob, th = ude.synthetic.config_c4(n_members=n or 1000, seed=seed, solver=solver, substeps=args.substeps)
+        name = "C4 coral UDE d=3 NN 4->10->2, conditional likelihood, %d members x 10 LFO folds per GPU" % (prob.n_models // 10)
+    else:
+        prob, th = ude.synthetic.config_c5(n_segments=n or 1_000_000, seed=seed, solver=solver, substeps=args.substeps)
+        name = "C5 wide NODE d=8 H=128, %d one-interval segments per GPU" % prob.n_series
+    # every rank must start from the SAME process model (shared parameters): take rank 0's initialisation
+    if prob.n_models == 1:
+        pm0 = ude.synthetic.init_pm(prob, np.random.default_rng(4242))
+        prob.pm_view(th, 0)[:] = pm0
+    return prob, th, name
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_oracle_rate(ude, args, n_sample, threads, min_seconds=8.0, max_reps=50):
+    """steps/s of the CPU oracle (loss + adjoint gradient) on an n_sample-series instance of the same workload."""
+    from oracle import oracle
+    prob, th, _ = build_problem(ude, args, 0, n_override=n_sample)
+    steps = prob.count_steps()
+    oracle.loss_grad(prob, th, threads=threads)          # warm-up (page-in, thread pool)
+    t0 = time.perf_counter(); reps = 0
+    while True:
+        oracle.loss_grad(prob, th, threads=threads)
+        reps += 1
+        el = time.perf_counter() - t0
+        if el >= min_seconds or reps >= max_reps:
+            break
+    return steps * reps / el, prob, steps, reps, el
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path.  The reference is Julia and cannot run in this
+    image (no julia binary, no depot, no network), so this arm times the CPU oracle port with all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import ude_b200 as ude
+    from oracle import oracle
+    threads = oracle.max_threads()
+    # one "step" = one loss+grad of a bounded sample of the workload (sized for ~0.3 s of wall time per step)
+    n_sample = args.cpu_sample or {"c2": 1500, "c3": 600, "c3mse": 600, "c4": 4, "c5": 1500}[args.config]
+    prob, th, name = build_problem(ude, args, 0, n_override=n_sample)
+    steps = prob.count_steps()
+    for _ in range(args.warmup):
+        oracle.loss_grad(prob, th, threads=threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oracle.loss_grad(prob, th, threads=threads)
+    el = time.perf_counter() - t0
+    value = steps * args.steps / el
+    sample = f"{prob.n_series} series ({steps} RK steps) of the workload per step, oracle/libude_oracle.so, {threads} OpenMP threads"
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": name + " (bounded CPU sample)", "solver": args.solver, "substeps": args.substeps,
+                      "note": "Julia reference not runnable here (parity unpinned); CPU oracle port timed instead"},
+           "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+           "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    import torch
+    import ude_b200 as ude
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the CUDA library is the only implementation (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    prob, theta0, name = build_problem(ude, args, rank)
+    eng = ude.Engine(prob, device=local, lanes_per_segment=args.lanes, hidden_per_lane=args.hpl)
+    if world > 1:
+        idt = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(ude.get_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        eng.comm_init(bytes(idt.cpu().numpy().tobytes()), world, rank)
+        if rank != 0:   # the regulariser is a function of the shared parameters: count it once (rank 0)
+            prob.reg_weight[:] = 0.0
+            eng._check(eng.lib.ude_set_model_weights(eng.handle, prob.obs_scale.ctypes.data, prob.proc_scale.ctypes.data,
+                                                     prob.shoot_weight.ctypes.data, prob.reg_weight.ctypes.data))
+    steps_per_eval = eng.steps_per_eval()
+    n_theta = prob.n_theta
+
+    d_theta = torch.from_numpy(theta0).to(dev)
+    d_grad = torch.empty(n_theta, dtype=torch.float64, device=dev)
+    d_loss = torch.empty(prob.n_models, dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        eng.loss_grad_device(d_theta.data_ptr(), d_loss.data_ptr(), d_grad.data_ptr(), stream)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    fp64_peak = ude.measure_fp64_peak(local)
+
+    # ---- device-resident timing -------------------------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    clocks = ClockSampler(local)
+    clocks.start()
+    eng.profile_begin(args.steps)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    kern_ms = eng.profile_read(args.steps)
+    clk = clocks.stop()
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    value = steps_per_eval * world / (ms_step * 1e-3)
+    loss_val = float(d_loss.sum().item())
+
+    # ---- end-to-end through the public host-buffer call ----------------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        h_theta = torch.from_numpy(theta0).pin_memory()
+        h_grad = torch.empty(n_theta, dtype=torch.float64).pin_memory()
+        h_loss = torch.empty(prob.n_models, dtype=torch.float64).pin_memory()
+        for _ in range(3):
+            eng.loss_grad_ptr(h_theta.data_ptr(), n_theta, h_loss.data_ptr(), h_grad.data_ptr())
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            eng.loss_grad_ptr(h_theta.data_ptr(), n_theta, h_loss.data_ptr(), h_grad.data_ptr())
+        torch.cuda.synchronize()
+        el = time.perf_counter() - t0
+        te = torch.tensor([el], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        el = float(te.item())
+        e2e = {"value": steps_per_eval * world * args.steps / el, "unit": UNIT, "h2d_bytes_per_step": 8 * n_theta,
+               "d2h_bytes_per_step": 8 * (n_theta + prob.n_models), "ms_per_step": 1e3 * el / args.steps,
+               "api": "ude_loss_grad (host pinned theta in, loss+grad out)", "loss_check": float(h_loss.sum().item())}
+
+    # ---- CPU baseline (rank 0, N = 1 only) ------------------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle
+        threads = oracle.max_threads()
+        n_sample = args.cpu_sample or {"c2": 6000, "c3": 2500, "c3mse": 2500, "c4": 16, "c5": 6000}[args.config]
+        rate, sp, ssteps, reps, el = cpu_oracle_rate(ude, args, n_sample, threads)
+        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"{sp.n_series} series = {ssteps} RK steps per evaluation x {reps} evaluations in {el:.1f} s "
+                         f"(oracle/libude_oracle.so, OpenMP over series); Julia reference not runnable here"}
+
+    if rank == 0:
+        kms = float(np.mean(kern_ms)) if len(kern_ms) else None
+        flops_step = prob.flops_per_step()
+        achieved = steps_per_eval * flops_step / (kms * 1e-3) * 1e-12 if kms else None
+        traffic = None
+        tf = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tf):
+            try:
+                traffic = json.load(open(tf)).get(args.config)
+            except Exception:
+                traffic = None
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        hbm_bytes = prob.hbm_bytes_per_eval()
+        roofline = {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+                    "frac": (achieved / fp64_peak) if achieved else None, "traffic": traffic,
+                    "peak_source": "measured live: ude_measure_fp64_peak (DFMA chain, 8-way ILP, 64 warps/SM); vendor 37.2",
+                    "flops_per_step": flops_step, "kernel": eng_kernel_name(eng), "kernel_ms": kms,
+                    "kernel_share_of_step": (kms / ms_step) if kms else None,
+                    "hbm_algorithmic_bytes": hbm_bytes, "hbm_achieved_gbs": (hbm_bytes / (kms * 1e-3) * 1e-9) if kms else None,
+                    "hbm_peak_gbs": hbm_peak, "hbm_peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"}
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+               "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+               "data": "synthetic",
+               "config": {"workload": name, "solver": args.solver, "substeps": args.substeps,
+                          "rk_steps_per_eval_per_gpu": steps_per_eval, "segments_per_gpu": prob.count_segments(),
+                          "n_theta_per_gpu": n_theta, "loss_value": loss_val,
+                          "l2": "inputs+stash larger than L2 (theta, grad, data = %.0f MB per step)" % (3 * 8 * prob.d * prob.n_cols / 1e6),
+                          "parallelism": f"dp{world} by series, one NCCL allreduce of {prob.n_pm + 1} doubles per step" if world > 1 else "single GPU"},
+               "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+               "gpu_launches": eng.launches_per_eval() * args.steps, "clocks": clk}
+        print(json.dumps(out), flush=True)
+    eng.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def eng_kernel_name(eng):
+    return "ude_seg_kernel (fused RK forward + loss + discrete adjoint)"
+
+
+if __name__ == "__main__":
+    main()

@@ -144,6 +144,12 @@ int ude_comm_init(ude_handle* h, const void* id_bytes, int32_t n_bytes, int32_t 
  * loss_trace (n_iter doubles per model, may be NULL) receives the loss before each update. */
 int ude_adam(ude_handle* h, double* theta, int64_t n_theta, double step_size, int32_t n_iter, double* loss_trace);
 
+/* Kernel timing for roofline reports: after ude_profile_begin(h, n) the next n evaluations bracket the segment
+ * kernel (the dominant launch) with CUDA events on the launching stream; ude_profile_read synchronises and returns
+ * how many were recorded, writing their durations in milliseconds. */
+int ude_profile_begin(ude_handle* h, int32_t max_evals);
+int ude_profile_read(ude_handle* h, float* ms_out, int32_t capacity);
+
 /* Measured FP64 FMA throughput of the device (TFLOP/s): the roofline denominator bench.py reports against. */
 int ude_measure_fp64_peak(int32_t device, double* tflops);
 

@@ -27,7 +27,8 @@ UDE_NONFINITE = -7
 EXPORTS = ["ude_abi_version", "ude_device_count", "ude_create", "ude_destroy", "ude_last_error", "ude_set_data",
            "ude_set_model_weights", "ude_set_covariates", "ude_set_targets", "ude_set_skip", "ude_n_theta",
            "ude_n_models", "ude_steps_per_eval", "ude_launches_per_eval", "ude_loss_grad", "ude_loss_grad_device",
-           "ude_forward", "ude_comm_unique_id", "ude_comm_init", "ude_adam", "ude_measure_fp64_peak"]
+           "ude_forward", "ude_comm_unique_id", "ude_comm_init", "ude_adam", "ude_profile_begin", "ude_profile_read",
+           "ude_measure_fp64_peak"]
 
 
 class UdeDesc(C.Structure):
@@ -104,6 +105,10 @@ def load_library():
     lib.ude_comm_init.argtypes = [vp, vp, i32, i32, i32]
     lib.ude_adam.restype = C.c_int
     lib.ude_adam.argtypes = [vp, dp, i64, C.c_double, i32, dp]
+    lib.ude_profile_begin.restype = C.c_int
+    lib.ude_profile_begin.argtypes = [vp, i32]
+    lib.ude_profile_read.restype = C.c_int
+    lib.ude_profile_read.argtypes = [vp, dp, i32]
     lib.ude_measure_fp64_peak.restype = C.c_int
     lib.ude_measure_fp64_peak.argtypes = [i32, C.POINTER(C.c_double)]
     if lib.ude_abi_version() != ABI_VERSION:
@@ -264,6 +269,16 @@ class Engine:
         trace = np.zeros((max(n_iter, 1), self.problem.n_models))
         self._check(self.lib.ude_adam(self.handle, _ptr(theta), theta.shape[0], float(step_size), int(n_iter), _ptr(trace)))
         return theta, trace[:n_iter]
+
+    def profile_begin(self, max_evals: int):
+        self._check(self.lib.ude_profile_begin(self.handle, int(max_evals)))
+
+    def profile_read(self, capacity: int) -> np.ndarray:
+        out = np.zeros(max(capacity, 1), dtype=np.float32)
+        n = self.lib.ude_profile_read(self.handle, _ptr(out), int(capacity))
+        if n < 0:
+            self._check(n)
+        return out[:n].astype(np.float64)
 
     def comm_init(self, unique_id: bytes, n_ranks: int, rank: int):
         buf = C.create_string_buffer(unique_id, 128)

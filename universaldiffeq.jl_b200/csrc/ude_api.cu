@@ -108,6 +108,9 @@ struct ude_handle {
   // multi-GPU
   void* comm = nullptr;
   int n_ranks = 1, rank = 0;
+  // optional kernel timing (ude_profile_begin / ude_profile_read)
+  std::vector<cudaEvent_t> ev0, ev1;
+  int ev_used = 0, ev_cap = 0;
 };
 
 namespace {
@@ -377,7 +380,10 @@ int enqueue_eval(ude_handle* h, const double* d_theta, double* d_loss, double* d
   if (want_grad) UDE_CUDA_TRY(h, cudaMemsetAsync(d_grad, 0, (size_t)h->n_theta * sizeof(double), s));
   if (h->n_models > 1) UDE_CUDA_TRY(h, cudaMemsetAsync(h->d_model_loss.p, 0, (size_t)h->n_models * sizeof(double), s));
   void* args[] = {&P};
+  const bool timed = h->ev_used < h->ev_cap;
+  if (timed) UDE_CUDA_TRY(h, cudaEventRecord(h->ev0[h->ev_used], s));
   UDE_CUDA_TRY(h, cudaLaunchKernel(k->fn, dim3(grid), dim3(ude::kBlockThreads), args, h->smem_bytes, s));
+  if (timed) { UDE_CUDA_TRY(h, cudaEventRecord(h->ev1[h->ev_used], s)); ++h->ev_used; }
   const long long n_w1 = (long long)D.nn_hidden * D.nn_in, n_w2 = (long long)D.nn_out * D.nn_hidden;
   if (h->n_models == 1) {
     const long long pmb = (long long)D.d * h->n_cols;
@@ -459,6 +465,8 @@ int ude_destroy(ude_handle* h) {
   cudaSetDevice(h->device);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+  for (cudaEvent_t e : h->ev0) cudaEventDestroy(e);
+  for (cudaEvent_t e : h->ev1) cudaEventDestroy(e);
   delete h;
   return UDE_OK;
 }
@@ -690,6 +698,30 @@ int ude_adam(ude_handle* h, double* theta, int64_t n_theta, double step_size, in
   if (loss_trace && n_iter > 0) UDE_CUDA_TRY(h, cudaMemcpyAsync(loss_trace, d_trace.p, M * (size_t)n_iter * sizeof(double), cudaMemcpyDeviceToHost, s));
   UDE_CUDA_TRY(h, cudaStreamSynchronize(s));
   return UDE_OK;
+}
+
+int ude_profile_begin(ude_handle* h, int32_t max_evals) {
+  if (!h || max_evals < 0) return UDE_ERR_INVALID;
+  UDE_CUDA_TRY(h, cudaSetDevice(h->device));
+  while ((int)h->ev0.size() < max_evals) {
+    cudaEvent_t a, b;
+    UDE_CUDA_TRY(h, cudaEventCreate(&a)); UDE_CUDA_TRY(h, cudaEventCreate(&b));
+    h->ev0.push_back(a); h->ev1.push_back(b);
+  }
+  h->ev_used = 0; h->ev_cap = max_evals;
+  return UDE_OK;
+}
+
+int ude_profile_read(ude_handle* h, float* ms_out, int32_t capacity) {
+  if (!h || !ms_out) return UDE_ERR_INVALID;
+  UDE_CUDA_TRY(h, cudaSetDevice(h->device));
+  const int n = std::min(h->ev_used, (int)capacity);
+  for (int i = 0; i < n; ++i) {
+    UDE_CUDA_TRY(h, cudaEventSynchronize(h->ev1[i]));
+    UDE_CUDA_TRY(h, cudaEventElapsedTime(&ms_out[i], h->ev0[i], h->ev1[i]));
+  }
+  h->ev_cap = 0;
+  return n;
 }
 
 int ude_measure_fp64_peak(int32_t device, double* tflops) {
