@@ -215,7 +215,11 @@ def main():
     d_theta = torch.from_numpy(theta0).to(dev)
     d_grad = torch.empty(n_theta, dtype=torch.float64, device=dev)
     d_loss = torch.empty(prob.n_models, dtype=torch.float64, device=dev)
-    stream = torch.cuda.current_stream().cuda_stream
+    # a dedicated non-default stream: the C ABI treats a NULL stream as "the handle's own stream", and CUDA events
+    # only see the stream they are recorded on
+    tstream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
 
     def step():
         eng.loss_grad_device(d_theta.data_ptr(), d_loss.data_ptr(), d_grad.data_ptr(), stream)

@@ -227,7 +227,8 @@ int build_plan(ude_handle* h) {
   const KernelEntry* best_g = nullptr; const KernelEntry* best_f = nullptr;
   for (const KernelEntry& e : ude::kernel_registry()) {
     if (e.rhs_kind != D.rhs_kind || e.d != D.d || e.n_cov != D.n_cov || e.nn_in != D.nn_in || e.nn_out != D.nn_out) continue;
-    if (e.solver != D.solver || e.G * e.HPL < D.nn_hidden) continue;
+    const int lk = D.loss_kind == UDE_LOSS_STATE_SPACE ? 0 : (D.loss_kind == UDE_LOSS_DERIV_MATCH ? 2 : 1);
+    if (e.solver != D.solver || e.lk != lk || e.G * e.HPL < D.nn_hidden) continue;
     if (D.lanes_per_segment > 0 && e.G != D.lanes_per_segment) continue;
     if (D.hidden_per_lane > 0 && e.HPL != D.hidden_per_lane) continue;
     const KernelEntry*& slot = e.grad ? best_g : best_f;
@@ -305,7 +306,10 @@ int build_plan(ude_handle* h) {
 
   // launch geometry: persistent grid, a multiple of the SM count
   const int stages = D.solver == UDE_TSIT5 ? 6 : 4;
-  h->smem_bytes = (h->n_models == 1) ? (size_t)(D.n_pm + 1) * sizeof(double) : 0;
+  // dynamic smem: block partial row (single model) padded to 16 B + per-warp two-step TMA staging ring of the stash
+  const size_t red_doubles = (size_t)(((h->n_models == 1 ? D.n_pm + 1 : 0) + 1) / 2 * 2);
+  const size_t stage_doubles = (size_t)(ude::kBlockThreads / 32) * 2 * (size_t)stages * h->k_grad->rows_per_stage * 32;
+  h->smem_bytes = (red_doubles + stage_doubles) * sizeof(double);
   for (const KernelEntry* k : {h->k_grad, h->k_fwd}) {
     if (h->smem_bytes > 40 * 1024)
       UDE_CUDA_TRY(h, cudaFuncSetAttribute(k->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));

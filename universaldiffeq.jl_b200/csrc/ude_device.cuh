@@ -122,30 +122,61 @@ __device__ __forceinline__ void group_allreduce(double (&v)[N], int lane) {
         w[0] += __shfl_xor_sync(0xffffffffu, w[0], off);
       }
     }
-    // all-gather: undo the splits in reverse order.  Splits happened at off = G/2, G/4, ... (ns of them).
+    // gather: after the reduce-scatter, element e = q * cnt_final + r (r < cnt_final) lives in slot r of every lane
+    // whose split bits (lane & G/2, lane & G/4, ...) spell q, most significant split first.  Each lane fetches all N
+    // sums with independent indexed shuffles: one level of latency, no selects.
     constexpr int cnt_final = (NP / G) > 1 ? (NP / G) : 1;
     constexpr int ns = ilog2(NP / cnt_final);
-    int c = cnt_final;
+    constexpr int split_mask = (G - 1) & ~((G >> ns) - 1);     // lane bits consumed by the splits
+    const int keep = lane & ~split_mask;
+    double out[N];
 #pragma unroll
-    for (int s = 0; s < 8; ++s) {
-      if (s < ns) {
-        const int off = G >> (ns - s);       // last split first
-        const bool up = (lane & off) != 0;
+    for (int e = 0; e < N; ++e) {
+      constexpr int dummy = 0; (void)dummy;
+      const int qe = e / cnt_final, re = e % cnt_final;
+      int src = keep;
 #pragma unroll
-        for (int i = 0; i < NP / 2; ++i) {
-          if (i < c) {
-            double recv = __shfl_xor_sync(0xffffffffu, w[i], off);
-            double lo = up ? recv : w[i];
-            double hi = up ? w[i] : recv;
-            w[i] = lo; w[i + c] = hi;
-          }
-        }
-        c *= 2;
-      }
+      for (int s2 = 0; s2 < ns; ++s2) if ((qe >> (ns - 1 - s2)) & 1) src |= (G >> (s2 + 1));
+      out[e] = __shfl_sync(0xffffffffu, w[re], src);
     }
 #pragma unroll
-    for (int i = 0; i < N; ++i) v[i] = w[i];
+    for (int i = 0; i < N; ++i) v[i] = out[i];
   }
 }
+
+// ------------------------------------------------------------------------------------------------
+// TMA bulk copies (cp.async.bulk, SASS UBLKCP) between a warp's shared-memory staging buffers and its stash in global
+// memory, completion through an mbarrier (loads) or a bulk async-group (stores).  One lane issues, the warp consumes.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "LAB_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra LAB_DONE_%=;\n"
+      "bra LAB_WAIT_%=;\n"
+      "LAB_DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* sdst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sdst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 }  // namespace ude

@@ -5,15 +5,20 @@
 #include "ude_registry.h"
 
 namespace ude {
+template <class R, int G, int HPL, int MINB, int SOLVER, int LK>
+void register_one(const char* name, int priority) {
+  kernel_registry().push_back(KernelEntry{R::KIND, R::D, R::NX, R::DIN, R::DOUT, G, HPL, SOLVER, LK, 1, Geo<R, G, HPL>::ROWS, priority,
+                                          (const void*)ude_seg_kernel<R, G, HPL, SOLVER, LK, true, MINB>, name});
+  kernel_registry().push_back(KernelEntry{R::KIND, R::D, R::NX, R::DIN, R::DOUT, G, HPL, SOLVER, LK, 0, Geo<R, G, HPL>::ROWS, priority,
+                                          (const void*)ude_seg_kernel<R, G, HPL, SOLVER, LK, false, MINB>, name});
+}
 template <class R, int G, int HPL, int MINB>
 void register_combo(const char* name, int priority) {
-  auto add = [&](int solver, int grad, const void* fn) {
-    kernel_registry().push_back(KernelEntry{R::KIND, R::D, R::NX, R::DIN, R::DOUT, G, HPL, solver, grad,
-                                            Geo<R, G, HPL>::ROWS, priority, fn, name});
-  };
-  add(0, 1, (const void*)ude_seg_kernel<R, G, HPL, 0, true, MINB>);
-  add(0, 0, (const void*)ude_seg_kernel<R, G, HPL, 0, false, MINB>);
-  add(1, 1, (const void*)ude_seg_kernel<R, G, HPL, 1, true, MINB>);
-  add(1, 0, (const void*)ude_seg_kernel<R, G, HPL, 1, false, MINB>);
+  register_one<R, G, HPL, MINB, 0, LK_STATE>(name, priority);
+  register_one<R, G, HPL, MINB, 0, LK_TRAJ>(name, priority);
+  register_one<R, G, HPL, MINB, 0, LK_DM>(name, priority);
+  register_one<R, G, HPL, MINB, 1, LK_STATE>(name, priority);
+  register_one<R, G, HPL, MINB, 1, LK_TRAJ>(name, priority);
+  register_one<R, G, HPL, MINB, 1, LK_DM>(name, priority);
 }
 }  // namespace ude

@@ -83,31 +83,47 @@ __device__ __forceinline__ void zero_grad(LaneGrad<R, HPL>& gr) {
   for (int k = 0; k < (R::NS > 0 ? R::NS : 1); ++k) gr.sc[k] = 0.0;
 }
 
-// piecewise-linear covariates with flat extrapolation (/root/reference/src/covariates.jl:16-19, :45-48);
-// `lo` is a per-variable cursor: stage times move monotonically inside a segment, so the search is O(1).
+// piecewise-linear covariates with flat extrapolation (/root/reference/src/covariates.jl:16-19, :45-48).
+// Each group caches the knot interval it is in (validity range, reference time, 1/dt, both knot values): stage times
+// move monotonically inside a segment, so almost every evaluation is 4 FP64 instructions and no memory access; the
+// refill (binary search over the series' knots) runs once per knot crossing.  Flat extrapolation is an interval with
+// inv = 0 and equal end values.
 template <int NX>
-__device__ __forceinline__ void cov_eval(const DevProblem& P, int series, double t, int (&lo)[NX > 0 ? NX : 1],
+struct CovCache {
+  static constexpr int N = NX > 0 ? NX : 1;
+  double vlo[N], vhi[N], tref[N], inv[N], xlo[N], xhi[N];
+};
+
+template <int NX>
+__device__ __forceinline__ void cov_reset(CovCache<NX>& c) {
+#pragma unroll
+  for (int v = 0; v < CovCache<NX>::N; ++v) { c.vlo[v] = 1.0; c.vhi[v] = 0.0; c.tref[v] = 0.0; c.inv[v] = 0.0; c.xlo[v] = 0.0; c.xhi[v] = 0.0; }
+}
+
+template <int NX>
+__device__ __forceinline__ void cov_refill(const DevProblem& P, int series, int v, double t, CovCache<NX>& c) {
+  const long long k0 = P.knot_off[(long long)series * NX + v];
+  const int n = (int)(P.knot_off[(long long)series * NX + v + 1] - k0);
+  const double* __restrict__ kt = P.knot_t + k0;
+  const double* __restrict__ kx = P.knot_x + k0;
+  const double inf = __longlong_as_double(0x7ff0000000000000LL);
+  if (n <= 0) { c.vlo[v] = -inf; c.vhi[v] = inf; c.tref[v] = 0.0; c.inv[v] = 0.0; c.xlo[v] = 0.0; c.xhi[v] = 0.0; return; }
+  if (t < kt[0]) { c.vlo[v] = -inf; c.vhi[v] = kt[0]; c.tref[v] = kt[0]; c.inv[v] = 0.0; c.xlo[v] = kx[0]; c.xhi[v] = kx[0]; return; }
+  if (t >= kt[n - 1]) { c.vlo[v] = kt[n - 1]; c.vhi[v] = inf; c.tref[v] = kt[n - 1]; c.inv[v] = 0.0; c.xlo[v] = kx[n - 1]; c.xhi[v] = kx[n - 1]; return; }
+  int lo = 0, hi = n - 1;                  // kt[lo] <= t < kt[hi]
+  while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (kt[mid] <= t) lo = mid; else hi = mid; }
+  c.vlo[v] = kt[lo]; c.vhi[v] = kt[lo + 1]; c.tref[v] = kt[lo]; c.inv[v] = P.knot_inv[k0 + lo];
+  c.xlo[v] = kx[lo]; c.xhi[v] = kx[lo + 1];
+}
+
+template <int NX>
+__device__ __forceinline__ void cov_eval(const DevProblem& P, int series, double t, CovCache<NX>& c,
                                          double (&X)[NX > 0 ? NX : 1]) {
 #pragma unroll
   for (int v = 0; v < NX; ++v) {
-    const long long k0 = P.knot_off[(long long)series * NX + v];
-    const int n = (int)(P.knot_off[(long long)series * NX + v + 1] - k0);
-    const double* __restrict__ kt = P.knot_t + k0;
-    const double* __restrict__ kx = P.knot_x + k0;
-    double val = 0.0;
-    if (n > 0) {
-      if (t <= kt[0]) val = kx[0];
-      else if (t >= kt[n - 1]) val = kx[n - 1];
-      else {
-        int l = min(max(lo[v], 0), n - 2);
-        while (kt[l + 1] <= t) ++l;
-        while (kt[l] > t) --l;
-        lo[v] = l;
-        const double f = (t - kt[l]) * P.knot_inv[k0 + l];
-        val = (1.0 - f) * kx[l] + f * kx[l + 1];
-      }
-    }
-    X[v] = val;
+    if (!(t >= c.vlo[v] && t < c.vhi[v])) cov_refill<NX>(P, series, v, t, c);
+    const double f = (t - c.tref[v]) * c.inv[v];
+    X[v] = fma(f, c.xhi[v], (1.0 - f) * c.xlo[v]);
   }
 }
 
@@ -118,13 +134,15 @@ __device__ __forceinline__ void stage_forward(const LaneNet<R, HPL>& n, const Rh
                                               double (&du)[R::D], double (&hh)[HPL], double (&y)[R::DOUT]) {
   double x[R::DIN];
   R::input(U, X, t, ctx, x);
+  double z[HPL];
 #pragma unroll
-  for (int i = 0; i < HPL; ++i) {
-    double z = n.b1[i];
+  for (int i = 0; i < HPL; ++i) z[i] = n.b1[i];
 #pragma unroll
-    for (int k = 0; k < R::DIN; ++k) z = fma(n.W1[i][k], x[k], z);
-    hh[i] = ude_tanh_tab(z, s_tab);
+  for (int k = 0; k < R::DIN; ++k) {
+#pragma unroll
+    for (int i = 0; i < HPL; ++i) z[i] = fma(n.W1[i][k], x[k], z[i]);
   }
+  ude_tanh_tab_vec<HPL>(z, hh, s_tab);
   double part[R::DOUT];
 #pragma unroll
   for (int o = 0; o < R::DOUT; ++o) {
@@ -207,7 +225,7 @@ __device__ __forceinline__ void stash_load(const double* __restrict__ rec, int l
 // ---- one explicit RK step forward; GRAD: record every stage -------------------------------------------------
 template <class R, int G, int HPL, int SOLVER, bool GRAD>
 __device__ __forceinline__ void rk_forward(const DevProblem& P, const LaneNet<R, HPL>& n, const RhsCtx& ctx, const double* s_tab,
-                                           int lane, int g, int series, int (&cur)[Geo<R, G, HPL>::NXA],
+                                           int lane, int g, int series, CovCache<R::NX>& cur,
                                            double (&u)[R::D], double t, double hs, double* __restrict__ step_rec) {
   using T = Tab<SOLVER>;
   using GG = Geo<R, G, HPL>;
@@ -232,7 +250,7 @@ __device__ __forceinline__ void rk_forward(const DevProblem& P, const LaneNet<R,
     if (R::NX > 0) cov_eval<R::NX>(P, series, ts, cur, X);
     double du[D], hh[HPL], y[R::DOUT];
     stage_forward<R, G, HPL>(n, ctx, s_tab, lane, U, X, ts, du, hh, y);
-    if (GRAD) stash_store<R, G, HPL>(step_rec + (long long)i * GG::ROWS * 32, lane, g, hh, U, X, y);
+    if (GRAD) stash_store<R, G, HPL>(step_rec + i * GG::ROWS * 32, lane, g, hh, U, X, y);
 #pragma unroll
     for (int j = 0; j < D; ++j) { k[i][j] = du[j]; acc[j] = fma(T::b(i), du[j], acc[j]); }
   }
@@ -241,6 +259,7 @@ __device__ __forceinline__ void rk_forward(const DevProblem& P, const LaneNet<R,
 }
 
 // ---- its discrete adjoint; returns the step's initial state in U0 ---------------------------
+// step_rec points at the step's record in the warp's shared-memory staging buffer (filled by a TMA bulk load).
 template <class R, int G, int HPL, int SOLVER>
 __device__ __forceinline__ void rk_reverse(const LaneNet<R, HPL>& n, LaneGrad<R, HPL>& gr, const RhsCtx& ctx, int lane, int g,
                                            double (&lam)[R::D], double t, double hs, const double* __restrict__ step_rec,
@@ -255,6 +274,11 @@ __device__ __forceinline__ void rk_reverse(const LaneNet<R, HPL>& n, LaneGrad<R,
 #pragma unroll
   for (int ii = 0; ii < T::S; ++ii) {
     const int i = T::S - 1 - ii;
+    double hh[HPL], U[D], X[GG::NXA], y[R::DOUT];
+    X[0] = 0.0;
+#pragma unroll
+    for (int o = 0; o < R::DOUT; ++o) y[o] = 0.0;
+    stash_load<R, G, HPL>(step_rec + i * GG::ROWS * 32, lane, g, hh, U, X, y);
     double kb[D];
 #pragma unroll
     for (int j = 0; j < D; ++j) {
@@ -263,11 +287,6 @@ __device__ __forceinline__ void rk_reverse(const LaneNet<R, HPL>& n, LaneGrad<R,
       for (int l = i + 1; l < T::S; ++l) if (T::a(l, i) != 0.0) a = fma(T::a(l, i), Ub[l][j], a);
       kb[j] = hs * a;
     }
-    double hh[HPL], U[D], X[GG::NXA], y[R::DOUT];
-    X[0] = 0.0;
-#pragma unroll
-    for (int o = 0; o < R::DOUT; ++o) y[o] = 0.0;
-    stash_load<R, G, HPL>(step_rec + (long long)i * GG::ROWS * 32, lane, g, hh, U, X, y);
     const double ts = t + T::c(i) * hs;
     double ub[D];
 #pragma unroll
@@ -373,15 +392,31 @@ __device__ __forceinline__ void flush_block(const DevProblem& P, const LaneGrad<
 }
 
 // ================================================================================================================
-template <class R, int G, int HPL, int SOLVER, bool GRAD, int MINB>
+// LK selects the loss family at compile time (keeps each kernel's code inside the instruction cache):
+//   LK_STATE  one observation interval per segment, target = the next uhat column (conditional likelihood / MSE loss)
+//   LK_TRAJ   shooting / multiple-shooting block, targets = data columns
+//   LK_DM     derivative matching: one RHS evaluation per column, no time stepping
+enum { LK_STATE = 0, LK_TRAJ = 1, LK_DM = 2 };
+
+template <class R, int G, int HPL, int SOLVER, int LK, bool GRAD, int MINB>
 __global__ void __launch_bounds__(kBlockThreads, MINB) ude_seg_kernel(const DevProblem P) {
   using GG = Geo<R, G, HPL>;
   using T = Tab<SOLVER>;
   constexpr int D = R::D;
   __shared__ double s_tab[64];
-  extern __shared__ double s_red[];          // n_pm + 1 doubles: block-level gradient/loss partial (single model)
+  __shared__ __align__(8) uint64_t s_bar[kBlockThreads / 32][2];
+  // dynamic shared memory: [n_pm + 1 doubles (block-level gradient/loss partial, single model), padded to 16 B]
+  //                        [per warp: two step records of S * ROWS rows of 256 B -- the TMA staging ring of the stash]
+  extern __shared__ __align__(16) double s_dyn[];
+  double* s_red = s_dyn;
   ude_load_exp2_tab(s_tab);
   if (P.n_models == 1) for (long long k = threadIdx.x; k <= P.n_pm; k += blockDim.x) s_red[k] = 0.0;
+  constexpr int kStepDoubles = T::S * GG::ROWS * 32;
+  constexpr uint32_t kStepBytes = kStepDoubles * 8;
+  double* s_stage = s_dyn + ((P.n_models == 1 ? P.n_pm + 1 : 0) + 1) / 2 * 2 + (size_t)(threadIdx.x >> 5) * 2 * kStepDoubles;
+  uint64_t* bar = s_bar[threadIdx.x >> 5];
+  if (GRAD && LK != LK_DM && (threadIdx.x & 31) == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); }
+  uint32_t bar_phase = 0;      // bit b = parity the next wait on bar[b] expects
   __syncthreads();
 
   const int lane = threadIdx.x & 31;
@@ -390,6 +425,7 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) ude_seg_kernel(const DevP
   const long long warp_global = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
   const long long total_warps = (long long)gridDim.x * warps_per_block;
   double* __restrict__ stash = GRAD ? P.stash + warp_global * P.stash_rows_per_warp * 32 : nullptr;
+  constexpr long long rec_stride = kStepDoubles;
   const int S = P.substeps;
 
   LaneNet<R, HPL> net;
@@ -421,73 +457,10 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) ude_seg_kernel(const DevP
     const long long series_local = series - P.model_series0[model];
     if (R::SERIES) ctx.series_param = pm[P.off_series_param + series_local];
     double gseries = 0.0;
-    int cur[GG::NXA];
-#pragma unroll
-    for (int v = 0; v < GG::NXA; ++v) cur[v] = 0;
+    CovCache<R::NX> cur;
+    cov_reset<R::NX>(cur);
 
-    if (P.loss_kind == UDE_LOSS_STATE_SPACE) {
-      // ---- one observation interval (c-1 -> c): LFC.jl:38-44, helpers.jl:31-37 --------------------------------
-      const bool skip = is_null || (sg.flags & SEG_SKIP_PROC);
-      const long long c = sg.col;
-      const long long cp = c - 1;
-      const bool has_prev = !(is_null) && (cp >= P.starts[series]);
-      const long long cpl = has_prev ? cp : c;
-      double u[D];
-#pragma unroll
-      for (int j = 0; j < D; ++j) u[j] = uh[D * cpl + j];
-      const double t0 = P.times[cpl];
-      const double dt = P.times[c] - t0;
-      const double hs = skip ? 0.0 : dt / S;
-      for (int n = 0; n < S; ++n)
-        rk_forward<R, G, HPL, SOLVER, GRAD>(P, net, ctx, s_tab, lane, g, series, cur, u, t0 + n * hs, hs,
-                                            stash + (long long)n * T::S * GG::ROWS * 32);
-      double r[D], sym[D], gc[D], gp[D];
-#pragma unroll
-      for (int j = 0; j < D; ++j) r[j] = uh[D * c + j] - u[j];
-      const double wsc = skip ? 0.0 : P.proc_scale[model] * (P.proc_inv_dt ? 1.0 / dt : 1.0);
-      loss = fma(wsc, quad_form<D>(P.B, P.Bsym, r, sym), loss);
-      double lam[D];
-#pragma unroll
-      for (int j = 0; j < D; ++j) { lam[j] = -wsc * sym[j]; gc[j] = wsc * sym[j]; gp[j] = 0.0; }
-      const double os = is_null ? 0.0 : P.obs_scale[model];
-      {
-        double e[D], es[D];
-#pragma unroll
-        for (int j = 0; j < D; ++j) e[j] = P.data[D * c + j] - uh[D * c + j];
-        loss = fma(os, quad_form<D>(P.A, P.Asym, e, es), loss);
-#pragma unroll
-        for (int j = 0; j < D; ++j) gc[j] = fma(-os, es[j], gc[j]);
-      }
-      if ((sg.flags & SEG_OBS_FIRST) && has_prev) {
-        double e[D], es[D];
-#pragma unroll
-        for (int j = 0; j < D; ++j) e[j] = P.data[D * cp + j] - uh[D * cp + j];
-        loss = fma(os, quad_form<D>(P.A, P.Asym, e, es), loss);
-#pragma unroll
-        for (int j = 0; j < D; ++j) gp[j] = -os * es[j];
-      }
-      if (GRAD) {
-        double U0[D];
-        for (int n = S - 1; n >= 0; --n)
-          rk_reverse<R, G, HPL, SOLVER>(net, gr, ctx, lane, g, lam, t0 + n * hs, hs,
-                                        stash + (long long)n * T::S * GG::ROWS * 32, U0, gseries);
-        if (!is_null) {
-#pragma unroll
-          for (int j = 0; j < D; ++j) {
-            if (g == j % G) {
-              atomicAdd(guh + D * c + j, gc[j]);
-              if (has_prev) atomicAdd(guh + D * cp + j, gp[j] + lam[j]);
-            }
-          }
-        }
-      } else if (P.traj_out != nullptr && !is_null) {
-#pragma unroll
-        for (int j = 0; j < D; ++j) if (g == j % G) {
-          if (!skip) P.traj_out[D * c + j] = u[j];
-          if (!has_prev || (sg.flags & SEG_OBS_FIRST)) P.traj_out[D * cpl + j] = uh[D * cpl + j];
-        }
-      }
-    } else if (P.loss_kind == UDE_LOSS_DERIV_MATCH) {
+    if (LK == LK_DM) {
       // ---- one column of the derivative-matching loss: LFC.jl:181-186, :525-533 ----------------------------------
       const long long c = sg.col;
       double U[D], X[GG::NXA], du[D], hh[HPL], y[R::DOUT], kb[D], ub[D];
@@ -506,65 +479,184 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) ude_seg_kernel(const DevP
       }
       if (GRAD) stage_backward<R, G, HPL>(net, gr, ctx, lane, U, X, ts, hh, y, kb, ub, gseries);
     } else {
-      // ---- shooting / multiple-shooting block: LFC.jl:261-305, :639-687, :196-232, :545-601 ----------------------
+      // ---- a segment = [pre-roll step] + maxL intervals of S steps; groups with fewer intervals step with h = 0 ----
       const bool multi = P.loss_kind == UDE_LOSS_MULTI_SHOOT;
-      const long long c0 = sg.col;
-      const int L = is_null ? 0 : sg.L;
-      const int maxL = (int)__reduce_max_sync(0xffffffffu, (unsigned)L);
-      const bool from_theta = multi || P.shoot_from_theta;
-      const int first_scored = multi ? 0 : P.shoot_first_scored;
-      const double wpt = is_null ? 0.0 : (multi ? 1.0 / ((double)D * (double)P.lengths[series]) : P.shoot_weight[model]);
-      const double eps = multi ? P.preroll_eps : 0.0;
-      const int pre = eps > 0.0 ? 1 : 0;
+      const bool skip = is_null || (LK == LK_STATE && (sg.flags & SEG_SKIP_PROC));
+      long long c0;            // first column of the segment
+      int L, maxL, pre, first_scored;
+      bool from_theta, has_prev = true;
+      double wpt = 0.0, eps = 0.0;
+      if (LK == LK_STATE) {
+        const long long c = sg.col;
+        has_prev = !is_null && (c - 1 >= P.starts[series]);
+        c0 = has_prev ? c - 1 : c;
+        L = (skip || !has_prev) ? 0 : 1; maxL = 1; pre = 0; first_scored = 0; from_theta = true;
+      } else {
+        c0 = sg.col;
+        L = is_null ? 0 : sg.L;
+        maxL = (int)__reduce_max_sync(0xffffffffu, (unsigned)L);
+        from_theta = multi || P.shoot_from_theta;
+        first_scored = multi ? 0 : P.shoot_first_scored;
+        wpt = is_null ? 0.0 : (multi ? 1.0 / ((double)D * (double)P.lengths[series]) : P.shoot_weight[model]);
+        eps = multi ? P.preroll_eps : 0.0;
+        pre = eps > 0.0 ? 1 : 0;
+      }
+      const int nsteps = pre + maxL * S;
       double u[D];
 #pragma unroll
       for (int j = 0; j < D; ++j) u[j] = from_theta ? uh[D * c0 + j] : P.data[D * c0 + j];
-      const long long rec_stride = (long long)T::S * GG::ROWS * 32;
-      if (pre) rk_forward<R, G, HPL, SOLVER, GRAD>(P, net, ctx, s_tab, lane, g, series, cur, u, P.times[c0] - eps,
-                                                   is_null ? 0.0 : eps, stash);
-      for (int i = 0; i <= maxL; ++i) {
-        const int ic = min(i, L);
-        const double w = (i <= L && i >= first_scored) ? wpt : 0.0;
+
+      // ---------------- forward sweep: ONE inlined RK step in a flat loop over the segment's steps ----------------
+      {
+        int i = pre ? -1 : 0, n = pre ? S - 1 : 0;
+        double t0 = P.times[c0] - eps, hs = is_null ? 0.0 : eps, nd = 0.0;
+        for (int k = 0; k < nsteps; ++k) {
+          if (k >= pre && n == 0) {
+            // entering interval i at observation point i
+            const int ic = min(i, L);
+            if (LK == LK_TRAJ) {
+              const double w = (i <= L && i >= first_scored) ? wpt : 0.0;
+#pragma unroll
+              for (int j = 0; j < D; ++j) { const double r = P.data[D * (c0 + ic) + j] - u[j]; loss = fma(w * r, r, loss); }
+              if (!GRAD && P.traj_out != nullptr && i <= L && !is_null) {
+#pragma unroll
+                for (int j = 0; j < D; ++j) if (g == j % G) P.traj_out[D * (c0 + i) + j] = u[j];
+              }
+            }
+            t0 = P.times[c0 + ic];
+            hs = (i < L) ? (P.times[c0 + ic + 1] - t0) / S : 0.0;
+            nd = 0.0;
+          }
+          double* sbuf = s_stage + (k & 1) * kStepDoubles;
+          if (GRAD) {   // the bulk store that last read this buffer (two steps ago) must have drained it
+            if (lane == 0) bulk_wait_read<1>();
+            __syncwarp();
+          }
+          rk_forward<R, G, HPL, SOLVER, GRAD>(P, net, ctx, s_tab, lane, g, series, cur, u, fma(nd, hs, t0), hs, sbuf);
+          if (GRAD) {   // hand the step record to the TMA: smem -> this warp's stash slot k
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) { bulk_store(stash + (long long)k * rec_stride, sbuf, kStepBytes); bulk_commit(); }
+          }
+          nd += 1.0;
+          if (++n == S) { n = 0; ++i; }
+        }
+        if (GRAD) {     // stash complete and visible before the reverse sweep's bulk loads; start fetching the last step
+          if (lane == 0) {
+            bulk_wait_all<0>();
+            if (nsteps > 0) {
+              const int b = (nsteps - 1) & 1;
+              mbar_expect_tx(&bar[b], kStepBytes);
+              bulk_load(s_stage + b * kStepDoubles, stash + (long long)(nsteps - 1) * rec_stride, kStepBytes, &bar[b]);
+            }
+          }
+          __syncwarp();
+        }
+      }
+      // ---------------- loss at the last point, seed of the adjoint ---------------------------------------------------
+      double lam[D];
+      double gc[D], gp[D];
+      if (LK == LK_STATE) {
+        // LFC.jl:38-44 / helpers.jl:31-37: (uhat_c - F(uhat_{c-1}))' B (.) weighted; observation terms LFC.jl:30-34
+        const long long c = sg.col;
+        const double dt = P.times[c] - P.times[c0];
+        double r[D], sym[D];
+#pragma unroll
+        for (int j = 0; j < D; ++j) r[j] = uh[D * c + j] - u[j];
+        const double wsc = (L == 1) ? P.proc_scale[model] * (P.proc_inv_dt ? 1.0 / dt : 1.0) : 0.0;
+        loss = fma(wsc, quad_form<D>(P.B, P.Bsym, r, sym), loss);
+#pragma unroll
+        for (int j = 0; j < D; ++j) { lam[j] = -wsc * sym[j]; gc[j] = wsc * sym[j]; gp[j] = 0.0; }
+        const double os = is_null ? 0.0 : P.obs_scale[model];
+        {
+          double e[D], es[D];
+#pragma unroll
+          for (int j = 0; j < D; ++j) e[j] = P.data[D * c + j] - uh[D * c + j];
+          loss = fma(os, quad_form<D>(P.A, P.Asym, e, es), loss);
+#pragma unroll
+          for (int j = 0; j < D; ++j) gc[j] = fma(-os, es[j], gc[j]);
+        }
+        if ((sg.flags & SEG_OBS_FIRST) && has_prev) {
+          double e[D], es[D];
+#pragma unroll
+          for (int j = 0; j < D; ++j) e[j] = P.data[D * c0 + j] - uh[D * c0 + j];
+          loss = fma(os, quad_form<D>(P.A, P.Asym, e, es), loss);
+#pragma unroll
+          for (int j = 0; j < D; ++j) gp[j] = -os * es[j];
+        }
+        if (!GRAD && P.traj_out != nullptr && !is_null) {
+#pragma unroll
+          for (int j = 0; j < D; ++j) if (g == j % G) {
+            if (L == 1) P.traj_out[D * c + j] = u[j];
+            if (!has_prev || (sg.flags & SEG_OBS_FIRST)) P.traj_out[D * c0 + j] = uh[D * c0 + j];
+          }
+        }
+      } else {
+        const double w = (maxL <= L && maxL >= first_scored) ? wpt : 0.0;
+        const int ic = min(maxL, L);
 #pragma unroll
         for (int j = 0; j < D; ++j) {
           const double r = P.data[D * (c0 + ic) + j] - u[j];
           loss = fma(w * r, r, loss);
+          lam[j] = -2.0 * w * r;
         }
-        if (!GRAD && P.traj_out != nullptr && i <= L && !is_null) {
+        // the block's end point is written by the block that STARTS there when one exists (a later block overwrites
+        // it in the reference, LFC.jl:336, :751): full blocks of a multiple-shooting series leave it alone
+        if (!GRAD && P.traj_out != nullptr && maxL <= L && !is_null && !(multi && L == P.pred_length)) {
 #pragma unroll
-          for (int j = 0; j < D; ++j) if (g == j % G) P.traj_out[D * (c0 + i) + j] = u[j];
+          for (int j = 0; j < D; ++j) if (g == j % G) P.traj_out[D * (c0 + L) + j] = u[j];
         }
-        if (i == maxL) break;
-        const double t0 = P.times[c0 + ic];
-        const double hs = (i < L) ? (P.times[c0 + ic + 1] - t0) / S : 0.0;
-        for (int n = 0; n < S; ++n)
-          rk_forward<R, G, HPL, SOLVER, GRAD>(P, net, ctx, s_tab, lane, g, series, cur, u, t0 + n * hs, hs,
-                                              stash + (long long)(pre + i * S + n) * rec_stride);
       }
+      // ---------------- reverse sweep ------------------------------------------------------------------------------------
       if (GRAD) {
-        double lam[D], U0[D];
-        {
-          const double w = (maxL <= L && maxL >= first_scored) ? wpt : 0.0;
+        double U0[D];
+        int i = maxL - 1, n = S - 1;
+        double t0 = 0.0, hs = 0.0;
+        for (int k = nsteps - 1; k >= 0; --k) {
+          const int b = k & 1;
+          if (k > 0 && lane == 0) {      // prefetch step k-1 into the other buffer while step k is reversed
+            mbar_expect_tx(&bar[b ^ 1], kStepBytes);
+            bulk_load(s_stage + (b ^ 1) * kStepDoubles, stash + (long long)(k - 1) * rec_stride, kStepBytes, &bar[b ^ 1]);
+          }
+          mbar_wait(&bar[b], (bar_phase >> b) & 1u);
+          bar_phase ^= (1u << b);
+          double t;
+          if (k >= pre) {
+            if (n == S - 1) {
+              const int ic = min(i, L);
+              t0 = P.times[c0 + ic];
+              hs = (i < L) ? (P.times[c0 + ic + 1] - t0) / S : 0.0;
+            }
+            t = fma((double)n, hs, t0);
+          } else { t = P.times[c0] - eps; hs = is_null ? 0.0 : eps; }
+          rk_reverse<R, G, HPL, SOLVER>(net, gr, ctx, lane, g, lam, t, hs, s_stage + b * kStepDoubles, U0, gseries);
+          __syncwarp();                  // every lane is done reading buffer b before it is refilled
+          if (k >= pre) {
+            if (n == 0) {
+              if (LK == LK_TRAJ) {   // U0 is the state at observation point i: add that point's loss cotangent
+                const int ic = min(i, L);
+                const double w = (i <= L && i >= first_scored) ? wpt : 0.0;
 #pragma unroll
-          for (int j = 0; j < D; ++j) lam[j] = -2.0 * w * (P.data[D * (c0 + min(maxL, L)) + j] - u[j]);
+                for (int j = 0; j < D; ++j) lam[j] = fma(-2.0 * w, P.data[D * (c0 + ic) + j] - U0[j], lam[j]);
+              }
+              --i; n = S - 1;
+            } else --n;
+          }
         }
-        for (int i = maxL - 1; i >= 0; --i) {
-          const int ic = min(i, L);
-          const double t0 = P.times[c0 + ic];
-          const double hs = (i < L) ? (P.times[c0 + ic + 1] - t0) / S : 0.0;
-          for (int n = S - 1; n >= 0; --n)
-            rk_reverse<R, G, HPL, SOLVER>(net, gr, ctx, lane, g, lam, t0 + n * hs, hs,
-                                          stash + (long long)(pre + i * S + n) * rec_stride, U0, gseries);
-          // U0 is now the state at observation point i: add that point's loss cotangent
-          const double w = (i <= L && i >= first_scored) ? wpt : 0.0;
+        if (!is_null) {
+          if (LK == LK_STATE) {
+            const long long c = sg.col;
 #pragma unroll
-          for (int j = 0; j < D; ++j) lam[j] = fma(-2.0 * w, P.data[D * (c0 + ic) + j] - U0[j], lam[j]);
-        }
-        if (pre) rk_reverse<R, G, HPL, SOLVER>(net, gr, ctx, lane, g, lam, P.times[c0] - eps, is_null ? 0.0 : eps,
-                                               stash, U0, gseries);
-        if (from_theta && !is_null) {
+            for (int j = 0; j < D; ++j) {
+              if (g == j % G) {
+                atomicAdd(guh + D * c + j, gc[j]);
+                if (has_prev) atomicAdd(guh + D * c0 + j, gp[j] + lam[j]);
+              }
+            }
+          } else if (from_theta) {
 #pragma unroll
-          for (int j = 0; j < D; ++j) if (g == j % G) atomicAdd(guh + D * c0 + j, lam[j]);
+            for (int j = 0; j < D; ++j) if (g == j % G) atomicAdd(guh + D * c0 + j, lam[j]);
+          }
         }
       }
     }

@@ -106,6 +106,64 @@ __device__ __forceinline__ double ude_tanh_tab(double x, const double* __restric
   return copysign(y, x);
 }
 
+// The same evaluation for N independent arguments, written phase by phase so that the N dependency chains are
+// interleaved in program order (the FP64 pipe has an 8-cycle dependent-issue latency and issues every 2 cycles:
+// a single chain leaves it 75% idle; profiles/ncu_c3_r01a.txt shows stall_wait as the top stall reason).
+template <int N>
+__device__ __forceinline__ void ude_tanh_tab_vec(const double (&x)[N], double (&out)[N], const double* __restrict__ s_tab) {
+  const double INV   = 184.6649652337873;
+  const double C_HI  = 0x1.62e42fee00000p-7;
+  const double C_LO  = 0x1.a39ef35793c76p-39;
+  const double SHIFT = 6755399441055744.0;
+  double ax[N], kf[N], r[N], q[N], p[N], T[N], s[N], em1[N], den[N], y[N], e[N];
+  int Nn[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    int hi = __double2hiint(x[i]) & 0x7fffffff;
+    hi = min(hi, 0x40340000);
+    ax[i] = __hiloint2double(hi, __double2loint(x[i]));
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) kf[i] = fma(ax[i], INV, SHIFT);
+#pragma unroll
+  for (int i = 0; i < N; ++i) { Nn[i] = __double2loint(kf[i]); kf[i] -= SHIFT; }
+#pragma unroll
+  for (int i = 0; i < N; ++i) T[i] = s_tab[Nn[i] & 63];
+#pragma unroll
+  for (int i = 0; i < N; ++i) r[i] = fma(kf[i], -C_HI, ax[i] + ax[i]);
+#pragma unroll
+  for (int i = 0; i < N; ++i) r[i] = fma(kf[i], -C_LO, r[i]);
+#pragma unroll
+  for (int i = 0; i < N; ++i) q[i] = fma(r[i], 8.333333333333333e-03, 4.1666666666666664e-02);
+#pragma unroll
+  for (int i = 0; i < N; ++i) q[i] = fma(q[i], r[i], 1.6666666666666666e-01);
+#pragma unroll
+  for (int i = 0; i < N; ++i) q[i] = fma(q[i], r[i], 0.5);
+#pragma unroll
+  for (int i = 0; i < N; ++i) p[i] = fma(q[i], r[i] * r[i], r[i]);
+#pragma unroll
+  for (int i = 0; i < N; ++i) s[i] = __hiloint2double(__double2hiint(T[i]) + ((Nn[i] >> 6) << 20), __double2loint(T[i]));
+#pragma unroll
+  for (int i = 0; i < N; ++i) em1[i] = fma(s[i], p[i], s[i] - 1.0);
+#pragma unroll
+  for (int i = 0; i < N; ++i) den[i] = em1[i] + 2.0;
+#pragma unroll
+  for (int i = 0; i < N; ++i) asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y[i]) : "d"(den[i]));
+#pragma unroll
+  for (int it = 0; it < UDE_RCP_NR; ++it) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) e[i] = fma(-den[i], y[i], 1.0);
+#pragma unroll
+    for (int i = 0; i < N; ++i) y[i] = fma(y[i], e[i], y[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) q[i] = em1[i] * y[i];
+#pragma unroll
+  for (int i = 0; i < N; ++i) e[i] = fma(-q[i], den[i], em1[i]);
+#pragma unroll
+  for (int i = 0; i < N; ++i) out[i] = copysign(fma(e[i], y[i], q[i]), x[i]);
+}
+
 // single-precision twin for the optional FP32 mode (1e-4 parity bar): hardware tanh is too coarse
 // (2^-11), so use the same E/(E+2) form with ex2.approx; ~1e-6 relative.
 __device__ __forceinline__ float ude_tanhf(float x) {

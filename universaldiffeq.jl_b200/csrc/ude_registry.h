@@ -8,7 +8,7 @@ namespace ude {
 
 struct KernelEntry {
   int rhs_kind, d, n_cov, nn_in, nn_out;
-  int G, HPL, solver, grad;
+  int G, HPL, solver, lk, grad;   // lk: 0 state-space, 1 trajectory (shooting kinds), 2 derivative matching
   int rows_per_stage;      // stash rows (256 B each) per RK stage
   int priority;            // lower = preferred when several (G, HPL) fit
   const void* fn;
