@@ -1,0 +1,117 @@
+"""Host-side mirror of the reference's constructors and loss builders: the Problems they emit encode the reference's
+formulas, checked by evaluating them with the oracle against a from-scratch NumPy evaluation."""
+import numpy as np
+import pandas as pd
+import pytest
+
+from oracle import oracle, ude_oracle_np as onp
+
+
+def _lv_frame(ude, n=25, seed=3):
+    Y, ts = ude.synthetic.lotka_volterra_data(np.random.default_rng(seed), 1, n)
+    return pd.DataFrame({"time": ts, "x1": Y[0, 0], "x2": Y[0, 1]})
+
+
+def _readme_model(ude, df):
+    _, p = ude.SimpleNeuralNetwork(2, 1)
+    return ude.CustomDerivatives(df, ude.LV_UDE_ABS, {"NN": p, "r": 0.1, "k": 10.1, "m": 0.1, "theta": 0.1})
+
+
+def test_constructor_layout_and_defaults(ude):
+    df = _lv_frame(ude).sample(frac=1.0, random_state=0)          # process_data sorts by time (src/helpers.jl:495)
+    m = _readme_model(ude, df)
+    assert np.all(np.diff(m.times) > 0) and m.data.shape == (2, 25)
+    assert m.parameters.shape[0] == 2 * 25 + 41 + 4                # uhat | NN (2->10->1 = 41) | r k m theta
+    assert np.all(m.uhat == 1e-3)                                  # src/helpers.jl:3
+    assert np.allclose(m.process_model[-4:], [0.1, 10.1, 0.1, 0.1])
+    assert m.weights == dict(regularization=1e-6, process=1.0, observation=1.0)
+    m2 = ude.MultiNODE(pd.concat([df.assign(series="b"), df.assign(series="a")]), hidden_units=7)
+    assert np.all(m2.uhat == 0.0) and m2.obs_divisor == m2.T       # src/MultipleTimeSeries.jl:200, :190
+    assert list(m2.starts) == [0, 25] and m2.rhs.nn_in == 2 and m2.hidden == 7
+
+
+def test_conditional_likelihood_formula(ude):
+    df = _lv_frame(ude)
+    m = _readme_model(ude, df)
+    m.parameters[:50] = m.data.reshape(-1, order="F") + 0.01
+    prob = ude.conditional_likelihood(m, regularization_weight=2.0, observation_error=0.05, process_error=[0.02, 0.04])
+    L, _ = oracle.loss_grad(prob, m.parameters)
+    # App. A.1 by hand
+    uh, pm = m.uhat, m.process_model
+    So, Sp = np.linalg.inv(0.05 * np.eye(2)), np.linalg.inv(np.diag([0.02, 0.04]))
+    ref = sum((m.data[:, t] - uh[:, t]) @ So @ (m.data[:, t] - uh[:, t]) for t in range(25))
+    for t in range(1, 25):
+        r = uh[:, t] - np.real(onp.flow(prob, pm, 0, 0, uh[:, t - 1], m.times[t - 1], m.times[t]))
+        ref += r @ Sp @ r
+    W1 = pm[:20]; W2 = pm[30:40]
+    ref += 2.0 * 1e-6 * (np.sum(W1 ** 2) + np.sum(W2 ** 2))       # train!'s weight times the constructor's (App. A.1)
+    assert abs(L[0] - ref) < 1e-11 * abs(ref)
+
+
+def test_default_loss_and_multi_reg_quirk(ude):
+    df = _lv_frame(ude)
+    dfm = pd.concat([df.assign(series=1), df.iloc[:14].assign(series=2)])
+    m = ude.MultiNODE(dfm, reg_weight=1e-3, obs_weight=0.5, proc_weight=2.0)
+    m.parameters[: m.d * m.N] = m.data.reshape(-1, order="F") * 0.9
+    prob = ude.default_loss(m)
+    L, _ = oracle.loss_grad(prob, m.parameters)
+    uh, pm = m.uhat, m.process_model
+    ref = 0.0
+    for s, (c0, n) in enumerate(zip(m.starts, m.lengths)):
+        for t in range(n):
+            ref += 0.5 * np.sum((m.data[:, c0 + t] - uh[:, c0 + t]) ** 2) / m.T                    # ObservationMSE(T, w)
+        for t in range(1, n):
+            dt = m.times[c0 + t] - m.times[c0 + t - 1]
+            r = uh[:, c0 + t] - np.real(onp.flow(prob, pm, s, s, uh[:, c0 + t - 1], m.times[c0 + t - 1], m.times[c0 + t]))
+            ref += m.T / dt * 2.0 * np.sum(r ** 2) / m.N ** 2                                        # ProcessMSE(N, T, w)
+        ref += 1e-3 * (np.sum(pm[prob.off_w1:prob.off_w1 + 20] ** 2) + np.sum(pm[prob.off_w2:prob.off_w2 + 20] ** 2))  # once PER SERIES
+    assert abs(L[0] - ref) < 1e-11 * abs(ref)
+
+
+def test_shooting_and_multiple_shooting_builders(ude):
+    df = _lv_frame(ude, n=16)
+    m = ude.NODE(df, hidden_units=5)
+    ms = ude.multiple_shooting_loss(m, 0.0, pred_length=5)
+    assert ms.preroll_eps == 1e-6 and ms.count_segments() == 4 and ms.count_steps() == 15 * 4 + 4   # LFC.jl:268 pre-roll
+    sh = ude.shooting_loss(m)
+    assert sh.shoot_from_theta and sh.shoot_first_scored == 2
+    assert np.isclose(sh.shoot_weight[0], m.T * 1.0 / 16 ** 2) and np.isclose(sh.reg_weight[0], 1e-6)
+    mm = ude.MultiNODE(pd.concat([df.assign(series=1), df.assign(series=2)]))
+    assert ude.multiple_shooting_loss(mm).preroll_eps == 0.0 and not ude.shooting_loss(mm).shoot_from_theta
+    with pytest.raises(ValueError):
+        ude.build_problem(m, "marginal likelihood")
+
+
+def test_covariates_long_and_wide(ude):
+    df = _lv_frame(ude, n=12)
+    Xw = pd.DataFrame({"time": np.linspace(0, 3, 7), "X1": np.arange(7.0), "X2": -np.arange(7.0)})
+    m = ude.NODE(df, Xw, hidden_units=4)
+    assert m.n_cov == 2 and m.rhs.nn_in == 4
+    Xl = Xw.melt(id_vars="time", var_name="variable", value_name="value")
+    m2 = ude.NODE(df, Xl, variable_column_name="variable", value_column_name="value", hidden_units=4)
+    assert np.array_equal(m.cov[2], m2.cov[2]) and np.array_equal(m.cov[3], m2.cov[3])
+    p = ude.conditional_likelihood(m)
+    assert np.allclose(onp.covariates_at(p, 0, 0.25), [0.5, -0.5]) and np.allclose(onp.covariates_at(p, 0, 99.0), [6, -6])
+
+
+def test_errors_to_matrix(ude):
+    assert np.array_equal(ude.errors_to_matrix(0.5, 2), 0.5 * np.eye(2))
+    assert np.array_equal(ude.errors_to_matrix([1, 2], 2), np.diag([1.0, 2.0]))
+    M = np.array([[1.0, 0.2], [0.2, 2.0]])
+    assert ude.errors_to_matrix(M, 2) is not None and np.array_equal(ude.errors_to_matrix(M, 2), M)
+    with pytest.raises(ValueError):
+        ude.errors_to_matrix([1, 2, 3], 2)
+
+
+def test_stack_models_is_independent_folds(ude):
+    df = _lv_frame(ude, n=14)
+    m = _readme_model(ude, df)
+    folds = [m.constructor(df.iloc[:-i]) for i in (1, 2, 3)]
+    for i, f in enumerate(folds):
+        f.parameters[: 2 * f.N] = f.data.reshape(-1, order="F") + 0.01 * (i + 1)
+    big, theta = ude.stack_models(folds, "conditional likelihood")
+    L, g = oracle.loss_grad(big, theta)
+    for i, f in enumerate(folds):
+        Li, gi = oracle.loss_grad(ude.conditional_likelihood(f), f.parameters)
+        lo = int(big.theta_base[i])
+        assert abs(L[i] - Li[0]) < 1e-12 * abs(Li[0]) and np.allclose(g[lo:lo + gi.shape[0]], gi, rtol=1e-12, atol=1e-14)

@@ -1,0 +1,155 @@
+"""Cross-validation drivers of the reference, on the CUDA hot path.
+
+  leave_future_out / leave_future_out_cv   /root/reference/src/CrossValidation.jl:17-45, :128-141 (UDE), :234-278, :354-366 (MultiUDE)
+  summarize_leave_future_out               :91-110
+  kfold_cv                                 :167-195 (internal in the reference)
+The reference trains the k folds under Threads.@threads, one optimiser per fold.  Here the folds are the *model* batch
+axis of one handle (ude_set_data's model_of_series): `leave_future_out_batched` trains all folds x ensemble members in
+one device-resident Adam run -- the folds are independent theta vectors, Adam is element-wise, so this is exactly k
+separate train! calls.
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional
+
+import numpy as np
+import pandas as pd
+
+from . import problem as P
+from ._capi import Engine
+from .models import UDE
+from .training import build_problem, default_options, forecast
+
+
+def _split(model: UDE, k: int, skip: int):
+    data = model.data_frame
+    tcol = model.time_column_name
+    train, test = [], []
+    for i in range(skip, skip * k + 1, skip):
+        if not model.multi:
+            train.append(data.iloc[:-i]); test.append(data.iloc[-i:])
+        else:   # src/CrossValidation.jl:242-255: drop the last i points of every series
+            g = data.groupby(model.series_column_name, sort=False, group_keys=False)
+            train.append(g.apply(lambda d: d.sort_values(tcol).iloc[:-i]))
+            test.append(g.apply(lambda d: d.sort_values(tcol).iloc[-i:]))
+    return train, test
+
+
+def _forecast_fold(model_i: UDE, test_i: pd.DataFrame, device=0) -> pd.DataFrame:
+    tcol = model_i.time_column_name
+    if not model_i.multi:
+        tt = np.sort(test_i[tcol].to_numpy(dtype=np.float64))
+        out = forecast(model_i, model_i.uhat[:, -1], model_i.times[-1], tt, device=device)
+        df = pd.DataFrame(out, columns=[tcol] + model_i.varnames)
+        df["horizon"] = df[tcol] - model_i.times.max()
+        return df
+    frames = []
+    for s, lab in enumerate(model_i.labels):
+        tt = np.sort(test_i[test_i[model_i.series_column_name] == lab][tcol].to_numpy(dtype=np.float64))
+        if tt.size == 0:
+            continue
+        c_last = int(model_i.starts[s] + model_i.lengths[s] - 1)
+        out = forecast(model_i, model_i.uhat[:, c_last], model_i.times[c_last], tt, series=s, device=device)
+        df = pd.DataFrame(out, columns=[tcol] + model_i.varnames)
+        df[model_i.series_column_name] = lab
+        df["horizon"] = df[tcol] - model_i.times[c_last]
+        frames.append(df)
+    return pd.concat(frames, ignore_index=True)
+
+
+def leave_future_out(model: UDE, training: Callable[[UDE], None], k: int, skip: int = 1, device=0):
+    """leave_future_out(model, training!, k; skip): k refits on data[1:end-i], forecasts of the held-out tail.
+    Returns (training_data, testing_data, forecasts) like leave_future_out_cv (src/CrossValidation.jl:17-45)."""
+    train, test = _split(model, k, int(round(skip)))
+    forecasts = []
+    for tr, te in zip(train, test):
+        m = model.constructor(tr)           # same seed => same NN init in every fold
+        training(m)
+        forecasts.append(_forecast_fold(m, te, device))
+    return train, test, forecasts
+
+
+def summarize_leave_future_out(model: UDE, testing: List[pd.DataFrame], forecasts: List[pd.DataFrame]):
+    """Mean absolute error by forecast horizon (src/CrossValidation.jl:91-110)."""
+    rows = []
+    keys = [model.time_column_name] + ([model.series_column_name] if model.multi else [])
+    for te, fc in zip(testing, forecasts):
+        mrg = fc.merge(te, on=keys, suffixes=("_forecast", "_testing"))
+        for v in model.varnames:
+            for h, a, b in zip(mrg["horizon"], mrg[v + "_forecast"], mrg[v + "_testing"]):
+                rows.append((h, v, abs(a - b)))
+    df = pd.DataFrame(rows, columns=["horizon", "variable", "abs_error"])
+    by_h = df.groupby("horizon")["abs_error"].agg(mean_absolute_error="mean", standard_error_of_MAE=lambda x: x.std(ddof=1) / np.sqrt(len(x)) if len(x) > 1 else 0.0)
+    return by_h.reset_index(), df
+
+
+def stack_models(models: List[UDE], loss_function, regularization_weight=0.0, loss_options=None) -> tuple:
+    """One Problem whose model axis holds `models` (folds and/or ensemble members of the SAME architecture):
+    returns (problem, theta_all).  Per-model loss scales keep each fold's own N and T (src/LossFunctions.jl:17-28)."""
+    probs = [build_problem(m, loss_function, regularization_weight, loss_options) for m in models]
+    p0 = probs[0]
+    big = P.Problem(d=p0.d, nn_in=p0.nn_in, nn_hidden=p0.nn_hidden, nn_out=p0.nn_out, rhs_kind=p0.rhs_kind, n_cov=p0.n_cov,
+                    n_scalars=p0.n_scalars, has_series_param=p0.has_series_param, solver=p0.solver, substeps=p0.substeps,
+                    time_scale=p0.time_scale, time_shift=p0.time_shift, loss_kind=p0.loss_kind, pred_length=p0.pred_length,
+                    proc_inv_dt=p0.proc_inv_dt, shoot_from_theta=p0.shoot_from_theta, shoot_first_scored=p0.shoot_first_scored,
+                    remove_ends=p0.remove_ends, preroll_eps=p0.preroll_eps, A=p0.A, B=p0.B)
+    big.off_w1, big.off_b1, big.off_w2, big.off_b2 = p0.off_w1, p0.off_b1, p0.off_w2, p0.off_b2
+    big.off_scalar, big.off_series_param, big.n_pm = list(p0.off_scalar), p0.off_series_param, p0.n_pm
+    col, ser = 0, 0
+    starts, lengths, mos, knot_off, kt, kx = [], [], [], [0], [], []
+    for mi, p in enumerate(probs):
+        if (p.n_pm, p.d, p.rhs_kind) != (p0.n_pm, p0.d, p0.rhs_kind):
+            raise ValueError("stacked models must share the architecture")
+        starts.append(p.starts + col); lengths.append(p.lengths); mos.append(np.full(p.n_series, mi))
+        if p.n_cov:
+            knot_off.extend((p.knot_off[1:] + knot_off[-1]).tolist()); kt.append(p.knot_t); kx.append(p.knot_x)
+        col += p.n_cols; ser += p.n_series
+    big.starts, big.lengths, big.model_of_series = np.concatenate(starts), np.concatenate(lengths), np.concatenate(mos)
+    big.times = np.concatenate([p.times for p in probs])
+    big.data = np.concatenate([np.asarray(p.data) for p in probs], axis=1)
+    for name in ("obs_scale", "proc_scale", "shoot_weight", "reg_weight"):
+        setattr(big, name, np.array([getattr(p, name)[0] for p in probs]))
+    if p0.n_cov:
+        big.knot_off, big.knot_t, big.knot_x = np.array(knot_off), np.concatenate(kt), np.concatenate(kx)
+    if p0.loss_kind == P.LOSS_DERIV_MATCH:
+        big.dm_u = np.concatenate([np.asarray(p.dm_u) for p in probs], axis=1)
+        big.dm_dudt = np.concatenate([np.asarray(p.dm_dudt) for p in probs], axis=1)
+    if any(p.skip_mask is not None for p in probs):
+        big.skip_mask = np.concatenate([p.skip_mask if p.skip_mask is not None else np.zeros(p.n_cols, np.uint8) for p in probs])
+    big.finalize()
+    theta = np.concatenate([m.parameters for m in models])
+    assert theta.shape[0] == big.n_theta
+    return big, theta
+
+
+def leave_future_out_batched(model: UDE, k: int, skip: int = 1, loss_function="conditional likelihood", regularization_weight=0.0,
+                             loss_options=None, optim_options=None, n_members: int = 1, member_seeds: Optional[List[int]] = None,
+                             device=0, do_forecast=True):
+    """All k folds (x n_members ensemble members built by `model.extra['member_constructor'](seed)` when given) trained
+    in ONE device-resident Adam run.  Returns (fold_models, training_data, testing_data, forecasts, loss_trace)."""
+    train, test = _split(model, k, int(round(skip)))
+    models = [model.constructor(tr) for tr in train]
+    opts = dict(default_options(loss_function)); opts.update(optim_options or {})
+    big, theta = stack_models(models, loss_function, regularization_weight, loss_options)
+    with Engine(big, device=device) as eng:
+        theta, trace = eng.adam(theta, opts["step_size"], opts["maxiter"])
+    for mi, m in enumerate(models):
+        lo = int(big.theta_base[mi]); hi = int(big.theta_base[mi + 1]) if mi + 1 < big.n_models else big.n_theta
+        m.parameters = theta[lo:hi].copy()
+    forecasts = [_forecast_fold(m, te, device) for m, te in zip(models, test)] if do_forecast else []
+    return models, train, test, forecasts, trace
+
+
+def kfold_cv(model: UDE, training: Callable[[UDE, float], None], k: int = 10):
+    """kfold_cv (src/CrossValidation.jl:167-195): k single-interval hold-outs via the t_skip loss variant; `training(model, t_skip)`
+    must fit with that interval left out.  Returns the one-step prediction errors at the skipped intervals."""
+    N = model.data.shape[1]
+    idx = np.unique(np.linspace(2, N - 1, k).round().astype(int))      # 1-based END index of the interval left out
+    rows = []
+    from .training import predictions
+    for t in idx:
+        m = model.constructor(model.data_frame)
+        training(m, float(t))
+        pred = predictions(m)[:, t - 1]
+        rows.append((t, float(np.mean(np.abs(pred - m.data[:, t - 1])))))
+    return pd.DataFrame(rows, columns=["t_skip", "mean_absolute_error"])

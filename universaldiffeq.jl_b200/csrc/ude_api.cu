@@ -183,11 +183,12 @@ __global__ void ude_finalize_multi(const double* __restrict__ theta, double* __r
   if (threadIdx.x == 0) loss_out[m] = fma(rw, sh[0], model_loss[m]);
 }
 
+// red = [loss | process-model gradient]; the per-series tail was produced by atomics and is left untouched
 __global__ void ude_scatter_reduced(const double* __restrict__ red, long long n_pm, long long series_lo, long long series_hi,
                                     double* __restrict__ grad_pm, double* __restrict__ loss_out) {
   const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k < n_pm) { if (!(k >= series_lo && k < series_hi)) grad_pm[k] = red[k]; }
-  else if (k == n_pm) loss_out[0] = red[n_pm];
+  if (k < n_pm) { if (grad_pm && !(k >= series_lo && k < series_hi)) grad_pm[k] = red[1 + k]; }
+  else if (k == n_pm) loss_out[0] = red[0];
 }
 
 // Optimisers.jl Adam: m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2; theta -= eta * (m/(1-b1^t)) / (sqrt(v/(1-b2^t)) + eps)
@@ -336,7 +337,9 @@ int build_plan(ude_handle* h) {
   UDE_CUDA_TRY(h, h->d_stash.reserve(stash_doubles));
   UDE_CUDA_TRY(h, h->d_block_part.reserve((size_t)std::max(h->grid_grad, h->grid_fwd) * (size_t)(D.n_pm + 1)));
   UDE_CUDA_TRY(h, h->d_model_loss.reserve((size_t)h->n_models));
-  UDE_CUDA_TRY(h, h->d_red.reserve((size_t)D.n_pm + 1));
+  UDE_CUDA_TRY(h, h->d_red.reserve((size_t)D.n_pm + 2));
+  if (h->comm && D.has_series_param && D.off_series_param + h->n_series != D.n_pm)
+    return fail(h, UDE_ERR_INVALID, "multi-GPU: the per-series parameter vector must be the last entry of process_model");
   UDE_CUDA_TRY(h, cudaStreamSynchronize(h->stream));   // segs came from a local vector
   h->dirty = false;
   return UDE_OK;
@@ -393,18 +396,21 @@ int enqueue_eval(ude_handle* h, const double* d_theta, double* d_loss, double* d
     const long long pmb = (long long)D.d * h->n_cols;
     const long long slo = D.has_series_param ? D.off_series_param : -1, shi = D.has_series_param ? slo + h->n_series : -1;
     const bool use_comm = h->comm != nullptr;
-    double* gp = use_comm ? h->d_red.p : (want_grad ? d_grad + pmb : h->d_red.p);
-    double* lp = use_comm ? h->d_red.p + D.n_pm : d_loss;
+    // with a communicator the reduce buffer is [loss | shared process-model gradient]: the per-series vector (which
+    // must be the tail of process_model) is rank-local and stays out of the exchange
+    const long long n_shared = D.has_series_param ? D.off_series_param : D.n_pm;
+    double* gp = use_comm ? h->d_red.p + 1 : (want_grad ? d_grad + pmb : h->d_red.p + 1);
+    double* lp = use_comm ? h->d_red.p : d_loss;
     const int nb = (int)((D.n_pm + 1 + 31) / 32);
     // rank r > 0 must not add the regulariser again: only rank 0 carries it (host passes reg_weight = 0 elsewhere)
     ude_finalize_single<<<nb, dim3(32, 8), 0, s>>>(h->d_block_part.p, grid, D.n_pm, d_theta + pmb, D.off_w1, n_w1, D.off_w2, n_w2,
                                                    slo, shi, h->d_reg_weight.p, gp, lp, 0);
     UDE_CUDA_TRY(h, cudaGetLastError());
     if (use_comm) {
-      int rc = g_nccl.AllReduce(h->d_red.p, h->d_red.p, (size_t)D.n_pm + 1, /*ncclFloat64*/ 8, /*ncclSum*/ 0, h->comm, s);
+      int rc = g_nccl.AllReduce(h->d_red.p, h->d_red.p, (size_t)n_shared + 1, /*ncclFloat64*/ 8, /*ncclSum*/ 0, h->comm, s);
       if (rc != 0) return fail(h, UDE_ERR_NCCL, std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
       const int nb2 = (int)((D.n_pm + 1 + 255) / 256);
-      ude_scatter_reduced<<<nb2, 256, 0, s>>>(h->d_red.p, D.n_pm, slo, shi, want_grad ? d_grad + pmb : h->d_red.p, d_loss);
+      ude_scatter_reduced<<<nb2, 256, 0, s>>>(h->d_red.p, D.n_pm, slo, shi, want_grad ? d_grad + pmb : nullptr, d_loss);
       UDE_CUDA_TRY(h, cudaGetLastError());
     }
   } else {

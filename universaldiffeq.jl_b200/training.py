@@ -1,0 +1,270 @@
+"""Host-side mirror of the reference's loss constructors and training driver for the hot path.
+
+  errors_to_matrix, conditional_likelihood   /root/reference/src/LossFunctionConstructors.jl:4-98, :347-404
+  derivative_matching_loss                   :161-192, :500-540
+  shooting_loss / multiple_shooting_loss     :196-305, :545-708        (+ *_states :237-258, :310-341, :604-631, :711-756)
+  default loss (init_loss)                   src/helpers.jl:16-76, src/MultipleTimeSeries.jl:51-157
+  train!, gradient_descent!, default_options src/Optimizers.jl:12-39, :242-258, :352-570, :578-742
+Each constructor returns a finalized Problem; the loss closure + Zygote pullback of the reference is
+Engine(problem).loss_grad.  Adam follows Optimisers.jl.
+"""
+from __future__ import annotations
+
+import copy
+from typing import Optional
+
+import numpy as np
+
+from . import problem as P
+from ._capi import Engine
+from .models import UDE
+
+
+def errors_to_matrix(error, dims):
+    """src/LossFunctionConstructors.jl:4-15: scalar -> e*I, vector -> diag(e), matrix -> itself."""
+    e = np.asarray(error, dtype=np.float64)
+    if e.ndim == 0:
+        return float(e) * np.eye(dims)
+    if e.ndim == 1 and e.shape[0] == dims:
+        return np.diag(e)
+    if e.shape == (dims, dims):
+        return e
+    raise ValueError("error term needs to be a float, vector or square matrix")
+
+
+def _n_series(model: UDE) -> int:
+    return len(model.starts) if model.multi else 1
+
+
+def _skip_mask(model: UDE, t_skip):
+    if t_skip is None or (np.isscalar(t_skip) and np.isnan(t_skip)):
+        return None
+    m = np.zeros(model.data.shape[1], dtype=np.uint8)
+    if not model.multi:
+        # LFC.jl:82: the interval whose END index t (1-based) equals t_skip is left out
+        idx = int(t_skip) - 1
+        if 1 <= idx < m.shape[0]:
+            m[idx] = 1
+    else:
+        # src/MultipleTimeSeries.jl:101: intervals STARTING at time t_skip (per series) are left out
+        for s, n in zip(model.starts, model.lengths):
+            tt = model.times[s:s + n]
+            for j in np.nonzero(np.isclose(tt[:-1], t_skip))[0]:
+                m[s + j + 1] = 1
+    return m
+
+
+def conditional_likelihood(model: UDE, regularization_weight=0.0, observation_error=0.025, process_error=0.025, t_skip=None) -> P.Problem:
+    p = model.base_problem()
+    p.loss_kind = P.LOSS_STATE_SPACE
+    p.A = np.linalg.inv(errors_to_matrix(observation_error, model.d))
+    p.B = np.linalg.inv(errors_to_matrix(process_error, model.d))
+    p.skip_mask = _skip_mask(model, t_skip)
+    p.reg_weight = regularization_weight * model.weights["regularization"]
+    return p.finalize()
+
+
+def default_loss(model: UDE, t_skip=None) -> P.Problem:
+    """model.loss_function of the reference: sum_t w_o |y-uhat|^2/N + sum_{t>=2} (T/dt) w_p |uhat_t - F(uhat_{t-1})|^2/N^2 + reg."""
+    p = model.base_problem()
+    p.loss_kind = P.LOSS_STATE_SPACE
+    p.proc_inv_dt = True
+    p.obs_scale = model.weights["observation"] / model.obs_divisor
+    p.proc_scale = model.T * model.weights["process"] / float(model.N) ** 2
+    p.skip_mask = _skip_mask(model, t_skip)
+    # multi-series: the regulariser sits inside single_loss and is counted once per series (src/MultipleTimeSeries.jl:77-79)
+    p.reg_weight = model.weights["regularization"] * _n_series(model)
+    return p.finalize()
+
+
+def multiple_shooting_loss(model: UDE, regularization_weight=0.0, pred_length=5) -> P.Problem:
+    p = model.base_problem()
+    p.loss_kind = P.LOSS_MULTI_SHOOT
+    p.pred_length = int(pred_length)
+    p.preroll_eps = 0.0 if model.multi else 1e-6      # LFC.jl:268 vs :646
+    p.reg_weight = regularization_weight * model.weights["regularization"]
+    return p.finalize()
+
+
+def shooting_loss(model: UDE, regularization_weight=0.0) -> P.Problem:
+    p = model.base_problem()
+    p.loss_kind = P.LOSS_SHOOT
+    p.shoot_first_scored = 2                           # LFC.jl:220-222, :572-574: `for i in 2:length(times)` over times[2:end]
+    if model.multi:
+        p.shoot_from_theta = False                     # LFC.jl:563: u0 = data[:, start]
+        p.shoot_weight = 1.0
+        p.reg_weight = regularization_weight * model.weights["regularization"]
+    else:
+        p.shoot_from_theta = True
+        p.shoot_weight = model.T * model.weights["process"] / float(model.N) ** 2      # ProcessMSE with dt = 1
+        p.reg_weight = model.weights["regularization"]                               # LFC.jl:225: not scaled by train!'s weight
+    return p.finalize()
+
+
+def smooth_derivs(u, t, lam_grid=None):
+    """Host pre-step of derivative matching (LFC.jl:161-171): a penalised smoother per state with GCV-chosen weight and
+    its time derivative.  The reference calls RegularizationTools.RegularizationSmooth (third-party, not in
+    /root/reference); this is a second-difference Tikhonov smoother with the same role.  Not on the GPU hot path."""
+    u = np.asarray(u, dtype=np.float64); t = np.asarray(t, dtype=np.float64)
+    n = t.shape[0]
+    if n < 4:
+        return u.copy(), np.gradient(u, t, axis=1) if n > 1 else np.zeros_like(u)
+    D = np.zeros((n - 2, n))
+    for i in range(n - 2):
+        h0, h1 = t[i + 1] - t[i], t[i + 2] - t[i + 1]
+        D[i, i], D[i, i + 1], D[i, i + 2] = 2 / (h0 * (h0 + h1)), -2 / (h0 * h1), 2 / (h1 * (h0 + h1))
+    DtD = D.T @ D
+    lam_grid = np.logspace(-8, 2, 41) * (t[-1] - t[0]) ** 4 if lam_grid is None else lam_grid
+    us, du = np.zeros_like(u), np.zeros_like(u)
+    for j in range(u.shape[0]):
+        best = None
+        for lam in lam_grid:
+            Hm = np.linalg.solve(np.eye(n) + lam * DtD, np.eye(n))
+            fit = Hm @ u[j]
+            gcv = n * np.sum((u[j] - fit) ** 2) / max(n - np.trace(Hm), 1e-9) ** 2
+            if best is None or gcv < best[0]:
+                best = (gcv, fit)
+        us[j] = best[1]
+        du[j] = np.gradient(best[1], t)
+    return us, du
+
+
+def derivative_matching_loss(model: UDE, regularization_weight=0.0, d=12, remove_ends=0) -> P.Problem:
+    p = model.base_problem()
+    p.loss_kind = P.LOSS_DERIV_MATCH
+    p.remove_ends = int(remove_ends)
+    us, du = np.zeros_like(model.data), np.zeros_like(model.data)
+    starts = model.starts if model.multi else [0]
+    lengths = model.lengths if model.multi else [model.data.shape[1]]
+    for s, n in zip(starts, lengths):
+        us[:, s:s + n], du[:, s:s + n] = smooth_derivs(model.data[:, s:s + n], model.times[s:s + n])
+    p.dm_u, p.dm_dudt = us, du
+    p.reg_weight = regularization_weight * model.weights["regularization"]
+    return p.finalize()
+
+
+def default_options(loss_function):
+    """src/Optimizers.jl:242-258."""
+    return {"conditional likelihood": dict(step_size=0.025, maxiter=500)}.get(loss_function, dict(step_size=0.05, maxiter=500))
+
+
+def build_problem(model: UDE, loss_function, regularization_weight=0.0, loss_options=None, t_skip=None) -> P.Problem:
+    o = dict(loss_options or {})
+    if loss_function == "conditional likelihood":
+        return conditional_likelihood(model, regularization_weight, o.get("observation_error", 0.025), o.get("process_error", 0.025), t_skip)
+    if loss_function in ("derivative matching", "gradient matching", "smooth gradient matching"):
+        return derivative_matching_loss(model, regularization_weight, d=o.get("d", 12), remove_ends=o.get("remove_ends", 0))
+    if loss_function == "shooting":
+        return shooting_loss(model, regularization_weight)
+    if loss_function == "multiple shooting":
+        return multiple_shooting_loss(model, regularization_weight, o.get("pred_length", 5))
+    if loss_function == "default":
+        return default_loss(model, t_skip)
+    raise ValueError("Select a valid loss function. The CUDA hot path implements 'conditional likelihood', 'derivative matching', "
+                     "'shooting', 'multiple shooting' (and 'default' = model.loss_function); 'marginal likelihood', 'neural "
+                     "gradient matching' and 'spline gradient matching' are outside its scope (SURVEY.md 8f).")
+
+
+def adam_host(engine: Engine, theta, step_size, maxiter, verbose=False, callback=None):
+    """Optimisers.jl Adam on the host, one ude_loss_grad call per iteration (what `train!` does through Optimization.solve)."""
+    th = np.array(theta, dtype=np.float64, copy=True)
+    m = np.zeros_like(th); v = np.zeros_like(th)
+    trace = []
+    for it in range(1, int(maxiter) + 1):
+        L, g = engine.loss_grad(th)
+        trace.append(L.copy())
+        if verbose:
+            print(round(float(L.sum()), 3), end=" ", flush=True)     # src/Optimizers.jl:480-483
+        if callback is not None and callback(th, L):
+            break
+        m = 0.9 * m + 0.1 * g
+        v = 0.999 * v + 0.001 * g * g
+        th -= step_size * (m / (1 - 0.9 ** it)) / (np.sqrt(v / (1 - 0.999 ** it)) + 1e-8)
+    return th, np.array(trace)
+
+
+def train_(model: UDE, loss_function="derivative matching", optimizer="ADAM", regularization_weight=0.0, verbose=True,
+           loss_options=None, optim_options=None, t_skip=None, device=0, on_device: Optional[bool] = None):
+    """train!(model; ...) (src/Optimizers.jl:352-570, :578-742) on the CUDA hot path.  Mutates model.parameters.
+    on_device=True keeps theta, Adam moments and the gradient on the GPU for all iterations;
+    the default does so whenever no per-iteration printing is requested."""
+    if optimizer != "ADAM":
+        raise ValueError("only optimizer='ADAM' is routed to the CUDA path (BFGS would consume the same loss/grad entry point)")
+    prob = build_problem(model, loss_function, regularization_weight, loss_options, t_skip)
+    opts = dict(default_options(loss_function)); opts.update(optim_options or {})
+    on_device = (not verbose) if on_device is None else on_device
+    with Engine(prob, device=device) as eng:
+        if on_device:
+            theta, trace = eng.adam(model.parameters, opts["step_size"], opts["maxiter"])
+        else:
+            theta, trace = adam_host(eng, model.parameters, opts["step_size"], opts["maxiter"], verbose=verbose)
+        model.parameters = theta
+        # states after training (src/Optimizers.jl:536-550): trajectories re-solved with the fitted parameters
+        if loss_function in ("shooting", "multiple shooting"):
+            model.uhat[:, :] = eng.forward(theta)
+        elif loss_function in ("derivative matching", "gradient matching", "smooth gradient matching"):
+            model.uhat[:, :] = prob.dm_u
+    model.extra["loss_trace"] = trace
+    return None
+
+
+def gradient_descent_(model: UDE, step_size=0.05, maxiter=500, verbose=False, device=0):
+    """gradient_descent!(model) (src/Optimizers.jl:12-39): Adam on model.loss_function (the default MSE state-space loss)."""
+    return train_(model, "default", verbose=verbose, optim_options=dict(step_size=step_size, maxiter=maxiter), device=device)
+
+
+def predictions(model: UDE, device=0):
+    """One-step-ahead predictions F(uhat_{t-1}) for every column (src/ModelTesting.jl:181-195)."""
+    prob = default_loss(model)
+    with Engine(prob, device=device) as eng:
+        return eng.forward(model.parameters)
+
+
+def forecast(model: UDE, u0, t0, times, series=0, device=0):
+    """forecast(UDE, u0, t0, times) (src/ModelTesting.jl:541-571) with the extrapolation damping of init_forecast
+    (src/ProcessModels.jl:2-25; l, extrap_rho from the constructor defaults).  Each interval is one segment on the GPU."""
+    times = np.asarray(times, dtype=np.float64)
+    assert np.all(times > t0), "t0 is greater than the first time point in times"
+    d, n = model.d, times.shape[0]
+    l, rho = model.extra.get("l", 0.25), model.extra.get("extrap_rho", 0.1)
+    uh = model.uhat
+    if model.multi:
+        s0, ln = int(model.starts[series]), int(model.lengths[series])
+        uh = uh[:, s0:s0 + ln]
+    umax, umin, umean = uh.max(axis=1), uh.min(axis=1), uh.mean(axis=1)
+    # one two-column series per forecast interval; column 0 of series j is filled with the running state
+    m2 = copy.copy(model)
+    tt = np.concatenate([[t0], times])
+    m2.times = np.stack([tt[:-1], tt[1:]], axis=1).reshape(-1)
+    m2.data = np.zeros((d, 2 * n), order="F")
+    m2.multi = True
+    m2.starts = np.arange(n, dtype=np.int64) * 2
+    m2.lengths = np.full(n, 2, dtype=np.int64)
+    if model.cov:
+        nc, off, kt, kx = model.cov
+        blk = slice(series * nc, series * nc + nc + 1) if model.multi else slice(0, nc + 1)
+        o = off[blk]
+        seg_t, seg_x = kt[o[0]:o[-1]], kx[o[0]:o[-1]]
+        m2.cov = (nc, np.concatenate([[0], np.tile(np.diff(o), n).cumsum()]).astype(np.int64), np.tile(seg_t, n), np.tile(seg_x, n))
+    pr = m2.base_problem()
+    pr.loss_kind = P.LOSS_STATE_SPACE
+    if pr.has_series_param:
+        raise NotImplementedError("forecast with per-series parameters")
+    pr.finalize()
+    theta = np.concatenate([np.zeros(d * 2 * n), model.process_model])
+    out = np.zeros((n, d + 1))
+    x = np.asarray(u0, dtype=np.float64).copy()
+    with Engine(pr, device=device) as eng:
+        for j in range(n):
+            theta[d * 2 * j: d * 2 * j + d] = x
+            pred = eng.forward(theta)[:, 2 * j + 1]
+            du = pred - x
+            hi, lo = x > umax, x < umin
+            span = umax - umin
+            w = np.exp(-0.5 / l ** 2 * ((x - umax) / span) ** 2)
+            du = np.where(hi, w * du - rho * (1 - w) * (x - umean), du)
+            w = np.exp(-0.5 / l ** 2 * ((x - umin) / span) ** 2)
+            du = np.where(lo, w * du - (1 - w) * rho * (x - umean), du)
+            x = x + du
+            out[j, 0], out[j, 1:] = times[j], x
+    return out
