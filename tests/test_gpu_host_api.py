@@ -1,0 +1,72 @@
+"""train! / gradient_descent! / leave_future_out through the host-side mirror on the GPU (reference tests:
+test/UDETests.jl:41-47, test/MultiUDE.jl:30-36, test/cross_validation.jl:36 -- smoke tests there; here every result is
+compared with the same optimiser driven by oracle gradients)."""
+import numpy as np
+import pandas as pd
+import pytest
+
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _lv_frame(ude, n=22, seed=3):
+    Y, ts = ude.synthetic.lotka_volterra_data(np.random.default_rng(seed), 1, n)
+    return pd.DataFrame({"time": ts, "x1": Y[0, 0], "x2": Y[0, 1]})
+
+
+def _oracle_adam(prob, theta, step, iters):
+    th = theta.copy(); m = np.zeros_like(th); v = np.zeros_like(th)
+    for it in range(1, iters + 1):
+        _, g = oracle.loss_grad(prob, th)
+        m = 0.9 * m + 0.1 * g; v = 0.999 * v + 0.001 * g * g
+        th = th - step * (m / (1 - 0.9 ** it)) / (np.sqrt(v / (1 - 0.999 ** it)) + 1e-8)
+    return th
+
+
+@pytest.mark.parametrize("loss_function", ["conditional likelihood", "multiple shooting", "shooting", "derivative matching"])
+@pytest.mark.parametrize("on_device", [True, False])
+def test_train_matches_oracle_adam(ude, loss_function, on_device):
+    df = _lv_frame(ude)
+    _, p = ude.SimpleNeuralNetwork(2, 1, seed=123)
+    m = ude.CustomDerivatives(df, ude.LV_UDE, {"NN": p, "r": 1.0, "m": 0.5, "theta": 0.5})        # test/UDETests.jl:20-31
+    m.parameters[: 2 * m.N] = m.data.reshape(-1, order="F")
+    theta0 = m.parameters.copy()
+    prob = ude.build_problem(m, loss_function, 0.0)
+    ude.train_(m, loss_function=loss_function, optimizer="ADAM", verbose=False, optim_options=dict(maxiter=4), on_device=on_device)
+    ref = _oracle_adam(prob, theta0, ude.training.default_options(loss_function)["step_size"], 4)
+    pmb = prob.pm_base(0)
+    assert np.max(np.abs(m.parameters[pmb:] - ref[pmb:])) < 1e-8 * max(1.0, np.max(np.abs(ref[pmb:])))
+    if loss_function == "conditional likelihood":
+        assert np.max(np.abs(m.parameters[:pmb] - ref[:pmb])) < 1e-8
+    elif loss_function in ("shooting", "multiple shooting"):      # uhat is overwritten with the fitted trajectories
+        assert np.max(np.abs(m.uhat - oracle.forward(prob, ref))) < 1e-7
+
+
+def test_multinode_default_loss_and_gradient_descent(ude):
+    df = _lv_frame(ude, n=15)
+    dfm = pd.concat([df.assign(series=1), df.iloc[:11].assign(series=2), df.iloc[:7].assign(series=3)])
+    X = pd.DataFrame({"time": np.tile(np.linspace(0, 3, 9), 3), "series": np.repeat([1, 2, 3], 9), "X": np.random.default_rng(0).normal(size=27)})
+    m = ude.MultiNODE(dfm, X, hidden_units=10, seed=1)
+    theta0 = m.parameters.copy()
+    prob = ude.default_loss(m)
+    ude.gradient_descent_(m, step_size=0.05, maxiter=3)
+    ref = _oracle_adam(prob, theta0, 0.05, 3)
+    assert np.max(np.abs(m.parameters - ref)) < 1e-8
+
+
+def test_leave_future_out_batched_equals_serial(ude):
+    """k folds as ONE batched handle == k separate fits (src/CrossValidation.jl:17-45 runs them under Threads.@threads)."""
+    df = _lv_frame(ude, n=20)
+    _, p = ude.SimpleNeuralNetwork(2, 1, seed=123)
+    m = ude.CustomDerivatives(df, ude.LV_UDE_ABS, {"NN": p, "r": 0.1, "k": 10.1, "m": 0.1, "theta": 0.1})
+    opts = dict(maxiter=5, step_size=0.025)
+    models, tr, te, fc, trace = ude.leave_future_out_batched(m, k=3, skip=1, loss_function="conditional likelihood", optim_options=opts)
+    training = lambda mi: ude.train_(mi, loss_function="conditional likelihood", verbose=False, optim_options=opts)
+    tr2, te2, fc2 = ude.leave_future_out(m, training, 3)
+    assert [len(t) for t in tr] == [19, 18, 17] and [len(t) for t in te] == [1, 2, 3]
+    for a, b in zip(fc, fc2):
+        assert np.allclose(a.to_numpy(), b.to_numpy(), rtol=1e-9, atol=1e-12)
+    by_h, _ = ude.summarize_leave_future_out(m, te, fc)
+    assert len(by_h) == 3 and np.all(np.isfinite(by_h["mean_absolute_error"]))
+    assert trace.shape == (5, 3) and np.all(np.diff(trace[:, 0]) < 0)        # the loss goes down

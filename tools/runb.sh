@@ -1,4 +1,4 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python -m pytest tests -m gpu -x -q 2>&1 | tail -4
 for cfg in "" "--lanes 8 --hpl 4"; do
 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e $cfg > gpurun_out/b.json 2> gpurun_out/b.err
 python -c "
