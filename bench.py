@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--substeps", type=int, default=4)
     ap.add_argument("--lanes", type=int, default=0)
     ap.add_argument("--hpl", type=int, default=0)
+    ap.add_argument("--ws", type=int, default=0, help="0 auto, 1 register-resident weights, 2 shared-memory weights")
     ap.add_argument("--cpu-sample", type=int, default=0, help="series in the CPU-oracle sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -198,7 +199,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     prob, theta0, name = build_problem(ude, args, rank)
-    eng = ude.Engine(prob, device=local, lanes_per_segment=args.lanes, hidden_per_lane=args.hpl)
+    eng = ude.Engine(prob, device=local, lanes_per_segment=args.lanes, hidden_per_lane=args.hpl, weights_in_smem=args.ws)
     if world > 1:
         idt = torch.zeros(128, dtype=torch.uint8, device=dev)
         if rank == 0:
@@ -206,7 +207,7 @@ def main():
         dist.broadcast(idt, 0)
         eng.comm_init(bytes(idt.cpu().numpy().tobytes()), world, rank)
         if rank != 0:   # the regulariser is a function of the shared parameters: count it once (rank 0)
-            prob.reg_weight[:] = 0.0
+            prob.reg_weight = np.zeros_like(prob.reg_weight)
             eng._check(eng.lib.ude_set_model_weights(eng.handle, prob.obs_scale.ctypes.data, prob.proc_scale.ctypes.data,
                                                      prob.shoot_weight.ctypes.data, prob.reg_weight.ctypes.data))
     steps_per_eval = eng.steps_per_eval()

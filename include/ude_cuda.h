@@ -86,7 +86,8 @@ typedef struct ude_desc {
   double B[UDE_MAX_D * UDE_MAX_D];                  /* process weight (Sigma_proc^-1) */
   int32_t lanes_per_segment;  /* 0 = choose; else force the sub-warp group size G (tuning / tests) */
   int32_t hidden_per_lane;    /* 0 = choose */
-  int32_t reserved[6];
+  int32_t weights_in_smem;    /* 0 = choose; 1 = force register-resident weights; 2 = force shared-memory weights */
+  int32_t reserved[5];
 } ude_desc;
 
 int ude_abi_version(void);

@@ -44,7 +44,7 @@ class UdeDesc(C.Structure):
         ("shoot_first_scored", C.c_int32), ("remove_ends", C.c_int32),
         ("preroll_eps", C.c_double),
         ("A", C.c_double * (MAX_D * MAX_D)), ("B", C.c_double * (MAX_D * MAX_D)),
-        ("lanes_per_segment", C.c_int32), ("hidden_per_lane", C.c_int32), ("reserved", C.c_int32 * 6),
+        ("lanes_per_segment", C.c_int32), ("hidden_per_lane", C.c_int32), ("weights_in_smem", C.c_int32), ("reserved", C.c_int32 * 5),
     ]
 
 
@@ -121,7 +121,7 @@ def _ptr(a: Optional[np.ndarray]):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
-def make_desc(p: Problem, device: int = 0, lanes_per_segment: int = 0, hidden_per_lane: int = 0) -> UdeDesc:
+def make_desc(p: Problem, device: int = 0, lanes_per_segment: int = 0, hidden_per_lane: int = 0, weights_in_smem: int = 0) -> UdeDesc:
     d = UdeDesc()
     d.abi_version = ABI_VERSION
     d.struct_bytes = C.sizeof(UdeDesc)
@@ -144,6 +144,7 @@ def make_desc(p: Problem, device: int = 0, lanes_per_segment: int = 0, hidden_pe
         d.B[k] = B[k]
     d.lanes_per_segment = lanes_per_segment
     d.hidden_per_lane = hidden_per_lane
+    d.weights_in_smem = weights_in_smem
     return d
 
 
@@ -172,11 +173,11 @@ def measure_fp64_peak(device: int = 0) -> float:
 class Engine:
     """One ude_handle: the batched loss-and-gradient evaluator of a finalized Problem on one GPU."""
 
-    def __init__(self, p: Problem, device: int = 0, lanes_per_segment: int = 0, hidden_per_lane: int = 0):
+    def __init__(self, p: Problem, device: int = 0, lanes_per_segment: int = 0, hidden_per_lane: int = 0, weights_in_smem: int = 0):
         self.lib = load_library()
         self.problem = p
         self.handle = C.c_void_p()
-        desc = make_desc(p, device, lanes_per_segment, hidden_per_lane)
+        desc = make_desc(p, device, lanes_per_segment, hidden_per_lane, weights_in_smem)
         rc = self.lib.ude_create(C.byref(desc), C.byref(self.handle))
         if rc != UDE_OK:
             raise UdeError(rc, self.lib.ude_last_error(None).decode())

@@ -104,7 +104,7 @@ struct ude_handle {
   int64_t n_tasks = 0, steps_per_eval = 0, max_steps_per_task = 0;
   int grid_grad = 0, grid_fwd = 0;
   long long stash_rows_per_warp = 0;
-  size_t smem_bytes = 0;
+  size_t smem_bytes = 0, smem_bytes_fwd = 0;
   // multi-GPU
   void* comm = nullptr;
   int n_ranks = 1, rank = 0;
@@ -232,6 +232,8 @@ int build_plan(ude_handle* h) {
     if (e.solver != D.solver || e.lk != lk || e.G * e.HPL < D.nn_hidden) continue;
     if (D.lanes_per_segment > 0 && e.G != D.lanes_per_segment) continue;
     if (D.hidden_per_lane > 0 && e.HPL != D.hidden_per_lane) continue;
+    if (D.weights_in_smem == 1 && e.ws_doubles != 0) continue;
+    if (D.weights_in_smem == 2 && e.ws_doubles == 0) continue;
     const KernelEntry*& slot = e.grad ? best_g : best_f;
     auto key = [](const KernelEntry* k) { return (long long)k->G * k->HPL * 1000 + k->priority; };
     if (!slot || key(&e) < key(slot)) slot = &e;
@@ -309,15 +311,19 @@ int build_plan(ude_handle* h) {
   const int stages = D.solver == UDE_TSIT5 ? 6 : 4;
   // dynamic smem: block partial row (single model) padded to 16 B + per-warp two-step TMA staging ring of the stash
   const size_t red_doubles = (size_t)(((h->n_models == 1 ? D.n_pm + 1 : 0) + 1) / 2 * 2);
-  const size_t stage_doubles = (size_t)(ude::kBlockThreads / 32) * 2 * (size_t)stages * h->k_grad->rows_per_stage * 32;
-  h->smem_bytes = (red_doubles + stage_doubles) * sizeof(double);
-  for (const KernelEntry* k : {h->k_grad, h->k_fwd}) {
-    if (h->smem_bytes > 40 * 1024)
-      UDE_CUDA_TRY(h, cudaFuncSetAttribute(k->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
-  }
+  auto smem_for = [&](const KernelEntry* k) {
+    const size_t per_warp = (size_t)k->ws_doubles + (k->stage_ring ? 2 * (size_t)stages * k->rows_per_stage * 32 : 0);
+    return (red_doubles + (size_t)(ude::kBlockThreads / 32) * per_warp) * sizeof(double);
+  };
+  h->smem_bytes = smem_for(h->k_grad);
+  h->smem_bytes_fwd = smem_for(h->k_fwd);
+  if (h->smem_bytes > 40 * 1024)
+    UDE_CUDA_TRY(h, cudaFuncSetAttribute(h->k_grad->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+  if (h->smem_bytes_fwd > 40 * 1024)
+    UDE_CUDA_TRY(h, cudaFuncSetAttribute(h->k_fwd->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes_fwd));
   int occ_g = 0, occ_f = 0;
   UDE_CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessorWithFlags(&occ_g, h->k_grad->fn, ude::kBlockThreads, h->smem_bytes, 0));
-  UDE_CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessorWithFlags(&occ_f, h->k_fwd->fn, ude::kBlockThreads, h->smem_bytes, 0));
+  UDE_CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessorWithFlags(&occ_f, h->k_fwd->fn, ude::kBlockThreads, h->smem_bytes_fwd, 0));
   if (occ_g < 1 || occ_f < 1) return fail(h, UDE_ERR_CUDA, "kernel does not fit on an SM");
   const int wpb = ude::kBlockThreads / 32;
   const int64_t need_blocks = (h->n_tasks + wpb - 1) / wpb;
@@ -389,7 +395,7 @@ int enqueue_eval(ude_handle* h, const double* d_theta, double* d_loss, double* d
   void* args[] = {&P};
   const bool timed = h->ev_used < h->ev_cap;
   if (timed) UDE_CUDA_TRY(h, cudaEventRecord(h->ev0[h->ev_used], s));
-  UDE_CUDA_TRY(h, cudaLaunchKernel(k->fn, dim3(grid), dim3(ude::kBlockThreads), args, h->smem_bytes, s));
+  UDE_CUDA_TRY(h, cudaLaunchKernel(k->fn, dim3(grid), dim3(ude::kBlockThreads), args, want_grad ? h->smem_bytes : h->smem_bytes_fwd, s));
   if (timed) { UDE_CUDA_TRY(h, cudaEventRecord(h->ev1[h->ev_used], s)); ++h->ev_used; }
   const long long n_w1 = (long long)D.nn_hidden * D.nn_in, n_w2 = (long long)D.nn_out * D.nn_hidden;
   if (h->n_models == 1) {

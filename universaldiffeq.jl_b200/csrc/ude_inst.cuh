@@ -5,20 +5,22 @@
 #include "ude_registry.h"
 
 namespace ude {
-template <class R, int G, int HPL, int MINB, int SOLVER, int LK>
+template <class R, int G, int HPL, int MINB, int SOLVER, int LK, bool WS>
 void register_one(const char* name, int priority) {
-  kernel_registry().push_back(KernelEntry{R::KIND, R::D, R::NX, R::DIN, R::DOUT, G, HPL, SOLVER, LK, 1, Geo<R, G, HPL>::ROWS, priority,
-                                          (const void*)ude_seg_kernel<R, G, HPL, SOLVER, LK, true, MINB>, name});
-  kernel_registry().push_back(KernelEntry{R::KIND, R::D, R::NX, R::DIN, R::DOUT, G, HPL, SOLVER, LK, 0, Geo<R, G, HPL>::ROWS, priority,
-                                          (const void*)ude_seg_kernel<R, G, HPL, SOLVER, LK, false, MINB>, name});
+  using GG = Geo<R, G, HPL>;
+  const int wsd = WS ? G * GG::WREC2 * 2 : 0;
+  kernel_registry().push_back(KernelEntry{R::KIND, R::D, R::NX, R::DIN, R::DOUT, G, HPL, SOLVER, LK, 1, GG::ROWS, wsd, LK != LK_DM, priority,
+                                          (const void*)ude_seg_kernel<R, G, HPL, SOLVER, LK, true, MINB, WS>, name});
+  kernel_registry().push_back(KernelEntry{R::KIND, R::D, R::NX, R::DIN, R::DOUT, G, HPL, SOLVER, LK, 0, GG::ROWS, wsd, 0, priority,
+                                          (const void*)ude_seg_kernel<R, G, HPL, SOLVER, LK, false, MINB, WS>, name});
 }
-template <class R, int G, int HPL, int MINB>
+template <class R, int G, int HPL, int MINB, bool WS = false>
 void register_combo(const char* name, int priority) {
-  register_one<R, G, HPL, MINB, 0, LK_STATE>(name, priority);
-  register_one<R, G, HPL, MINB, 0, LK_TRAJ>(name, priority);
-  register_one<R, G, HPL, MINB, 0, LK_DM>(name, priority);
-  register_one<R, G, HPL, MINB, 1, LK_STATE>(name, priority);
-  register_one<R, G, HPL, MINB, 1, LK_TRAJ>(name, priority);
-  register_one<R, G, HPL, MINB, 1, LK_DM>(name, priority);
+  register_one<R, G, HPL, MINB, 0, LK_STATE, WS>(name, priority);
+  register_one<R, G, HPL, MINB, 0, LK_TRAJ, WS>(name, priority);
+  register_one<R, G, HPL, MINB, 0, LK_DM, WS>(name, priority);
+  register_one<R, G, HPL, MINB, 1, LK_STATE, WS>(name, priority);
+  register_one<R, G, HPL, MINB, 1, LK_TRAJ, WS>(name, priority);
+  register_one<R, G, HPL, MINB, 1, LK_DM, WS>(name, priority);
 }
 }  // namespace ude

@@ -18,6 +18,7 @@
 #include "ude_device.cuh"
 #include "ude_math.cuh"
 #include "ude_rhs.cuh"
+#include <type_traits>
 
 namespace ude {
 
@@ -44,6 +45,19 @@ struct Geo {
   static constexpr int NU = D + NX + (R::NEED_Y ? DOUT : 0);   // uniform doubles stashed per stage
   static constexpr int ROWS = HPL + (NU + G - 1) / G;          // 256-byte stash rows per stage
   static constexpr int SPW = 32 / G;                            // segments per warp
+  // shared-memory weight record of one lane (WS kernels): per owned hidden unit [W1 row | b1 | pad][W2 column | pad],
+  // both padded to an even count so every access is one LDS.128; the record stride is an odd number of 16-byte
+  // units, which spreads the G records of a warp over all banks (lanes of equal g broadcast).
+  static constexpr int DINP = (DIN + 1 + 1) / 2 * 2;            // inputs + the constant-1 bias input, even
+  static constexpr int DOUTP = (DOUT + 1) / 2 * 2;
+  static constexpr int HB2 = (DINP + DOUTP) / 2;                // double2 per hidden unit
+  static constexpr int WREC2 = (HPL * HB2) | 1;                 // double2 per lane record (odd)
+};
+
+template <class R, int HPL>
+struct LaneNetS {            // weights in shared memory, only the uniform output bias in registers
+  const double2* rec;
+  double b2[R::DOUT];
 };
 
 template <class R, int G, int HPL>
@@ -191,6 +205,147 @@ __device__ __forceinline__ void stage_backward(const LaneNet<R, HPL>& n, LaneGra
   for (int k = 0; k < R::D; ++k) ub[k] += xpart[k];
 }
 
+// ---- the same two routines with the lane's weights read from shared memory (LDS.128, two weights per load) -------
+// Used when the register-resident copy would push the kernel past the register file (H >= 32): the gradient
+// accumulators stay in registers, the weights are re-read each stage on the otherwise idle LSU pipe.
+template <class R, int G, int HPL>
+__device__ __forceinline__ void stage_forward(const LaneNetS<R, HPL>& n, const RhsCtx& ctx, const double* s_tab, int lane,
+                                              const double (&U)[R::D], const double* X, double t,
+                                              double (&du)[R::D], double (&hh)[HPL], double (&y)[R::DOUT]) {
+  using GG = Geo<R, G, HPL>;
+  double x[R::DIN];
+  R::input(U, X, t, ctx, x);
+  double xx[GG::DINP];
+#pragma unroll
+  for (int k = 0; k < GG::DINP; ++k) xx[k] = (k < R::DIN) ? x[k < R::DIN ? k : 0] : (k == R::DIN ? 1.0 : 0.0);
+  double z[HPL];
+#pragma unroll
+  for (int i = 0; i < HPL; ++i) z[i] = 0.0;
+#pragma unroll
+  for (int kp = 0; kp < GG::DINP / 2; ++kp) {
+#pragma unroll
+    for (int i = 0; i < HPL; ++i) {
+      const double2 w = n.rec[i * GG::HB2 + kp];
+      z[i] = fma(w.x, xx[2 * kp], z[i]);
+      z[i] = fma(w.y, xx[2 * kp + 1], z[i]);
+    }
+  }
+  ude_tanh_tab_vec<HPL>(z, hh, s_tab);
+  double part[GG::DOUTP];
+#pragma unroll
+  for (int o = 0; o < GG::DOUTP; ++o) part[o] = 0.0;
+#pragma unroll
+  for (int i = 0; i < HPL; ++i) {
+#pragma unroll
+    for (int op = 0; op < GG::DOUTP / 2; ++op) {
+      const double2 w = n.rec[i * GG::HB2 + GG::DINP / 2 + op];
+      part[2 * op] = fma(w.x, hh[i], part[2 * op]);
+      part[2 * op + 1] = fma(w.y, hh[i], part[2 * op + 1]);
+    }
+  }
+  double pr[R::DOUT];
+#pragma unroll
+  for (int o = 0; o < R::DOUT; ++o) pr[o] = part[o];
+  group_allreduce<G, R::DOUT>(pr, lane);
+#pragma unroll
+  for (int o = 0; o < R::DOUT; ++o) y[o] = pr[o] + n.b2[o];
+  R::combine(U, X, y, ctx, du);
+}
+
+template <class R, int G, int HPL>
+__device__ __forceinline__ void stage_backward(const LaneNetS<R, HPL>& n, LaneGrad<R, HPL>& gr, const RhsCtx& ctx, int lane,
+                                               const double (&U)[R::D], const double* X, double t,
+                                               const double (&hh)[HPL], const double (&y)[R::DOUT],
+                                               const double (&kb)[R::D], double (&ub)[R::D], double& gseries) {
+  using GG = Geo<R, G, HPL>;
+  double x[R::DIN];
+  R::input(U, X, t, ctx, x);
+  double yb[R::DOUT];
+  R::combine_vjp(U, X, y, ctx, kb, yb, ub, gr.sc, gseries);
+  double ybp[GG::DOUTP];
+#pragma unroll
+  for (int o = 0; o < GG::DOUTP; ++o) ybp[o] = (o < R::DOUT) ? yb[o < R::DOUT ? o : 0] : 0.0;
+  double hb[HPL], zb[HPL];
+#pragma unroll
+  for (int i = 0; i < HPL; ++i) hb[i] = 0.0;
+#pragma unroll
+  for (int op = 0; op < GG::DOUTP / 2; ++op) {
+#pragma unroll
+    for (int i = 0; i < HPL; ++i) {
+      const double2 w = n.rec[i * GG::HB2 + GG::DINP / 2 + op];
+      hb[i] = fma(w.x, ybp[2 * op], hb[i]);
+      hb[i] = fma(w.y, ybp[2 * op + 1], hb[i]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < HPL; ++i) zb[i] = hb[i] * fma(-hh[i], hh[i], 1.0);
+  double xpart[(R::D + 1) / 2 * 2];
+#pragma unroll
+  for (int k = 0; k < (R::D + 1) / 2 * 2; ++k) xpart[k] = 0.0;
+#pragma unroll
+  for (int kp = 0; kp < (R::D + 1) / 2; ++kp) {
+#pragma unroll
+    for (int i = 0; i < HPL; ++i) {
+      const double2 w = n.rec[i * GG::HB2 + kp];
+      xpart[2 * kp] = fma(w.x, zb[i], xpart[2 * kp]);
+      xpart[2 * kp + 1] = fma(w.y, zb[i], xpart[2 * kp + 1]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < HPL; ++i) {
+#pragma unroll
+    for (int o = 0; o < R::DOUT; ++o) gr.W2[o][i] = fma(yb[o], hh[i], gr.W2[o][i]);
+    gr.b1[i] += zb[i];
+#pragma unroll
+    for (int k = 0; k < R::DIN; ++k) gr.W1[i][k] = fma(zb[i], x[k], gr.W1[i][k]);
+  }
+#pragma unroll
+  for (int o = 0; o < R::DOUT; ++o) gr.b2[o] += yb[o];
+  double xr[R::D];
+#pragma unroll
+  for (int k = 0; k < R::D; ++k) xr[k] = xpart[k];
+  group_allreduce<G, R::D>(xr, lane);
+#pragma unroll
+  for (int k = 0; k < R::D; ++k) ub[k] += xr[k];
+}
+
+// fill this warp's shared-memory weight records (one per g) and the uniform leaves
+template <class R, int G, int HPL>
+__device__ __forceinline__ void load_net(const DevProblem& P, const double* __restrict__ pm, int lane, int g,
+                                         double* s_w, LaneNetS<R, HPL>& n, RhsCtx& ctx) {
+  using GG = Geo<R, G, HPL>;
+  __syncwarp();
+  double* rec = s_w + (size_t)g * GG::WREC2 * 2;
+  if (lane < G) {
+#pragma unroll
+    for (int i = 0; i < HPL; ++i) {
+      const int j = g + G * i;
+      const bool ok = j < P.H;
+      const int jj = ok ? j : 0;
+#pragma unroll
+      for (int k = 0; k < GG::DINP; ++k) {
+        double v = 0.0;
+        if (k < R::DIN) v = pm[P.off_w1 + jj + (long long)P.H * k];
+        else if (k == R::DIN) v = pm[P.off_b1 + jj];
+        rec[i * GG::HB2 * 2 + k] = ok ? v : 0.0;
+      }
+#pragma unroll
+      for (int o = 0; o < GG::DOUTP; ++o) {
+        double v = 0.0;
+        if (o < R::DOUT) v = pm[P.off_w2 + o + (long long)P.nn_out * jj];
+        rec[i * GG::HB2 * 2 + GG::DINP + o] = ok ? v : 0.0;
+      }
+    }
+  }
+  __syncwarp();
+  n.rec = reinterpret_cast<const double2*>(rec);
+#pragma unroll
+  for (int o = 0; o < R::DOUT; ++o) n.b2[o] = pm[P.off_b2 + o];
+#pragma unroll
+  for (int k = 0; k < R::NS; ++k) ctx.sc[k] = pm[P.off_scalar[k]];
+  ctx.time_scale = P.time_scale; ctx.time_shift = P.time_shift; ctx.series_param = 0.0;
+}
+
 // ---- stash rows: [HPL rows of h | ceil(NU/G) rows holding the uniform values spread over the group's lanes] --
 template <class R, int G, int HPL>
 __device__ __forceinline__ void stash_store(double* __restrict__ rec, int lane, int g, const double (&hh)[HPL],
@@ -223,8 +378,8 @@ __device__ __forceinline__ void stash_load(const double* __restrict__ rec, int l
 }
 
 // ---- one explicit RK step forward; GRAD: record every stage -------------------------------------------------
-template <class R, int G, int HPL, int SOLVER, bool GRAD>
-__device__ __forceinline__ void rk_forward(const DevProblem& P, const LaneNet<R, HPL>& n, const RhsCtx& ctx, const double* s_tab,
+template <class R, int G, int HPL, int SOLVER, bool GRAD, class NetT>
+__device__ __forceinline__ void rk_forward(const DevProblem& P, const NetT& n, const RhsCtx& ctx, const double* s_tab,
                                            int lane, int g, int series, CovCache<R::NX>& cur,
                                            double (&u)[R::D], double t, double hs, double* __restrict__ step_rec) {
   using T = Tab<SOLVER>;
@@ -260,8 +415,8 @@ __device__ __forceinline__ void rk_forward(const DevProblem& P, const LaneNet<R,
 
 // ---- its discrete adjoint; returns the step's initial state in U0 ---------------------------
 // step_rec points at the step's record in the warp's shared-memory staging buffer (filled by a TMA bulk load).
-template <class R, int G, int HPL, int SOLVER>
-__device__ __forceinline__ void rk_reverse(const LaneNet<R, HPL>& n, LaneGrad<R, HPL>& gr, const RhsCtx& ctx, int lane, int g,
+template <class R, int G, int HPL, int SOLVER, class NetT>
+__device__ __forceinline__ void rk_reverse(const NetT& n, LaneGrad<R, HPL>& gr, const RhsCtx& ctx, int lane, int g,
                                            double (&lam)[R::D], double t, double hs, const double* __restrict__ step_rec,
                                            double (&U0)[R::D], double& gseries) {
   using T = Tab<SOLVER>;
@@ -398,7 +553,7 @@ __device__ __forceinline__ void flush_block(const DevProblem& P, const LaneGrad<
 //   LK_DM     derivative matching: one RHS evaluation per column, no time stepping
 enum { LK_STATE = 0, LK_TRAJ = 1, LK_DM = 2 };
 
-template <class R, int G, int HPL, int SOLVER, int LK, bool GRAD, int MINB>
+template <class R, int G, int HPL, int SOLVER, int LK, bool GRAD, int MINB, bool WS>
 __global__ void __launch_bounds__(kBlockThreads, MINB) ude_seg_kernel(const DevProblem P) {
   using GG = Geo<R, G, HPL>;
   using T = Tab<SOLVER>;
@@ -413,7 +568,11 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) ude_seg_kernel(const DevP
   if (P.n_models == 1) for (long long k = threadIdx.x; k <= P.n_pm; k += blockDim.x) s_red[k] = 0.0;
   constexpr int kStepDoubles = T::S * GG::ROWS * 32;
   constexpr uint32_t kStepBytes = kStepDoubles * 8;
-  double* s_stage = s_dyn + ((P.n_models == 1 ? P.n_pm + 1 : 0) + 1) / 2 * 2 + (size_t)(threadIdx.x >> 5) * 2 * kStepDoubles;
+  constexpr int kWDoubles = WS ? G * GG::WREC2 * 2 : 0;      // this warp's weight records
+  constexpr int kStageDoubles = (GRAD && LK != LK_DM) ? 2 * kStepDoubles : 0;
+  double* s_warp = s_dyn + ((P.n_models == 1 ? P.n_pm + 1 : 0) + 1) / 2 * 2 + (size_t)(threadIdx.x >> 5) * (kWDoubles + kStageDoubles);
+  double* s_w = s_warp;
+  double* s_stage = s_warp + kWDoubles;
   uint64_t* bar = s_bar[threadIdx.x >> 5];
   if (GRAD && LK != LK_DM && (threadIdx.x & 31) == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); }
   uint32_t bar_phase = 0;      // bit b = parity the next wait on bar[b] expects
@@ -428,7 +587,7 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) ude_seg_kernel(const DevP
   constexpr long long rec_stride = kStepDoubles;
   const int S = P.substeps;
 
-  LaneNet<R, HPL> net;
+  typename std::conditional<WS, LaneNetS<R, HPL>, LaneNet<R, HPL>>::type net;
   LaneGrad<R, HPL> gr;
   RhsCtx ctx;
   zero_grad<R, HPL>(gr);
@@ -446,7 +605,8 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) ude_seg_kernel(const DevP
         zero_grad<R, HPL>(gr);
         loss = 0.0;
       }
-      load_net<R, G, HPL>(P, pm, g, net, ctx);
+      if constexpr (WS) load_net<R, G, HPL>(P, pm, lane, g, s_w, net, ctx);
+      else load_net<R, G, HPL>(P, pm, g, net, ctx);
       cur_model = model;
     }
     const bool is_null = (sg.flags & SEG_NULL) != 0;

@@ -30,7 +30,7 @@ MAX_SCALARS = 8
 
 
 def _f64(a, order="C"):
-    return np.ascontiguousarray(np.asarray(a, dtype=np.float64)) if order == "C" else np.asfortranarray(np.asarray(a, dtype=np.float64))
+    return np.array(a, dtype=np.float64, order=order, copy=True)
 
 
 def _i64(a):
