@@ -232,6 +232,7 @@ int build_plan(ude_handle* h) {
     if (e.solver != D.solver || e.lk != lk || e.G * e.HPL < D.nn_hidden) continue;
     if (D.lanes_per_segment > 0 && e.G != D.lanes_per_segment) continue;
     if (D.hidden_per_lane > 0 && e.HPL != D.hidden_per_lane) continue;
+    if (const char* want = getenv("UDE_KERNEL")) { if (*want && !strstr(e.name, want)) continue; }   // tuning aid: pick a specialisation by name
     if (D.weights_in_smem == 1 && e.ws_doubles != 0) continue;
     if (D.weights_in_smem == 2 && e.ws_doubles == 0) continue;
     const KernelEntry*& slot = e.grad ? best_g : best_f;
