@@ -56,14 +56,15 @@ def test_parity_group_shapes_node2(ude, g_hpl):
 
 
 @pytest.mark.parametrize("g_hpl,hidden,ws", [((4, 3), 12, 1), ((16, 2), 32, 1), ((8, 4), 32, 1), ((16, 2), 20, 1), ((8, 4), 7, 1),
-                                             ((16, 2), 32, 2), ((8, 4), 32, 2), ((8, 4), 19, 2)])
+                                             ((16, 2), 32, 2), ((8, 4), 32, 2), ((8, 4), 19, 2),
+                                             ((4, 8), 32, 0), ((4, 8), 27, 0), ((4, 8), 8, 0)])   # (4, 8) = the FP64 tensor-core (DMMA) kernel
 @pytest.mark.parametrize("loss", ["multi_shoot", "mse", "deriv_match"])
 def test_parity_group_shapes_c3(ude, g_hpl, hidden, ws, loss):
     """Every (lanes per segment, hidden units per lane, weight storage) specialisation of the C3 shape."""
     for solver in (0, 1):
         prob, theta = cases.make_case("node_d4x1", loss, solver, hidden=hidden, lengths=(30, 30, 7, 12, 1, 30, 26, 3), substeps=4)
         _check(prob, theta, ude, lanes_per_segment=g_hpl[0], hidden_per_lane=g_hpl[1], weights_in_smem=ws)
-    if loss == "mse":    # several models per handle: the per-warp weight records are reloaded at model boundaries
+    if loss == "mse" and g_hpl != (4, 8):    # several models per handle: the per-warp weight records are reloaded at model boundaries
         prob, theta = cases.make_case("node_d4x1", loss, 0, hidden=hidden, lengths=(9, 8, 7, 6, 5, 4), n_models=3)
         _check(prob, theta, ude, lanes_per_segment=g_hpl[0], hidden_per_lane=g_hpl[1], weights_in_smem=ws)
 

@@ -232,6 +232,7 @@ int build_plan(ude_handle* h) {
     if (e.solver != D.solver || e.lk != lk || e.G * e.HPL < D.nn_hidden) continue;
     if (D.lanes_per_segment > 0 && e.G != D.lanes_per_segment) continue;
     if (D.hidden_per_lane > 0 && e.HPL != D.hidden_per_lane) continue;
+    if (e.single_model_only && h->n_models != 1) continue;
     if (const char* want = getenv("UDE_KERNEL")) { if (*want && !strstr(e.name, want)) continue; }   // tuning aid: pick a specialisation by name
     if (D.weights_in_smem == 1 && e.ws_doubles != 0) continue;
     if (D.weights_in_smem == 2 && e.ws_doubles == 0) continue;
@@ -313,8 +314,7 @@ int build_plan(ude_handle* h) {
   // dynamic smem: block partial row (single model) padded to 16 B + per-warp two-step TMA staging ring of the stash
   const size_t red_doubles = (size_t)(((h->n_models == 1 ? D.n_pm + 1 : 0) + 1) / 2 * 2);
   auto smem_for = [&](const KernelEntry* k) {
-    const size_t per_warp = (size_t)k->ws_doubles + (k->stage_ring ? 2 * (size_t)stages * k->rows_per_stage * 32 : 0);
-    return (red_doubles + (size_t)(ude::kBlockThreads / 32) * per_warp) * sizeof(double);
+    return (red_doubles + (size_t)k->block_doubles + (size_t)(ude::kBlockThreads / 32) * (size_t)k->warp_doubles) * sizeof(double);
   };
   h->smem_bytes = smem_for(h->k_grad);
   h->smem_bytes_fwd = smem_for(h->k_fwd);

@@ -10,8 +10,10 @@ struct KernelEntry {
   int rhs_kind, d, n_cov, nn_in, nn_out;
   int G, HPL, solver, lk, grad;   // lk: 0 state-space, 1 trajectory (shooting kinds), 2 derivative matching
   int rows_per_stage;      // stash rows (256 B each) per RK stage
-  int ws_doubles;          // per-warp shared-memory weight records (0: weights live in registers)
-  int stage_ring;          // 1: the kernel uses the per-warp two-step TMA staging ring
+  int ws_doubles;          // per-warp shared-memory weight records (0: weights live in registers or in block fragments)
+  int block_doubles;       // per-block dynamic shared memory besides the partial row (MMA kernels: weight fragments)
+  int warp_doubles;        // per-warp dynamic shared memory (weight records + TMA staging ring + scratch tiles)
+  int single_model_only;   // MMA kernels keep one model's weights per block
   int priority;            // lower = preferred when several (G, HPL) fit
   const void* fn;
   const char* name;
