@@ -49,10 +49,12 @@ def test_parity_many_models(ude, loss):
     _check(prob, theta, ude)
 
 
-@pytest.mark.parametrize("g_hpl", [(4, 3), (16, 2)])
-def test_parity_group_shapes_node2(ude, g_hpl):
-    prob, theta = cases.make_case("node_d2", "multi_shoot", 0, hidden=10, lengths=(23, 11, 6, 31, 5, 1, 2, 16))
-    _check(prob, theta, ude, lanes_per_segment=g_hpl[0], hidden_per_lane=g_hpl[1])
+@pytest.mark.parametrize("g_hpl", [(4, 3), (16, 2), (4, 4)])      # (4, 4) = DMMA kernel, hidden padded to 16
+@pytest.mark.parametrize("loss", ["multi_shoot", "multi_shoot_preroll", "cond_lik", "shoot_data", "deriv_match"])
+def test_parity_group_shapes_node2(ude, g_hpl, loss):
+    for solver in (0, 1):
+        prob, theta = cases.make_case("node_d2", loss, solver, hidden=10, lengths=(23, 11, 6, 31, 5, 1, 2, 16), skip=(loss == "cond_lik"))
+        _check(prob, theta, ude, lanes_per_segment=g_hpl[0], hidden_per_lane=g_hpl[1])
 
 
 @pytest.mark.parametrize("g_hpl,hidden,ws", [((4, 3), 12, 1), ((16, 2), 32, 1), ((8, 4), 32, 1), ((16, 2), 20, 1), ((8, 4), 7, 1),

@@ -237,7 +237,8 @@ int build_plan(ude_handle* h) {
     if (D.weights_in_smem == 1 && e.ws_doubles != 0) continue;
     if (D.weights_in_smem == 2 && e.ws_doubles == 0) continue;
     const KernelEntry*& slot = e.grad ? best_g : best_f;
-    auto key = [](const KernelEntry* k) { return (long long)k->G * k->HPL * 1000 + k->priority; };
+    // priority first (set per specialisation from measurements), then the smallest padded hidden width
+    auto key = [](const KernelEntry* k) { return (long long)k->priority * 100000 + (long long)k->G * k->HPL; };
     if (!slot || key(&e) < key(slot)) slot = &e;
   }
   if (!best_g || !best_f) {

@@ -3,6 +3,6 @@
 namespace {
 using namespace ude;
 RegisterKernels reg([] {
-  register_mma_combo<4, 1, 4, 3>("node_d4x1_mma_h32", 9);
+  register_mma_combo<4, 1, 4, 3>("node_d4x1_mma_h32", 1);
 });
 }  // namespace

@@ -3,7 +3,7 @@
 namespace {
 using namespace ude;
 RegisterKernels reg([] {
-  register_combo<RhsNode<4, 1>, 16, 2, 3>("node_d4x1_g16h2", 2);
+  register_combo<RhsNode<4, 1>, 16, 2, 3>("node_d4x1_g16h2", 4);
   register_combo<RhsNode<4, 1>, 8, 4, 2>("node_d4x1_g8h4", 3);
   register_combo<RhsNode<4, 1>, 4, 3, 3>("node_d4x1_g4h3", 0);
 });

@@ -3,7 +3,7 @@
 namespace {
 using namespace ude;
 RegisterKernels reg([] {
-  register_combo<RhsNode<4, 1>, 8, 4, 2, true>("node_d4x1_g8h4_ws_b2", 1);
+  register_combo<RhsNode<4, 1>, 8, 4, 2, true>("node_d4x1_g8h4_ws_b2", 2);
   register_combo<RhsNode<4, 1>, 16, 2, 4, true>("node_d4x1_g16h2_ws_b4", 5);
 });
 }  // namespace

@@ -38,11 +38,12 @@ struct MmaGeo {
   static constexpr int KO = (D + 3) / 4;                 // output k-steps (h-bar = W2^T k-bar)
   static constexpr int MT = (NSLOT + 7) / 8;             // M tiles of the W1 gradient (slots)
   static constexpr int HS = 8 * HT + 4;                  // row stride of the [segment][hidden] tiles: conflict-free B reads
-  static constexpr int XS = MT * 8;                      // row stride of the [segment][slot] tile
+  static constexpr int XS = MT * 8 + 4;                  // row stride of the [segment][slot] tile (12, 20: conflict-free A reads)
   static constexpr int REC = 8 * HS + 8 * XS;            // doubles per stage record (h tile + x tile), multiple of 2
   static constexpr int NF1 = HT * KS, NF2 = HT * 2, NF3 = HT * KO, NF4 = HT * 2;
   static constexpr int NFRAG = NF1 + NF2 + NF3 + NF4;
-  static constexpr int SCRATCH = 8 * HS + 64;            // z-bar tile + k-bar tile
+  static constexpr int KSTR = 12;                        // row stride of the [segment][output] k-bar tile
+  static constexpr int SCRATCH = 8 * HS + 8 * KSTR;      // z-bar tile + k-bar tile
   static_assert(D <= 8, "state dimension above 8 needs a second output tile");
   __host__ __device__ static constexpr int outmap(int n) { return (n >> 1) + 4 * (n & 1); }   // N column -> output / slot
 };
@@ -242,15 +243,15 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) ude_mma_kernel(const DevP
         for (int t = 0; t < HT; ++t) {
           zb[t][0] = hb[t][0] * fma(-h[t][0], h[t][0], 1.0);
           zb[t][1] = hb[t][1] * fma(-h[t][1], h[t][1], 1.0);
-          *reinterpret_cast<double2*>(s_zs + r * MG::HS + 8 * t + 2 * c) = make_double2(zb[t][0], zb[t][1]);
+          s_zs[r * MG::HS + 8 * t + c] = zb[t][0]; s_zs[r * MG::HS + 8 * t + c + 4] = zb[t][1];
         }
-        s_ks[r * 8 + c] = kb[0]; s_ks[r * 8 + 4 + c] = kb[1];
+        s_ks[r * MG::KSTR + c] = kb[0]; s_ks[r * MG::KSTR + 4 + c] = kb[1];
         gb2[0] += kb[0]; gb2[1] += kb[1];
         // no stage record in this loss family: the h and x tiles are staged behind the k-bar tile
-        double* s_hs = s_ks + 64;
+        double* s_hs = s_ks + 8 * MG::KSTR;
         double* s_xs = s_hs + 8 * MG::HS;
 #pragma unroll
-        for (int t = 0; t < HT; ++t) *reinterpret_cast<double2*>(s_hs + r * MG::HS + 8 * t + 2 * c) = make_double2(h[t][0], h[t][1]);
+        for (int t = 0; t < HT; ++t) { s_hs[r * MG::HS + 8 * t + c] = h[t][0]; s_hs[r * MG::HS + 8 * t + c + 4] = h[t][1]; }
 #pragma unroll
         for (int e = 0; e < KS; ++e) s_xs[r * MG::XS + slot[e]] = xs[e];
         __syncwarp();
@@ -260,7 +261,7 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) ude_mma_kernel(const DevP
           double aX[MG::MT];
 #pragma unroll
           for (int m = 0; m < MG::MT; ++m) aX[m] = s_xs[seg * MG::XS + r + 8 * m];
-          const double aK = s_ks[seg * 8 + r];
+          const double aK = s_ks[seg * MG::KSTR + r];
 #pragma unroll
           for (int t = 0; t < HT; ++t) {
             const double bZ = s_zs[seg * MG::HS + 8 * t + r];
@@ -347,8 +348,7 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) ude_mma_kernel(const DevP
               if (lane == 0) bulk_wait_read<1>();
               __syncwarp();
 #pragma unroll
-              for (int t2 = 0; t2 < HT; ++t2)
-                *reinterpret_cast<double2*>(sbuf + r * MG::HS + 8 * t2 + 2 * c) = make_double2(h[t2][0], h[t2][1]);
+              for (int t2 = 0; t2 < HT; ++t2) { sbuf[r * MG::HS + 8 * t2 + c] = h[t2][0]; sbuf[r * MG::HS + 8 * t2 + c + 4] = h[t2][1]; }
 #pragma unroll
               for (int e = 0; e < KS; ++e) sbuf[8 * MG::HS + r * MG::XS + slot[e]] = xs[e];
               fence_async_smem();
@@ -463,10 +463,7 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) ude_mma_kernel(const DevP
             const double* __restrict__ sbuf = s_stage + b * MG::REC;
             double h[HT][2], xs[KS];
 #pragma unroll
-            for (int t = 0; t < HT; ++t) {
-              const double2 v = *reinterpret_cast<const double2*>(sbuf + r * MG::HS + 8 * t + 2 * c);
-              h[t][0] = v.x; h[t][1] = v.y;
-            }
+            for (int t = 0; t < HT; ++t) { h[t][0] = sbuf[r * MG::HS + 8 * t + c]; h[t][1] = sbuf[r * MG::HS + 8 * t + c + 4]; }
 #pragma unroll
             for (int e = 0; e < KS; ++e) xs[e] = sbuf[8 * MG::HS + r * MG::XS + slot[e]];
             // k-bar on my output slots (outputs o = c + 4j coincide with state slots e = j)
@@ -493,9 +490,9 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) ude_mma_kernel(const DevP
             for (int t = 0; t < HT; ++t) {
               zb[t][0] = hb[t][0] * fma(-h[t][0], h[t][0], 1.0);
               zb[t][1] = hb[t][1] * fma(-h[t][1], h[t][1], 1.0);
-              *reinterpret_cast<double2*>(s_zs + r * MG::HS + 8 * t + 2 * c) = make_double2(zb[t][0], zb[t][1]);
+              s_zs[r * MG::HS + 8 * t + c] = zb[t][0]; s_zs[r * MG::HS + 8 * t + c + 4] = zb[t][1];
             }
-            s_ks[r * 8 + c] = kb[0]; s_ks[r * 8 + 4 + c] = kb[1];
+            s_ks[r * MG::KSTR + c] = kb[0]; s_ks[r * MG::KSTR + 4 + c] = kb[1];
             gb2[0] += kb[0]; gb2[1] += kb[1];
             // x-bar = W1^T z-bar on the state slots
             double xa[2] = {0.0, 0.0}, xb[2] = {0.0, 0.0};
@@ -518,7 +515,7 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) ude_mma_kernel(const DevP
               double aX[MG::MT];
 #pragma unroll
               for (int m = 0; m < MG::MT; ++m) aX[m] = sbuf[8 * MG::HS + seg * MG::XS + r + 8 * m];
-              const double aK = s_ks[seg * 8 + r];
+              const double aK = s_ks[seg * MG::KSTR + r];
 #pragma unroll
               for (int t = 0; t < HT; ++t) {
                 const double bZ = s_zs[seg * MG::HS + 8 * t + r];
@@ -573,7 +570,8 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) ude_mma_kernel(const DevP
           for (int t = 0; t < HT; ++t) {
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-              const int hid = 8 * t + 2 * c + j;
+              const int ncol = 2 * c + j;              // tile column n holds the hidden unit of lane (n & 3), value (n >> 2)
+              const int hid = 8 * t + 2 * (ncol & 3) + (ncol >> 2);
               if (hid < P.H) {
 #pragma unroll
                 for (int m = 0; m < MG::MT; ++m) {
