@@ -130,7 +130,7 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_oracle_rate(ude, args, n_sample, threads, min_seconds=8.0, max_reps=50):
+def cpu_oracle_rate(ude, args, n_sample, threads, min_seconds=12.0, max_reps=400):
     """steps/s of the CPU oracle (loss + adjoint gradient) on an n_sample-series instance of the same workload."""
     from oracle import oracle
     prob, th, _ = build_problem(ude, args, 0, n_override=n_sample)
@@ -293,11 +293,12 @@ def main():
         kms = float(np.mean(kern_ms)) if len(kern_ms) else None
         flops_step = prob.flops_per_step()
         achieved = steps_per_eval * flops_step / (kms * 1e-3) * 1e-12 if kms else None
-        traffic = None
+        traffic = None      # dram__bytes_read+write of the dominant kernel per launch, from the committed ncu capture (per RK step x steps)
         tf = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tf):
             try:
-                traffic = json.load(open(tf)).get(args.config)
+                per_step = json.load(open(tf)).get(eng.kernel_name(), {}).get("dram_bytes_per_rk_step")
+                traffic = per_step * steps_per_eval if per_step else None
             except Exception:
                 traffic = None
         peaks = {}
@@ -332,7 +333,9 @@ def main():
 
 
 def eng_kernel_name(eng):
-    return "ude_seg_kernel (fused RK forward + loss + discrete adjoint)"
+    nm = eng.kernel_name()
+    fam = "ude_mma_kernel (FP64 DMMA m8n8k4)" if "mma" in nm else "ude_seg_kernel (DFMA + warp shuffles)"
+    return f"{fam} <{nm}>: fused RK forward + loss + discrete adjoint"
 
 
 if __name__ == "__main__":

@@ -122,6 +122,8 @@ int64_t ude_n_theta(const ude_handle* h);
 int64_t ude_n_models(const ude_handle* h);
 /* RK steps one loss evaluation integrates (unit of the throughput metric) and kernels launched per call */
 int64_t ude_steps_per_eval(const ude_handle* h);
+/* name of the compiled kernel specialisation the handle dispatches to (e.g. "node_d4x1_mma_h32") */
+const char* ude_kernel_name(ude_handle* h);
 int32_t ude_launches_per_eval(const ude_handle* h);
 
 /* loss[n_models] and grad[n_theta] (grad may be NULL: loss only). Synchronous, host buffers:

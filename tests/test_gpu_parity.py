@@ -140,3 +140,14 @@ def test_adam_matches_host_loop(ude):
         m = 0.9 * m + 0.1 * g; v = 0.999 * v + 0.001 * g * g
         th = th - 0.01 * (m / (1 - 0.9 ** it)) / (np.sqrt(v / (1 - 0.999 ** it)) + 1e-8)
     assert cases.relerr(th_dev, th) < 1e-9
+
+
+@pytest.mark.parametrize("loss", ["multi_shoot", "cond_lik", "mse", "shoot_theta"])
+@pytest.mark.parametrize("chunks", [2, 3, 7])
+def test_pipelined_host_path(ude, loss, chunks, monkeypatch):
+    """ude_loss_grad overlaps H2D(uhat chunk k+1) / kernel(chunk k) / D2H(grad chunk k-1); chunk borders fall inside
+    series here, so columns shared by two chunks exercise the upload/download bookkeeping."""
+    monkeypatch.setenv("UDE_HOST_CHUNKS", str(chunks))
+    for rhs, kw in (("node_d4x1", dict(hidden=32)), ("lv_ude", {})):
+        prob, theta = cases.make_case(rhs, loss, 0, lengths=(13, 2, 30, 7, 1, 22, 9, 16, 5, 11, 3, 8), skip=(loss == "cond_lik"), **kw)
+        _check(prob, theta, ude)

@@ -26,7 +26,7 @@ UDE_NONFINITE = -7
 
 EXPORTS = ["ude_abi_version", "ude_device_count", "ude_create", "ude_destroy", "ude_last_error", "ude_set_data",
            "ude_set_model_weights", "ude_set_covariates", "ude_set_targets", "ude_set_skip", "ude_n_theta",
-           "ude_n_models", "ude_steps_per_eval", "ude_launches_per_eval", "ude_loss_grad", "ude_loss_grad_device",
+           "ude_n_models", "ude_steps_per_eval", "ude_kernel_name", "ude_launches_per_eval", "ude_loss_grad", "ude_loss_grad_device",
            "ude_forward", "ude_comm_unique_id", "ude_comm_init", "ude_adam", "ude_profile_begin", "ude_profile_read",
            "ude_measure_fp64_peak"]
 
@@ -91,6 +91,8 @@ def load_library():
     lib.ude_n_models.argtypes = [vp]
     lib.ude_steps_per_eval.restype = i64
     lib.ude_steps_per_eval.argtypes = [vp]
+    lib.ude_kernel_name.restype = C.c_char_p
+    lib.ude_kernel_name.argtypes = [vp]
     lib.ude_launches_per_eval.restype = i32
     lib.ude_launches_per_eval.argtypes = [vp]
     lib.ude_loss_grad.restype = C.c_int
@@ -237,6 +239,9 @@ class Engine:
         if n < 0:
             raise UdeError(-1, self.lib.ude_last_error(self.handle).decode())
         return n
+
+    def kernel_name(self) -> str:
+        return self.lib.ude_kernel_name(self.handle).decode()
 
     def launches_per_eval(self) -> int:
         return int(self.lib.ude_launches_per_eval(self.handle))

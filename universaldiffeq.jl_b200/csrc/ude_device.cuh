@@ -43,7 +43,7 @@ struct DevProblem {
   const long long* knot_off; const double* knot_t; const double* knot_x; const double* knot_inv;
   const double* dm_u; const double* dm_dudt;
   // work
-  const Seg* segs; long long n_tasks; int n_models;
+  const Seg* segs; long long task_begin, n_tasks; int n_models;   // this launch covers tasks [task_begin, n_tasks)
   // io
   const double* theta; double* grad; double* traj_out;
   double* block_part;   // [grid][n_pm + 1]: per-block gradient of process_model and loss (n_models == 1)

@@ -594,7 +594,7 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) ude_seg_kernel(const DevP
   double loss = 0.0;
   int cur_model = -1;
 
-  for (long long task = warp_global; task < P.n_tasks; task += total_warps) {
+  for (long long task = P.task_begin + warp_global; task < P.n_tasks; task += total_warps) {
     const Seg sg = P.segs[task * GG::SPW + q];
     const int model = __shfl_sync(0xffffffffu, sg.model, 0);
     const long long ncols_m = P.model_col0[model + 1] - P.model_col0[model];

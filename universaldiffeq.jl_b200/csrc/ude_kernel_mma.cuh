@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) ude_mma_kernel(const DevP
   const double* __restrict__ uh = P.theta;        // single model: uhat is indexed by global column
   double* __restrict__ guh = P.grad;
 
-  for (long long task = warp_global; task < P.n_tasks; task += total_warps) {
+  for (long long task = P.task_begin + warp_global; task < P.n_tasks; task += total_warps) {
     const Seg sg = P.segs[task * 8 + r];
     const bool is_null = (sg.flags & SEG_NULL) != 0;
     const int series = sg.series;
