@@ -175,11 +175,33 @@ def run_reference(args):
            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
-    print(json.dumps(out), flush=True)
+    emit(out)
+
+
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """Libraries (NCCL's version banner) write to fd 1; the contract is ONE JSON line on stdout.  Point fd 1 at stderr for
+    the duration of the run and keep the real stdout for the result line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, line)
+    else:
+        sys.stdout.write(line.decode()); sys.stdout.flush()
 
 
 def main():
     args = parse()
+    _quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
         return
@@ -325,7 +347,7 @@ def main():
                           "parallelism": f"dp{world} by series, one NCCL allreduce of {prob.n_pm + 1} doubles per step" if world > 1 else "single GPU"},
                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
                "gpu_launches": eng.launches_per_eval() * args.steps, "clocks": clk}
-        print(json.dumps(out), flush=True)
+        emit(out)
     eng.close()
     if dist is not None:
         dist.barrier()

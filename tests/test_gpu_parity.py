@@ -71,10 +71,18 @@ def test_parity_group_shapes_c3(ude, g_hpl, hidden, ws, loss):
         _check(prob, theta, ude, lanes_per_segment=g_hpl[0], hidden_per_lane=g_hpl[1], weights_in_smem=ws)
 
 
-def test_parity_wide_node(ude):
+@pytest.mark.parametrize("kernel", ["mma", "g32h4"])
+def test_parity_wide_node(ude, kernel, monkeypatch):
+    """d = 8, hidden 128 (BASELINE config C5): the DMMA kernel with the hidden layer split over four warps, and the
+    lane-per-hidden-unit kernel, against the oracle."""
+    monkeypatch.setenv("UDE_KERNEL", kernel)
     prob, theta = cases.make_case("node_d8", "cond_lik", 0, hidden=128, lengths=(2,) * 9 + (5,), substeps=4)
     _check(prob, theta, ude)
-    prob, theta = cases.make_case("node_d8", "multi_shoot", 1, hidden=100, lengths=(7, 6, 3), substeps=2)
+    prob, theta = cases.make_case("node_d8", "multi_shoot", 1, hidden=100, lengths=(7, 6, 3, 11, 2, 9, 5, 5, 4), substeps=2)
+    _check(prob, theta, ude)
+    prob, theta = cases.make_case("node_d8", "deriv_match", 0, hidden=128, lengths=(7, 6, 3, 11))
+    _check(prob, theta, ude)
+    prob, theta = cases.make_case("node_d8", "mse", 1, hidden=30, lengths=(7, 6, 3, 11, 2), skip=True)
     _check(prob, theta, ude)
 
 

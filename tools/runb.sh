@@ -1,6 +1,6 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/b.json 2> gpurun_out/b.err
+python -m pytest tests -m gpu -x -q 2>&1 | tail -6
+for k in mma g32h4; do
+UDE_KERNEL=$k python bench.py --config c5 --series 200000 --steps 5 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/b.json 2> gpurun_out/b.err
 python -c "
-import json; d=json.load(open('gpurun_out/b.json')); print('%.3e steps/s' % d['value'], 'ms/step', round(d['ms_per_step'],3), 'e2e %.3e' % d['e2e']['value'], 'e2e ms', round(d['e2e']['ms_per_step'],3), d['roofline']['kernel'], d['roofline']['traffic'])" || tail -5 gpurun_out/b.err
-for K in 1 3 4 8 12; do UDE_HOST_CHUNKS=$K python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/b.json 2> gpurun_out/b.err; python -c "
-import json; d=json.load(open('gpurun_out/b.json')); print('K=$K e2e %.3e' % d['e2e']['value'], 'e2e ms', round(d['e2e']['ms_per_step'],3))"; done
+import json; d=json.load(open('gpurun_out/b.json')); print('c5 $k', '%.3e steps/s' % d['value'], 'ms/step', round(d['ms_per_step'],3), 'frac', round(d['roofline']['frac'],4), d['roofline']['kernel'][:60], 'loss', d['config']['loss_value'])" || tail -5 gpurun_out/b.err
+done

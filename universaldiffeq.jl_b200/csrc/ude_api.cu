@@ -255,7 +255,7 @@ int build_plan(ude_handle* h) {
     return fail(h, UDE_ERR_UNSUPPORTED, buf);
   }
   h->k_grad = best_g; h->k_fwd = best_f;
-  const int G = best_g->G, SPW = 32 / G;
+  const int SPW = best_g->spw;
   const int S = D.substeps, pre = (D.loss_kind == UDE_LOSS_MULTI_SHOOT && D.preroll_eps > 0.0) ? 1 : 0;
 
   std::vector<Seg> segs;
@@ -366,7 +366,8 @@ int build_plan(ude_handle* h) {
   UDE_CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessorWithFlags(&occ_f, h->k_fwd->fn, ude::kBlockThreads, h->smem_bytes_fwd, 0));
   if (occ_g < 1 || occ_f < 1) return fail(h, UDE_ERR_CUDA, "kernel does not fit on an SM");
   const int wpb = ude::kBlockThreads / 32;
-  const int64_t need_blocks = (h->n_tasks + wpb - 1) / wpb;
+  const int tpb = wpb / best_g->warps_per_task;            // tasks a block works on concurrently
+  const int64_t need_blocks = (h->n_tasks + tpb - 1) / tpb;
   const char* env_occ = getenv("UDE_MAX_BLOCKS_PER_SM");
   if (env_occ && atoi(env_occ) > 0) { occ_g = std::min(occ_g, atoi(env_occ)); occ_f = std::min(occ_f, atoi(env_occ)); }
   h->grid_grad = (int)std::min<int64_t>(need_blocks, (int64_t)occ_g * h->sm_count);

@@ -11,9 +11,9 @@ void register_one(const char* name, int priority) {
   using GG = Geo<R, G, HPL>;
   const int wsd = WS ? G * GG::WREC2 * 2 : 0;
   const int ring = (LK != LK_DM) ? 2 * Tab<SOLVER>::S * GG::ROWS * 32 : 0;
-  kernel_registry().push_back(KernelEntry{R::KIND, R::D, R::NX, R::DIN, R::DOUT, G, HPL, SOLVER, LK, 1, GG::ROWS, wsd, 0, wsd + ring, 0, priority,
+  kernel_registry().push_back(KernelEntry{R::KIND, R::D, R::NX, R::DIN, R::DOUT, G, HPL, SOLVER, LK, 1, GG::ROWS, wsd, 0, wsd + ring, 0, 32 / G, 1, priority,
                                           (const void*)ude_seg_kernel<R, G, HPL, SOLVER, LK, true, MINB, WS>, name});
-  kernel_registry().push_back(KernelEntry{R::KIND, R::D, R::NX, R::DIN, R::DOUT, G, HPL, SOLVER, LK, 0, GG::ROWS, wsd, 0, wsd, 0, priority,
+  kernel_registry().push_back(KernelEntry{R::KIND, R::D, R::NX, R::DIN, R::DOUT, G, HPL, SOLVER, LK, 0, GG::ROWS, wsd, 0, wsd, 0, 32 / G, 1, priority,
                                           (const void*)ude_seg_kernel<R, G, HPL, SOLVER, LK, false, MINB, WS>, name});
 }
 template <class R, int G, int HPL, int MINB, bool WS = false>
@@ -26,24 +26,27 @@ void register_combo(const char* name, int priority) {
   register_one<R, G, HPL, MINB, 1, LK_DM, WS>(name, priority);
 }
 
-// tensor-core (FP64 DMMA) family: NODE right-hand sides, 8 segments per warp, hidden width padded to 8*HT
-template <int D, int NX, int HT, int MINB, int SOLVER, int LK>
+// tensor-core (FP64 DMMA) family: NODE right-hand sides, 8 segments per task, HW warps per task each owning HT hidden
+// tiles (hidden width padded to 8*HT*HW)
+template <int D, int NX, int HT, int HW, int MINB, int SOLVER, int LK>
 void register_mma_one(const char* name, int priority) {
-  using MG = MmaGeo<D, NX, HT>;
-  kernel_registry().push_back(KernelEntry{UDE_RHS_NODE, D, NX, D + NX, D, 4, 2 * HT, SOLVER, LK, 1, MG::REC / 32, 0,
-                                          MmaSmem<MG, LK, true>::BLOCK, MmaSmem<MG, LK, true>::WARP, 1, priority,
-                                          (const void*)ude_mma_kernel<D, NX, HT, SOLVER, LK, true, MINB>, name});
-  kernel_registry().push_back(KernelEntry{UDE_RHS_NODE, D, NX, D + NX, D, 4, 2 * HT, SOLVER, LK, 0, MG::REC / 32, 0,
-                                          MmaSmem<MG, LK, false>::BLOCK, MmaSmem<MG, LK, false>::WARP, 1, priority,
-                                          (const void*)ude_mma_kernel<D, NX, HT, SOLVER, LK, false, MINB>, name});
+  using MG = MmaGeo<D, NX, HT, HW>;
+  // registry fields G / HPL are reused as "segments per warp-task = 32/G" and capacity G*HPL >= nn_hidden
+  const int G = 4, HPLcap = 2 * HT * HW;
+  kernel_registry().push_back(KernelEntry{UDE_RHS_NODE, D, NX, D + NX, D, G, HPLcap, SOLVER, LK, 1, MG::REC / 32, 0,
+                                          MmaSmem<MG, LK, true>::BLOCK, MmaSmem<MG, LK, true>::WARP, 1, 8, HW, priority,
+                                          (const void*)ude_mma_kernel<D, NX, HT, HW, SOLVER, LK, true, MINB>, name});
+  kernel_registry().push_back(KernelEntry{UDE_RHS_NODE, D, NX, D + NX, D, G, HPLcap, SOLVER, LK, 0, MG::REC / 32, 0,
+                                          MmaSmem<MG, LK, false>::BLOCK, MmaSmem<MG, LK, false>::WARP, 1, 8, HW, priority,
+                                          (const void*)ude_mma_kernel<D, NX, HT, HW, SOLVER, LK, false, MINB>, name});
 }
-template <int D, int NX, int HT, int MINB>
+template <int D, int NX, int HT, int MINB, int HW = 1>
 void register_mma_combo(const char* name, int priority) {
-  register_mma_one<D, NX, HT, MINB, 0, LK_STATE>(name, priority);
-  register_mma_one<D, NX, HT, MINB, 0, LK_TRAJ>(name, priority);
-  register_mma_one<D, NX, HT, MINB, 0, LK_DM>(name, priority);
-  register_mma_one<D, NX, HT, MINB, 1, LK_STATE>(name, priority);
-  register_mma_one<D, NX, HT, MINB, 1, LK_TRAJ>(name, priority);
-  register_mma_one<D, NX, HT, MINB, 1, LK_DM>(name, priority);
+  register_mma_one<D, NX, HT, HW, MINB, 0, LK_STATE>(name, priority);
+  register_mma_one<D, NX, HT, HW, MINB, 0, LK_TRAJ>(name, priority);
+  register_mma_one<D, NX, HT, HW, MINB, 0, LK_DM>(name, priority);
+  register_mma_one<D, NX, HT, HW, MINB, 1, LK_STATE>(name, priority);
+  register_mma_one<D, NX, HT, HW, MINB, 1, LK_TRAJ>(name, priority);
+  register_mma_one<D, NX, HT, HW, MINB, 1, LK_DM>(name, priority);
 }
 }  // namespace ude

@@ -29,9 +29,11 @@ __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
                : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
 
-template <int D_, int NX_, int HT_>
+template <int D_, int NX_, int HT_, int HW_ = 1>
 struct MmaGeo {
   static constexpr int D = D_, NX = NX_, HT = HT_;
+  static constexpr int HW = HW_;                         // warps that share one 8-segment task, each owning HT hidden tiles
+  static constexpr int HTT = HT_ * HW_;                  // hidden tiles of the whole network (8 units each)
   static constexpr int NXA = NX > 0 ? NX : 1;
   static constexpr int KS = (D + NX + 1 + 3) / 4;        // input k-steps (state, covariates, constant-1 bias slot)
   static constexpr int NSLOT = 4 * KS;
@@ -40,7 +42,7 @@ struct MmaGeo {
   static constexpr int HS = 8 * HT + 4;                  // row stride of the [segment][hidden] tiles: conflict-free B reads
   static constexpr int XS = MT * 8 + 4;                  // row stride of the [segment][slot] tile (12, 20: conflict-free A reads)
   static constexpr int REC = 8 * HS + 8 * XS;            // doubles per stage record (h tile + x tile), multiple of 2
-  static constexpr int NF1 = HT * KS, NF2 = HT * 2, NF3 = HT * KO, NF4 = HT * 2;
+  static constexpr int NF1 = HTT * KS, NF2 = HTT * 2, NF3 = HTT * KO, NF4 = HTT * 2;
   static constexpr int NFRAG = NF1 + NF2 + NF3 + NF4;
   static constexpr int KSTR = 12;                        // row stride of the [segment][output] k-bar tile
   static constexpr int SCRATCH = 8 * HS + 8 * KSTR;      // z-bar tile + k-bar tile
@@ -52,8 +54,28 @@ struct MmaGeo {
 template <class MG, int LK, bool GRAD>
 struct MmaSmem {
   static constexpr int WARP = GRAD ? ((LK != LK_DM ? 2 * MG::REC : MG::REC) + MG::SCRATCH) : 0;
-  static constexpr int BLOCK = MG::NFRAG * 32;
+  static constexpr int XCH = MG::HW > 1 ? 2 * MG::HW * 64 : 0;     // double-buffered exchange of the warps' partial y / x-bar
+  static constexpr int BLOCK = MG::NFRAG * 32 + XCH;
 };
+
+// sum of the HW cooperating warps' partial C fragments (fixed order => identical in every warp, bitwise reproducible).
+// Two alternating buffers let a warp run one exchange ahead of the slowest one with a single barrier per exchange.
+template <int HW>
+__device__ __forceinline__ void xchg_sum(double (&v)[2], double* s_xch, int& parity, int wl, int lane) {
+  if constexpr (HW > 1) {
+    double* buf = s_xch + (parity & 1) * HW * 64;
+    parity ^= 1;
+    *reinterpret_cast<double2*>(buf + wl * 64 + lane * 2) = make_double2(v[0], v[1]);
+    __syncthreads();
+    double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+    for (int w = 0; w < HW; ++w) {
+      const double2 t = *reinterpret_cast<const double2*>(buf + w * 64 + lane * 2);
+      a0 += t.x; a1 += t.y;
+    }
+    v[0] = a0; v[1] = a1;
+  }
+}
 
 // weight of W1 for (hidden j, slot s): inputs, then the bias column, zero padding
 template <class MG>
@@ -95,16 +117,18 @@ __device__ __forceinline__ void build_frags(const DevProblem& P, const double* _
 
 // ---- one RHS evaluation for the warp's 8 segments; xs = this lane's input slots --------------------------------
 template <class MG>
-__device__ __forceinline__ void mma_stage_forward(const double* __restrict__ s_w, const double* s_tab, int lane,
+__device__ __forceinline__ void mma_stage_forward(const double* __restrict__ s_w, const double* s_tab, int lane, int wl,
+                                                  double* s_xch, int& xpar,
                                                   const double (&xs)[MG::KS], const double (&b2own)[2],
                                                   double (&h)[MG::HT][2], double (&y)[2]) {
+  const int tb = wl * MG::HT;                 // first hidden tile of this warp
   double z[MG::HT][2];
 #pragma unroll
   for (int t = 0; t < MG::HT; ++t) { z[t][0] = 0.0; z[t][1] = 0.0; }
 #pragma unroll
   for (int e = 0; e < MG::KS; ++e) {
 #pragma unroll
-    for (int t = 0; t < MG::HT; ++t) dmma(z[t], xs[e], s_w[(t * MG::KS + e) * 32 + lane]);
+    for (int t = 0; t < MG::HT; ++t) dmma(z[t], xs[e], s_w[((tb + t) * MG::KS + e) * 32 + lane]);
   }
   // tanh on the 2*HT hidden units this lane owns, four chains at a time
 #pragma unroll
@@ -122,16 +146,21 @@ __device__ __forceinline__ void mma_stage_forward(const double* __restrict__ s_w
   double ya[2] = {0.0, 0.0}, yb[2] = {0.0, 0.0};     // two accumulators: halves the dependent DMMA chain
 #pragma unroll
   for (int t = 0; t < MG::HT; ++t) {
-    dmma(ya, h[t][0], s_w[(MG::NF1 + 2 * t) * 32 + lane]);
-    dmma(yb, h[t][1], s_w[(MG::NF1 + 2 * t + 1) * 32 + lane]);
+    dmma(ya, h[t][0], s_w[(MG::NF1 + 2 * (tb + t)) * 32 + lane]);
+    dmma(yb, h[t][1], s_w[(MG::NF1 + 2 * (tb + t) + 1) * 32 + lane]);
   }
-  y[0] = ya[0] + yb[0] + b2own[0];
-  y[1] = ya[1] + yb[1] + b2own[1];
+  y[0] = ya[0] + yb[0];
+  y[1] = ya[1] + yb[1];
+  xchg_sum<MG::HW>(y, s_xch, xpar, wl, lane);
+  y[0] += b2own[0];
+  y[1] += b2own[1];
 }
 
-template <int D_, int NX_, int HT_, int SOLVER, int LK, bool GRAD, int MINB>
+template <int D_, int NX_, int HT_, int HW_, int SOLVER, int LK, bool GRAD, int MINB>
 __global__ void __launch_bounds__(kBlockThreads, MINB) ude_mma_kernel(const DevProblem P) {
-  using MG = MmaGeo<D_, NX_, HT_>;
+  using MG = MmaGeo<D_, NX_, HT_, HW_>;
+  constexpr int HW = HW_;
+  static_assert(HW == 1 || HW == kBlockThreads / 32, "a task is shared by one warp or by the whole block");
   using T = Tab<SOLVER>;
   constexpr int D = D_, NX = NX_, HT = HT_, KS = MG::KS;
   __shared__ double s_tab[64];
@@ -141,7 +170,8 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) ude_mma_kernel(const DevP
   double* s_red = s_dyn;
   double* s_w = s_dyn + (P.n_pm + 1 + 1) / 2 * 2;
   constexpr int kPerWarp = MmaSmem<MG, LK, GRAD>::WARP;
-  double* s_warp = s_w + MG::NFRAG * 32 + (size_t)(threadIdx.x >> 5) * kPerWarp;
+  double* s_xch = s_w + MG::NFRAG * 32;
+  double* s_warp = s_xch + MmaSmem<MG, LK, GRAD>::XCH + (size_t)(threadIdx.x >> 5) * kPerWarp;
   double* s_stage = s_warp;
   // ring first (LK_DM: nothing), then the scratch tiles; LK_DM puts its h/x tiles behind the k-bar tile
   double* s_zs = s_warp + ((GRAD && LK != LK_DM) ? 2 * MG::REC : 0);
@@ -152,7 +182,12 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) ude_mma_kernel(const DevP
   const int r = lane >> 2, c = lane & 3;
   const long long warps_per_block = blockDim.x >> 5;
   const long long warp_global = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
-  const long long total_warps = (long long)gridDim.x * warps_per_block;
+  // a task (8 segments) belongs to a group of HW warps; wl = this warp's slice of the hidden layer
+  const int wl = (threadIdx.x >> 5) % HW;
+  const long long group_global = warp_global / HW;
+  const long long total_groups = (long long)gridDim.x * warps_per_block / HW;
+  const bool lead = wl == 0;                  // the group's lead warp owns the loss, the uhat gradient and gb2
+  int xpar = 0;
   const int S = P.substeps;
   constexpr uint32_t kRecBytes = MG::REC * 8;
   // stash: one record per RK stage
@@ -188,7 +223,7 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) ude_mma_kernel(const DevP
   const double* __restrict__ uh = P.theta;        // single model: uhat is indexed by global column
   double* __restrict__ guh = P.grad;
 
-  for (long long task = P.task_begin + warp_global; task < P.n_tasks; task += total_warps) {
+  for (long long task = P.task_begin + group_global; task < P.n_tasks; task += total_groups) {
     const Seg sg = P.segs[task * 8 + r];
     const bool is_null = (sg.flags & SEG_NULL) != 0;
     const int series = sg.series;
@@ -218,7 +253,7 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) ude_mma_kernel(const DevP
       const double ts = P.times[col];
       if (NX > 0) cov_eval<NX>(P, series, ts, cur, X);
       make_xs(U, X, xs);
-      mma_stage_forward<MG>(s_w, s_tab, lane, xs, b2own, h, y);
+      mma_stage_forward<MG>(s_w, s_tab, lane, wl, s_xch, xpar, xs, b2own, h, y);
       const double w = is_null ? 0.0 : 1.0;
       double kb[2];
 #pragma unroll
@@ -236,7 +271,7 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) ude_mma_kernel(const DevP
 #pragma unroll
         for (int e = 0; e < MG::KO; ++e) {
 #pragma unroll
-          for (int t = 0; t < HT; ++t) dmma(hb[t], kb[e], s_w[(MG::NF1 + MG::NF2 + t * MG::KO + e) * 32 + lane]);
+          for (int t = 0; t < HT; ++t) dmma(hb[t], kb[e], s_w[(MG::NF1 + MG::NF2 + (wl * HT + t) * MG::KO + e) * 32 + lane]);
         }
         __syncwarp();
 #pragma unroll
@@ -246,7 +281,7 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) ude_mma_kernel(const DevP
           s_zs[r * MG::HS + 8 * t + c] = zb[t][0]; s_zs[r * MG::HS + 8 * t + c + 4] = zb[t][1];
         }
         s_ks[r * MG::KSTR + c] = kb[0]; s_ks[r * MG::KSTR + 4 + c] = kb[1];
-        gb2[0] += kb[0]; gb2[1] += kb[1];
+        if (lead) { gb2[0] += kb[0]; gb2[1] += kb[1]; }
         // no stage record in this loss family: the h and x tiles are staged behind the k-bar tile
         double* s_hs = s_ks + 8 * MG::KSTR;
         double* s_xs = s_hs + 8 * MG::HS;
@@ -314,7 +349,7 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) ude_mma_kernel(const DevP
               for (int e = 0; e < KS; ++e) if (is_state[e]) {
                 const double res = P.data[D * (c0 + ic) + slot[e]] - u[e];
                 loss = fma(w * res, res, loss);
-                if (!GRAD && P.traj_out != nullptr && i <= L && !is_null) P.traj_out[D * (c0 + i) + slot[e]] = u[e];
+                if (!GRAD && lead && P.traj_out != nullptr && i <= L && !is_null) P.traj_out[D * (c0 + i) + slot[e]] = u[e];
               }
             }
             t0 = P.times[c0 + ic];
@@ -340,7 +375,7 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) ude_mma_kernel(const DevP
             const double ts = t + T::c(st) * hs;
             if (NX > 0) cov_eval<NX>(P, series, ts, cur, X);
             make_xs(U, X, xs);
-            mma_stage_forward<MG>(s_w, s_tab, lane, xs, b2own, h, y);
+            mma_stage_forward<MG>(s_w, s_tab, lane, wl, s_xch, xpar, xs, b2own, h, y);
             if (GRAD) {
               // stage record -> shared memory -> TMA bulk store to the stash (two-buffer ring, one record per stage)
               const int rec = k * T::S + st;
@@ -416,7 +451,7 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) ude_mma_kernel(const DevP
             lam[e] = -wsc * sym[b]; gc[e] = wsc * sym[b] - os * es[b]; gp[e] = -os * fs[b];
           }
         }
-        if (!GRAD && P.traj_out != nullptr && !is_null) {
+        if (!GRAD && lead && P.traj_out != nullptr && !is_null) {
 #pragma unroll
           for (int e = 0; e < KS; ++e) if (is_state[e]) {
             if (L == 1) P.traj_out[D * col + slot[e]] = u[e];
@@ -431,7 +466,7 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) ude_mma_kernel(const DevP
           const double res = P.data[D * (c0 + ic) + slot[e]] - u[e];
           loss = fma(w * res, res, loss);
           lam[e] = -2.0 * w * res;
-          if (!GRAD && P.traj_out != nullptr && maxL <= L && !is_null && !(multi && L == P.pred_length))
+          if (!GRAD && lead && P.traj_out != nullptr && maxL <= L && !is_null && !(multi && L == P.pred_length))
             P.traj_out[D * (c0 + L) + slot[e]] = u[e];
         }
       }
@@ -484,7 +519,7 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) ude_mma_kernel(const DevP
 #pragma unroll
             for (int e = 0; e < MG::KO; ++e) {
 #pragma unroll
-              for (int t = 0; t < HT; ++t) dmma(hb[t], kb[e], s_w[(MG::NF1 + MG::NF2 + t * MG::KO + e) * 32 + lane]);
+              for (int t = 0; t < HT; ++t) dmma(hb[t], kb[e], s_w[(MG::NF1 + MG::NF2 + (wl * HT + t) * MG::KO + e) * 32 + lane]);
             }
 #pragma unroll
             for (int t = 0; t < HT; ++t) {
@@ -493,17 +528,19 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) ude_mma_kernel(const DevP
               s_zs[r * MG::HS + 8 * t + c] = zb[t][0]; s_zs[r * MG::HS + 8 * t + c + 4] = zb[t][1];
             }
             s_ks[r * MG::KSTR + c] = kb[0]; s_ks[r * MG::KSTR + 4 + c] = kb[1];
-            gb2[0] += kb[0]; gb2[1] += kb[1];
+            if (lead) { gb2[0] += kb[0]; gb2[1] += kb[1]; }
             // x-bar = W1^T z-bar on the state slots
             double xa[2] = {0.0, 0.0}, xb[2] = {0.0, 0.0};
 #pragma unroll
             for (int t = 0; t < HT; ++t) {
-              dmma(xa, zb[t][0], s_w[(MG::NF1 + MG::NF2 + MG::NF3 + 2 * t) * 32 + lane]);
-              dmma(xb, zb[t][1], s_w[(MG::NF1 + MG::NF2 + MG::NF3 + 2 * t + 1) * 32 + lane]);
+              dmma(xa, zb[t][0], s_w[(MG::NF1 + MG::NF2 + MG::NF3 + 2 * (wl * HT + t)) * 32 + lane]);
+              dmma(xb, zb[t][1], s_w[(MG::NF1 + MG::NF2 + MG::NF3 + 2 * (wl * HT + t) + 1) * 32 + lane]);
             }
+            double xsum[2] = {xa[0] + xb[0], xa[1] + xb[1]};
+            xchg_sum<HW>(xsum, s_xch, xpar, wl, lane);
 #pragma unroll
             for (int e = 0; e < KS; ++e) {
-              const double ub = (e < 2 && is_state[e]) ? xa[e < 2 ? e : 0] + xb[e < 2 ? e : 0] : 0.0;
+              const double ub = (e < 2 && is_state[e]) ? xsum[e < 2 ? e : 0] : 0.0;
               Ub[st][e] = ub; lamacc[e] += ub;
               if (st == 0) U0[e] = xs[e];
             }
@@ -541,7 +578,7 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) ude_mma_kernel(const DevP
             } else --n;
           }
         }
-        if (!is_null) {
+        if (!is_null && lead) {
 #pragma unroll
           for (int e = 0; e < KS; ++e) if (is_state[e]) {
             if (LK == LK_STATE) {
@@ -557,7 +594,7 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) ude_mma_kernel(const DevP
   // ---- flush: the C fragments already hold sums over the warp's segments; warps add into the block row in order ----
   {
     // gb2 and the loss still need the sum over the 8 segments (lane bits 2..4), the loss also over the quad
-    double l = loss;
+    double l = lead ? loss : 0.0;          // the cooperating warps computed identical losses: count the lead's
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) l += __shfl_xor_sync(0xffffffffu, l, off);
 #pragma unroll
@@ -571,7 +608,7 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) ude_mma_kernel(const DevP
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
               const int ncol = 2 * c + j;              // tile column n holds the hidden unit of lane (n & 3), value (n >> 2)
-              const int hid = 8 * t + 2 * (ncol & 3) + (ncol >> 2);
+              const int hid = 8 * (wl * HT + t) + 2 * (ncol & 3) + (ncol >> 2);
               if (hid < P.H) {
 #pragma unroll
                 for (int m = 0; m < MG::MT; ++m) {

@@ -14,6 +14,8 @@ struct KernelEntry {
   int block_doubles;       // per-block dynamic shared memory besides the partial row (MMA kernels: weight fragments)
   int warp_doubles;        // per-warp dynamic shared memory (weight records + TMA staging ring + scratch tiles)
   int single_model_only;   // MMA kernels keep one model's weights per block
+  int spw;                 // segments per task (32/G, or 8 for the MMA kernels)
+  int warps_per_task;      // warps that cooperate on one task (MMA kernels with a split hidden layer: 4)
   int priority;            // lower = preferred when several (G, HPL) fit
   const void* fn;
   const char* name;
