@@ -277,6 +277,7 @@ def main():
     ms_step = float(t.item()) / args.steps
     value = steps_per_eval * world / (ms_step * 1e-3)
     loss_val = float(d_loss.sum().item())
+    grad_l1 = float(d_grad.abs().sum().item())          # cheap checksum: lets two builds of the kernel be compared at full size
 
     # ---- end-to-end through the public host-buffer call ----------------------------------------------------------
     e2e = None
@@ -342,7 +343,7 @@ def main():
                "data": "synthetic",
                "config": {"workload": name, "solver": args.solver, "substeps": args.substeps,
                           "rk_steps_per_eval_per_gpu": steps_per_eval, "segments_per_gpu": prob.count_segments(),
-                          "n_theta_per_gpu": n_theta, "loss_value": loss_val,
+                          "n_theta_per_gpu": n_theta, "loss_value": loss_val, "grad_l1": grad_l1,
                           "l2": "inputs+stash larger than L2 (theta, grad, data = %.0f MB per step)" % (3 * 8 * prob.d * prob.n_cols / 1e6),
                           "parallelism": f"dp{world} by series, one NCCL allreduce of {prob.n_pm + 1} doubles per step" if world > 1 else "single GPU"},
                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,

@@ -431,6 +431,7 @@ DevProblem make_dev_problem(const ude_handle* h, const double* d_theta, double* 
   P.theta = d_theta; P.grad = d_grad; P.traj_out = d_traj;
   P.block_part = h->d_block_part.p; P.model_loss = h->d_model_loss.p;
   P.stash = h->d_stash.p; P.stash_rows_per_warp = h->stash_rows_per_warp;
+  { const char* e = getenv("UDE_STASH_DISCARD"); P.stash_discard = e ? atoi(e) : 1; }
   return P;
 }
 

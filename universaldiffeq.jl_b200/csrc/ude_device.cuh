@@ -49,6 +49,7 @@ struct DevProblem {
   double* block_part;   // [grid][n_pm + 1]: per-block gradient of process_model and loss (n_models == 1)
   double* model_loss;   // [n_models], atomics                                       (n_models  > 1)
   double* stash; long long stash_rows_per_warp;
+  int stash_discard;    // 1: records are discarded from L2 (no write-back) once the reverse sweep has consumed them
 };
 
 // ------------------------------------------------------------------------------------------------

@@ -4,5 +4,6 @@ namespace {
 using namespace ude;
 RegisterKernels reg([] {
   register_mma_combo<4, 1, 4, 3>("node_d4x1_mma_h32", 1);
+  register_mma_combo<4, 1, 4, 4>("node_d4x1_mma_h32_b4", 8);
 });
 }  // namespace

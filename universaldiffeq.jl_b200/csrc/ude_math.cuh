@@ -10,8 +10,10 @@
 #pragma once
 #include <cuda_runtime.h>
 
+// Newton steps on the MUFU.RCP64H seed.  One step (2^-40) followed by the residual correction in ude_div / the tanh
+// epilogue is already at the 2.2e-16 error floor (tools/microbench.cu built with -DUDE_RCP_NR=1, profiles/).
 #ifndef UDE_RCP_NR
-#define UDE_RCP_NR 2
+#define UDE_RCP_NR 1
 #endif
 
 // reciprocal of a normal double d (|d| in [2^-500, 2^500]); relative error ~1e-16 after the Newton steps
