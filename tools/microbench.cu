@@ -144,6 +144,30 @@ __global__ void k_dmma(double* out, int iters) {
   if (s == 123.456) out[0] = s;
 }
 
+// DMMA and DFMA interleaved: do the FP64 tensor sub-pipe and the FP64 FMA pipe overlap or share one datapath?
+template <int NMMA, int NFMA>
+__global__ void k_mix_dmma_dfma(double* out, int iters, double fa, double fb) {
+  double c0[NMMA > 0 ? NMMA : 1], c1[NMMA > 0 ? NMMA : 1], acc[NFMA > 0 ? NFMA : 1];
+  double a = threadIdx.x * 1e-3, b = 1.0 - threadIdx.x * 1e-3;
+#pragma unroll
+  for (int c = 0; c < (NMMA > 0 ? NMMA : 1); ++c) { c0[c] = c; c1[c] = -c; }
+#pragma unroll
+  for (int c = 0; c < (NFMA > 0 ? NFMA : 1); ++c) acc[c] = threadIdx.x * 1e-3 + c;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int c = 0; c < NMMA; ++c)
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0[c]), "+d"(c1[c]) : "d"(a), "d"(b));
+#pragma unroll
+    for (int c = 0; c < NFMA; ++c) acc[c] = fma(acc[c], fa, fb);
+  }
+  double s = 0;
+#pragma unroll
+  for (int c = 0; c < (NMMA > 0 ? NMMA : 1); ++c) s += c0[c] + c1[c];
+#pragma unroll
+  for (int c = 0; c < (NFMA > 0 ? NFMA : 1); ++c) s += acc[c];
+  if (s == 123.456) out[0] = s;
+}
+
 template <typename F>
 static float time_ms(F launch, int reps = 5) {
   cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
@@ -232,6 +256,14 @@ int main() {
     float ms = time_ms([&] { k_dmma<8><<<blocks, threads>>>(d_out, iters / 4); });
     double flops = 2.0 * 8 * 8 * 4 * 8.0 * (iters / 4) * blocks * (threads / 32);
     printf(", \"dmma_m8n8k4_tflops\": %.3f", flops / ms * 1e-9);
+  }
+  {
+    const int it = iters / 4;
+    float m_mma = time_ms([&] { k_mix_dmma_dfma<4, 0><<<blocks, threads>>>(d_out, it, 1.0000001, 1e-9); });
+    float m_fma = time_ms([&] { k_mix_dmma_dfma<0, 32><<<blocks, threads>>>(d_out, it, 1.0000001, 1e-9); });
+    float m_both = time_ms([&] { k_mix_dmma_dfma<4, 32><<<blocks, threads>>>(d_out, it, 1.0000001, 1e-9); });
+    // 4 DMMA (4*256 FMA) and 32 DFMA (32*32 FMA) per warp-iteration: equal FMA counts
+    printf(", \"mix_4dmma_ms\": %.4f, \"mix_32dfma_ms\": %.4f, \"mix_4dmma_32dfma_ms\": %.4f", m_mma, m_fma, m_both);
   }
   printf("}\n");
   return 0;

@@ -150,14 +150,18 @@ __device__ __forceinline__ void mma_stage_forward(const double* __restrict__ s_w
       h[t][0] = ho[0]; h[t][1] = ho[1];
     }
   }
-  double ya[2] = {0.0, 0.0}, yb[2] = {0.0, 0.0};     // two accumulators: halves the dependent DMMA chain
+  // one accumulator per hidden tile: HT independent DMMA chains of length 2 instead of 2 chains of length HT
+  double yt[MG::HT][2];
 #pragma unroll
   for (int t = 0; t < MG::HT; ++t) {
-    dmma(ya, h[t][0], s_w[(MG::NF1 + 2 * (tb + t)) * 32 + lane]);
-    dmma(yb, h[t][1], s_w[(MG::NF1 + 2 * (tb + t) + 1) * 32 + lane]);
+    yt[t][0] = 0.0; yt[t][1] = 0.0;
+    dmma(yt[t], h[t][0], s_w[(MG::NF1 + 2 * (tb + t)) * 32 + lane]);
   }
-  y[0] = ya[0] + yb[0];
-  y[1] = ya[1] + yb[1];
+#pragma unroll
+  for (int t = 0; t < MG::HT; ++t) dmma(yt[t], h[t][1], s_w[(MG::NF1 + 2 * (tb + t) + 1) * 32 + lane]);
+  y[0] = 0.0; y[1] = 0.0;
+#pragma unroll
+  for (int t = 0; t < MG::HT; ++t) { y[0] += yt[t][0]; y[1] += yt[t][1]; }
   xchg_sum<MG::HW>(y, s_xch, xpar, wl, lane);
   y[0] += b2own[0];
   y[1] += b2own[1];
@@ -339,6 +343,12 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) ude_mma_kernel(const DevP
         pre = eps > 0.0 ? 1 : 0;
       }
       const int nsteps = pre + maxL * S;
+      // the interval loop reads times and this lane's data entries once per interval, each a cold HBM access on the
+      // critical path: start them all now
+      for (int i = lane & 3; i <= L + 1; i += 4) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(P.times + c0 + min(i, L)));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(P.data + (long long)D * (c0 + min(i, L))));
+      }
       double u[KS];
 #pragma unroll
       for (int e = 0; e < KS; ++e) u[e] = is_state[e] ? (from_theta ? uh[D * c0 + slot[e]] : P.data[D * c0 + slot[e]]) : 0.0;
@@ -537,13 +547,17 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) ude_mma_kernel(const DevP
             s_ks[r * MG::KSTR + c] = kb[0]; s_ks[r * MG::KSTR + 4 + c] = kb[1];
             if (lead) { gb2[0] += kb[0]; gb2[1] += kb[1]; }
             // x-bar = W1^T z-bar on the state slots
-            double xa[2] = {0.0, 0.0}, xb[2] = {0.0, 0.0};
+            double xt[HT][2];
 #pragma unroll
             for (int t = 0; t < HT; ++t) {
-              dmma(xa, zb[t][0], s_w[(MG::NF1 + MG::NF2 + MG::NF3 + 2 * (wl * HT + t)) * 32 + lane]);
-              dmma(xb, zb[t][1], s_w[(MG::NF1 + MG::NF2 + MG::NF3 + 2 * (wl * HT + t) + 1) * 32 + lane]);
+              xt[t][0] = 0.0; xt[t][1] = 0.0;
+              dmma(xt[t], zb[t][0], s_w[(MG::NF1 + MG::NF2 + MG::NF3 + 2 * (wl * HT + t)) * 32 + lane]);
             }
-            double xsum[2] = {xa[0] + xb[0], xa[1] + xb[1]};
+#pragma unroll
+            for (int t = 0; t < HT; ++t) dmma(xt[t], zb[t][1], s_w[(MG::NF1 + MG::NF2 + MG::NF3 + 2 * (wl * HT + t) + 1) * 32 + lane]);
+            double xsum[2] = {0.0, 0.0};
+#pragma unroll
+            for (int t = 0; t < HT; ++t) { xsum[0] += xt[t][0]; xsum[1] += xt[t][1]; }
             xchg_sum<HW>(xsum, s_xch, xpar, wl, lane);
 #pragma unroll
             for (int e = 0; e < KS; ++e) {
