@@ -47,6 +47,12 @@ RHS_SPECS = {
     "fishery": (P.RHS_FISHERY, 2, 1, 3, 1, 3, False, (1.0, 0.5, 4.0)),
     "nn_decay_d1": (P.RHS_NN_DECAY, 1, 0, 1, 1, 1, False, (0.5,)),
     "series_growth_d1": (P.RHS_SERIES_GROWTH, 1, 0, 1, 1, 0, True, ()),
+    "node_d1": (P.RHS_NODE, 1, 0, 1, 1, 0, False, ()),
+    "node_d3": (P.RHS_NODE, 3, 0, 3, 3, 0, False, ()),
+    "node_d4": (P.RHS_NODE, 4, 0, 4, 4, 0, False, ()),
+    "node_d1x1": (P.RHS_NODE, 1, 1, 2, 1, 0, False, ()),
+    "node_d3x1": (P.RHS_NODE, 3, 1, 4, 3, 0, False, ()),
+    "node_d2x2": (P.RHS_NODE, 2, 2, 4, 2, 0, False, ()),
 }
 LOSSES = ("cond_lik", "mse", "multi_shoot", "multi_shoot_preroll", "shoot_theta", "shoot_data", "deriv_match")
 

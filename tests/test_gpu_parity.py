@@ -159,3 +159,25 @@ def test_pipelined_host_path(ude, loss, chunks, monkeypatch):
     for rhs, kw in (("node_d4x1", dict(hidden=32)), ("lv_ude", {})):
         prob, theta = cases.make_case(rhs, loss, 0, lengths=(13, 2, 30, 7, 1, 22, 9, 16, 5, 11, 3, 8), skip=(loss == "cond_lik"), **kw)
         _check(prob, theta, ude)
+
+
+@pytest.mark.parametrize("rhs,hidden", [("node_d1", 32), ("node_d2", 29), ("node_d3", 32), ("node_d1x1", 20), ("node_d2x1", 32),
+                                        ("node_d3x1", 17), ("node_d4", 32), ("node_d4x1", 128), ("node_d4", 100), ("node_d2", 128)])
+def test_parity_dmma_shapes(ude, rhs, hidden, monkeypatch):
+    """The FP64 tensor-core kernels for every instantiated NODE shape (hidden width not a multiple of 8 included)."""
+    monkeypatch.setenv("UDE_KERNEL", "mma")
+    for loss, solver in (("multi_shoot", 0), ("cond_lik", 1), ("deriv_match", 0), ("shoot_theta", 1)):
+        prob, theta = cases.make_case(rhs, loss, solver, hidden=hidden, lengths=(9, 1, 14, 2, 6, 11, 3, 8, 5), skip=(loss == "cond_lik"))
+        with ude.Engine(prob) as eng:
+            assert "mma" in eng.kernel_name()
+        _check(prob, theta, ude)
+
+
+def test_long_shooting_series(ude):
+    """One long trajectory per series (shooting loss): thousands of RK steps per segment, the reverse-sweep stash is sized
+    by the longest segment and the persistent grid shrinks to fit it."""
+    for rhs, kw in (("node_d2", dict(hidden=10)), ("node_d4x1", dict(hidden=32)), ("lv_ude", {})):
+        prob, theta = cases.make_case(rhs, "shoot_theta", 0, lengths=(1500, 700, 64, 3), substeps=2, **kw)
+        # tame the dynamics so a 1500-point open-loop trajectory stays bounded
+        theta[prob.pm_base(0):] *= 0.2
+        _check(prob, theta, ude)
