@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="series in the CPU-oracle sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the short C2/C4/C5 side measurements (N = 1 only)")
     return ap.parse_args()
 
 
@@ -312,6 +313,33 @@ def main():
                "sample": f"{sp.n_series} series = {ssteps} RK steps per evaluation x {reps} evaluations in {el:.1f} s "
                          f"(oracle/libude_oracle.so, OpenMP over series); Julia reference not runnable here"}
 
+    # ---- the other BASELINE configs, same protocol (resident inputs, CUDA events), a few steps each: context, not the headline
+    others = None
+    if rank == 0 and world == 1 and args.config == "c3" and not args.no_other_configs:
+        others = {}
+        for cfg, n in (("c2", 10_000), ("c4", 1000), ("c5", 1_000_000)):
+            try:
+                a2 = argparse.Namespace(**vars(args)); a2.config = cfg; a2.series = n
+                p2, th2, nm2 = build_problem(ude, a2, 0)
+                with ude.Engine(p2, device=local) as e2:
+                    dt2 = torch.from_numpy(th2).to(dev); dg2 = torch.empty_like(dt2)
+                    dl2 = torch.empty(p2.n_models, dtype=torch.float64, device=dev)
+                    for _ in range(3):
+                        e2.loss_grad_device(dt2.data_ptr(), dl2.data_ptr(), dg2.data_ptr(), stream)
+                    torch.cuda.synchronize()
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record()
+                    for _ in range(10):
+                        e2.loss_grad_device(dt2.data_ptr(), dl2.data_ptr(), dg2.data_ptr(), stream)
+                    b.record(); torch.cuda.synchronize()
+                    ms2 = a.elapsed_time(b) / 10
+                    st2 = e2.steps_per_eval()
+                    others[cfg] = {"workload": nm2, "steps_per_s": st2 / (ms2 * 1e-3), "ms_per_step": ms2, "kernel": e2.kernel_name(),
+                                   "fp64_frac": st2 * p2.flops_per_step() / (ms2 * 1e-3) * 1e-12 / fp64_peak}
+                del dt2, dg2, dl2
+            except Exception as ex:        # a side measurement must never take the headline down
+                others[cfg] = {"error": str(ex)[:200]}
+
     if rank == 0:
         kms = float(np.mean(kern_ms)) if len(kern_ms) else None
         flops_step = prob.flops_per_step()
@@ -347,7 +375,7 @@ def main():
                           "l2": "inputs+stash larger than L2 (theta, grad, data = %.0f MB per step)" % (3 * 8 * prob.d * prob.n_cols / 1e6),
                           "parallelism": f"dp{world} by series, one NCCL allreduce of {prob.n_pm + 1} doubles per step" if world > 1 else "single GPU"},
                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-               "gpu_launches": eng.launches_per_eval() * args.steps, "clocks": clk}
+               "gpu_launches": eng.launches_per_eval() * args.steps, "clocks": clk, "other_configs": others}
         emit(out)
     eng.close()
     if dist is not None:
