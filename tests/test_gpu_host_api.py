@@ -70,3 +70,40 @@ def test_leave_future_out_batched_equals_serial(ude):
     by_h, _ = ude.summarize_leave_future_out(m, te, fc)
     assert len(by_h) == 3 and np.all(np.isfinite(by_h["mean_absolute_error"]))
     assert trace.shape == (5, 3) and np.all(np.diff(trace[:, 0]) < 0)        # the loss goes down
+
+
+def test_forecast_and_predictions_match_oracle(ude):
+    """forecast() (src/ModelTesting.jl:541-571 with the damping of src/ProcessModels.jl:2-25) and predictions()
+    (:181-195) through the GPU against the same steps integrated by the oracle."""
+    df = _lv_frame(ude, n=18)
+    X = pd.DataFrame({"time": np.linspace(-0.5, 4.5, 11), "X": np.sin(np.linspace(0, 3, 11))})
+    m = ude.NODE(df, X, hidden_units=10, seed=3)
+    m.parameters[: 2 * m.N] = m.data.reshape(-1, order="F")
+    prob = ude.default_loss(m)
+    pred = ude.predictions(m)
+    assert np.max(np.abs(pred - oracle.forward(prob, m.parameters))) < 1e-10
+    t_new = m.times[-1] + np.array([0.1, 0.25, 0.6, 1.0])
+    fc = ude.forecast(m, m.uhat[:, -1], m.times[-1], t_new)
+    # the same recursion with oracle one-step predictions
+    from oracle import ude_oracle_np as onp
+    x = m.uhat[:, -1].copy(); t0 = m.times[-1]
+    umax, umin, umean = m.uhat.max(axis=1), m.uhat.min(axis=1), m.uhat.mean(axis=1)
+    for j, t1 in enumerate(t_new):
+        p1 = np.real(onp.flow(prob, m.process_model, 0, 0, x, t0, t1))
+        du = p1 - x
+        w = np.exp(-0.5 / 0.25 ** 2 * ((x - umax) / (umax - umin)) ** 2); du = np.where(x > umax, w * du - 0.1 * (1 - w) * (x - umean), du)
+        w = np.exp(-0.5 / 0.25 ** 2 * ((x - umin) / (umax - umin)) ** 2); du = np.where(x < umin, w * du - (1 - w) * 0.1 * (x - umean), du)
+        x = x + du; t0 = t1
+        assert np.max(np.abs(fc[j, 1:] - x)) < 1e-9 and fc[j, 0] == t1
+
+
+def test_multinode_leave_future_out_and_kfold(ude):
+    df = _lv_frame(ude, n=14)
+    dfm = pd.concat([df.assign(series="a"), df.iloc[:12].assign(series="b")])
+    m = ude.MultiNODE(dfm, hidden_units=10)
+    opts = dict(maxiter=3, step_size=0.05)
+    models, tr, te, fc, trace = ude.leave_future_out_batched(m, k=2, skip=1, loss_function="multiple shooting", optim_options=opts)
+    assert len(fc) == 2 and set(fc[0]["series"]) == {"a", "b"} and np.all(np.isfinite(fc[1][["x1", "x2"]].to_numpy()))
+    m1 = ude.NODE(df, hidden_units=10)
+    out = ude.kfold_cv(m1, lambda mi, ts: ude.train_(mi, "conditional likelihood", verbose=False, t_skip=ts, optim_options=dict(maxiter=2)), k=3)
+    assert len(out) == 3 and np.all(np.isfinite(out["mean_absolute_error"]))

@@ -1,3 +1,5 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e 2>/dev/null | python -c "
-import json,sys; d=json.loads(sys.stdin.read()); print('c3 %.3e' % d['value']); print({k:(v.get('kernel'), '%.3e' % v.get('steps_per_s',0), round(v.get('fp64_frac',0),3)) for k,v in d['other_configs'].items()})"
+for k in mma_h32 t8b2 t8b3; do
+UDE_KERNEL=$k python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e --no-other-configs > gpurun_out/b.json 2> gpurun_out/b.err
+python -c "
+import json; d=json.load(open('gpurun_out/b.json')); print('$k', '%.3e steps/s' % d['value'], 'ms/step', round(d['ms_per_step'],3), 'frac', round(d['roofline']['frac'],4), d['roofline']['kernel'][:60], d['config']['grad_l1'])" || tail -5 gpurun_out/b.err
+done

@@ -29,9 +29,9 @@ def _split(model: UDE, k: int, skip: int):
         if not model.multi:
             train.append(data.iloc[:-i]); test.append(data.iloc[-i:])
         else:   # src/CrossValidation.jl:242-255: drop the last i points of every series
-            g = data.groupby(model.series_column_name, sort=False, group_keys=False)
-            train.append(g.apply(lambda d: d.sort_values(tcol).iloc[:-i]))
-            test.append(g.apply(lambda d: d.sort_values(tcol).iloc[-i:]))
+            parts = [data[data[model.series_column_name] == lab].sort_values(tcol) for lab in pd.unique(data[model.series_column_name])]
+            train.append(pd.concat([d.iloc[:-i] for d in parts], ignore_index=True))
+            test.append(pd.concat([d.iloc[-i:] for d in parts], ignore_index=True))
     return train, test
 
 

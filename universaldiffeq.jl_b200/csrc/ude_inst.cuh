@@ -28,25 +28,25 @@ void register_combo(const char* name, int priority) {
 
 // tensor-core (FP64 DMMA) family: NODE right-hand sides, 8 segments per task, HW warps per task each owning HT hidden
 // tiles (hidden width padded to 8*HT*HW)
-template <int D, int NX, int HT, int HW, int MINB, int SOLVER, int LK>
+template <int D, int NX, int HT, int HW, int MINB, int SOLVER, int LK, int TB = 4>
 void register_mma_one(const char* name, int priority) {
-  using MG = MmaGeo<D, NX, HT, HW>;
+  using MG = MmaGeo<D, NX, HT, HW, TB>;
   // registry fields G / HPL are reused as "segments per warp-task = 32/G" and capacity G*HPL >= nn_hidden
   const int G = 4, HPLcap = 2 * HT * HW;
   kernel_registry().push_back(KernelEntry{UDE_RHS_NODE, D, NX, D + NX, D, G, HPLcap, SOLVER, LK, 1, MG::REC / 32, 0,
                                           MmaSmem<MG, LK, true>::BLOCK, MmaSmem<MG, LK, true>::WARP, 1, 8, HW, priority,
-                                          (const void*)ude_mma_kernel<D, NX, HT, HW, SOLVER, LK, true, MINB>, name});
+                                          (const void*)ude_mma_kernel<D, NX, HT, HW, SOLVER, LK, true, MINB, TB>, name});
   kernel_registry().push_back(KernelEntry{UDE_RHS_NODE, D, NX, D + NX, D, G, HPLcap, SOLVER, LK, 0, MG::REC / 32, 0,
                                           MmaSmem<MG, LK, false>::BLOCK, MmaSmem<MG, LK, false>::WARP, 1, 8, HW, priority,
-                                          (const void*)ude_mma_kernel<D, NX, HT, HW, SOLVER, LK, false, MINB>, name});
+                                          (const void*)ude_mma_kernel<D, NX, HT, HW, SOLVER, LK, false, MINB, TB>, name});
 }
-template <int D, int NX, int HT, int MINB, int HW = 1>
+template <int D, int NX, int HT, int MINB, int HW = 1, int TB = 4>
 void register_mma_combo(const char* name, int priority) {
-  register_mma_one<D, NX, HT, HW, MINB, 0, LK_STATE>(name, priority);
-  register_mma_one<D, NX, HT, HW, MINB, 0, LK_TRAJ>(name, priority);
-  register_mma_one<D, NX, HT, HW, MINB, 0, LK_DM>(name, priority);
-  register_mma_one<D, NX, HT, HW, MINB, 1, LK_STATE>(name, priority);
-  register_mma_one<D, NX, HT, HW, MINB, 1, LK_TRAJ>(name, priority);
-  register_mma_one<D, NX, HT, HW, MINB, 1, LK_DM>(name, priority);
+  register_mma_one<D, NX, HT, HW, MINB, 0, LK_STATE, TB>(name, priority);
+  register_mma_one<D, NX, HT, HW, MINB, 0, LK_TRAJ, TB>(name, priority);
+  register_mma_one<D, NX, HT, HW, MINB, 0, LK_DM, TB>(name, priority);
+  register_mma_one<D, NX, HT, HW, MINB, 1, LK_STATE, TB>(name, priority);
+  register_mma_one<D, NX, HT, HW, MINB, 1, LK_TRAJ, TB>(name, priority);
+  register_mma_one<D, NX, HT, HW, MINB, 1, LK_DM, TB>(name, priority);
 }
 }  // namespace ude

@@ -29,8 +29,9 @@ __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
                : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
 
-template <int D_, int NX_, int HT_, int HW_ = 1>
+template <int D_, int NX_, int HT_, int HW_ = 1, int TB_ = 4>
 struct MmaGeo {
+  static constexpr int TB = TB_;                         // tanh evaluations interleaved per batch (4 or 8)
   static constexpr int D = D_, NX = NX_, HT = HT_;
   static constexpr int HW = HW_;                         // warps that share one 8-segment task, each owning HT hidden tiles
   static constexpr int HTT = HT_ * HW_;                  // hidden tiles of the whole network (8 units each)
@@ -137,7 +138,14 @@ __device__ __forceinline__ void mma_stage_forward(const double* __restrict__ s_w
 #pragma unroll
     for (int t = 0; t < MG::HT; ++t) dmma(z[t], xs[e], s_w[((tb + t) * MG::KS + e) * 32 + lane]);
   }
-  // tanh on the 2*HT hidden units this lane owns, four chains at a time
+  // tanh on the 2*HT hidden units this lane owns, TB chains at a time (8 hides the 8-cycle dependent-issue latency
+  // completely but needs ~40 more live registers)
+  if constexpr (MG::TB == 8 && MG::HT == 4) {
+    double zi[8] = {z[0][0], z[0][1], z[1][0], z[1][1], z[2][0], z[2][1], z[3][0], z[3][1]}, ho[8];
+    ude_tanh_tab_vec<8>(zi, ho, s_tab);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) { h[t][0] = ho[2 * t]; h[t][1] = ho[2 * t + 1]; }
+  } else
 #pragma unroll
   for (int t = 0; t < MG::HT; t += 2) {
     if (t + 1 < MG::HT) {
@@ -167,9 +175,9 @@ __device__ __forceinline__ void mma_stage_forward(const double* __restrict__ s_w
   y[1] += b2own[1];
 }
 
-template <int D_, int NX_, int HT_, int HW_, int SOLVER, int LK, bool GRAD, int MINB>
+template <int D_, int NX_, int HT_, int HW_, int SOLVER, int LK, bool GRAD, int MINB, int TB_ = 4>
 __global__ void __launch_bounds__(kBlockThreads, MINB) ude_mma_kernel(const DevProblem P) {
-  using MG = MmaGeo<D_, NX_, HT_, HW_>;
+  using MG = MmaGeo<D_, NX_, HT_, HW_, TB_>;
   constexpr int HW = HW_;
   static_assert(HW == 1 || HW == kBlockThreads / 32, "a task is shared by one warp or by the whole block");
   using T = Tab<SOLVER>;
