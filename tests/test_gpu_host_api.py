@@ -107,3 +107,19 @@ def test_multinode_leave_future_out_and_kfold(ude):
     m1 = ude.NODE(df, hidden_units=10)
     out = ude.kfold_cv(m1, lambda mi, ts: ude.train_(mi, "conditional likelihood", verbose=False, t_skip=ts, optim_options=dict(maxiter=2)), k=3)
     assert len(out) == 3 and np.all(np.isfinite(out["mean_absolute_error"]))
+
+
+def test_ensemble_times_folds_in_one_handle(ude):
+    """BASELINE config C4 in miniature: members (different NN seeds) x leave-future-out folds = independent theta vectors
+    trained together; every (member, fold) equals its own separate fit."""
+    df = _lv_frame(ude, n=16)
+    m = ude.NODE(df, hidden_units=10, seed=1)
+    opts = dict(maxiter=4, step_size=0.05)
+    models, tr, te, fc, trace = ude.leave_future_out_batched(m, k=2, skip=1, loss_function="conditional likelihood", optim_options=opts,
+                                                              member_seeds=[1, 7, 9], do_forecast=False)
+    assert len(models) == 6 and trace.shape == (4, 6)
+    assert not np.allclose(models[0].process_model, models[2].process_model)          # different seeds
+    for mi in (0, 3, 5):
+        solo = ude.NODE(tr[mi], hidden_units=10, seed=[1, 7, 9][mi // 2])
+        ude.train_(solo, "conditional likelihood", verbose=False, optim_options=opts)
+        assert np.max(np.abs(solo.parameters - models[mi].parameters)) < 1e-9

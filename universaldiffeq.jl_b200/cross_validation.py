@@ -125,10 +125,19 @@ def stack_models(models: List[UDE], loss_function, regularization_weight=0.0, lo
 def leave_future_out_batched(model: UDE, k: int, skip: int = 1, loss_function="conditional likelihood", regularization_weight=0.0,
                              loss_options=None, optim_options=None, n_members: int = 1, member_seeds: Optional[List[int]] = None,
                              device=0, do_forecast=True):
-    """All k folds (x n_members ensemble members built by `model.extra['member_constructor'](seed)` when given) trained
-    in ONE device-resident Adam run.  Returns (fold_models, training_data, testing_data, forecasts, loss_trace)."""
+    """All k folds x n_members ensemble members (same model re-initialised with different NN seeds through
+    `model.extra['reseed'](data, seed)`; BASELINE config C4) trained in ONE device-resident Adam run: member-major,
+    fold-minor.  Returns (models, training_data, testing_data, forecasts, loss_trace)."""
     train, test = _split(model, k, int(round(skip)))
-    models = [model.constructor(tr) for tr in train]
+    if n_members > 1 or member_seeds is not None:
+        seeds = list(member_seeds) if member_seeds is not None else list(range(1, n_members + 1))
+        if "reseed" not in model.extra:
+            raise ValueError("this model cannot be re-seeded")
+        models = [model.extra["reseed"](tr, sd) for sd in seeds for tr in train]
+        test = [te for _ in seeds for te in test]
+        train = [tr for _ in seeds for tr in train]
+    else:
+        models = [model.constructor(tr) for tr in train]
     opts = dict(default_options(loss_function)); opts.update(optim_options or {})
     big, theta = stack_models(models, loss_function, regularization_weight, loss_options)
     with Engine(big, device=device) as eng:

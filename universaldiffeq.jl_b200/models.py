@@ -259,6 +259,13 @@ def CustomDerivatives(data, derivs: Rhs, initial_parameters: dict, X=None, time_
                                         proc_weight, obs_weight, reg_weight, extrap_rho, l, reg_type, ode_solver, ad_method)
     m = UDE(times, mat, df, X, derivs, hidden, np.zeros(0), [], dict(regularization=reg_weight, process=proc_weight, observation=obs_weight),
             ctor, time_column_name, ode_solver, varnames, N=N, T=T, cov=cov, obs_divisor=float(N))
+
+    def reseed(d2, sd):
+        p2 = dict(initial_parameters)
+        p2["NN"] = SimpleNeuralNetwork(derivs.nn_in, derivs.nn_out, hidden=hidden, seed=sd)[1]
+        return CustomDerivatives(d2, derivs, p2, X, time_column_name, variable_column_name, value_column_name, proc_weight, obs_weight,
+                                 reg_weight, extrap_rho, l, reg_type, ode_solver, ad_method)
+    m.extra.update(l=l, extrap_rho=extrap_rho, reseed=reseed)
     return _finish(m, initial_parameters)
 
 
@@ -275,6 +282,9 @@ def NODE(data, X=None, time_column_name="time", variable_column_name=None, value
     m = UDE(times, mat, df, X, node_rhs(dims, n_cov), hidden_units, np.zeros(0), [],
             dict(regularization=reg_weight, process=proc_weight, observation=obs_weight), ctor, time_column_name, ode_solver,
             varnames, N=N, T=T, cov=cov, obs_divisor=float(N))
+    m.extra.update(l=l, extrap_rho=extrap_rho,
+                   reseed=lambda d2, sd: NODE(d2, X, time_column_name, variable_column_name, value_column_name, hidden_units, sd,
+                                              proc_weight, obs_weight, reg_weight, reg_type, l, extrap_rho, ode_solver, ad_method))
     return _finish(m, {"NN": nn})
 
 
@@ -298,6 +308,10 @@ def MultiNODE(data, X=None, time_column_name="time", series_column_name="series"
     m = _multi(data, X, node_rhs, None, time_column_name, series_column_name, variable_column_name, value_column_name, proc_weight,
                obs_weight, reg_weight, ode_solver, hidden_units, ctor, True, 0.0)
     _, nn = SimpleNeuralNetwork(m.rhs.nn_in, m.rhs.nn_out, hidden=hidden_units, seed=seed)
+    m.extra.update(l=l, extrap_rho=extrap_rho,
+                   reseed=lambda d2, sd: MultiNODE(d2, X, time_column_name, series_column_name, variable_column_name, value_column_name,
+                                                   hidden_units, sd, proc_weight, obs_weight, reg_weight, reg_type, l, extrap_rho,
+                                                   ode_solver, ad_method))
     return _finish(m, {"NN": nn})
 
 
