@@ -146,6 +146,9 @@ int ude_comm_init(ude_handle* h, const void* id_bytes, int32_t n_bytes, int32_t 
  * Runs n_iter iterations of loss_grad + update without leaving the device; theta is read and written back.
  * loss_trace (n_iter doubles per model, may be NULL) receives the loss before each update. */
 int ude_adam(ude_handle* h, double* theta, int64_t n_theta, double step_size, int32_t n_iter, double* loss_trace);
+/* 1 if the last ude_adam call replayed a captured CUDA graph (one iteration = memset + segment kernel + finalize + update),
+ * which is what makes small, launch-bound models train at kernel speed; UDE_ADAM_GRAPH=0 disables it. */
+int ude_adam_used_graph(const ude_handle* h);
 
 /* Kernel timing for roofline reports: after ude_profile_begin(h, n) the next n evaluations bracket the segment
  * kernel (the dominant launch) with CUDA events on the launching stream; ude_profile_read synchronises and returns

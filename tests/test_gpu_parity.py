@@ -181,3 +181,21 @@ def test_long_shooting_series(ude):
         # tame the dynamics so a 1500-point open-loop trajectory stays bounded
         theta[prob.pm_base(0):] *= 0.2
         _check(prob, theta, ude)
+
+
+def test_adam_cuda_graph_equals_plain_loop(ude, monkeypatch):
+    """ude_adam replays one captured iteration as a CUDA graph; bit-identical to the launch-by-launch loop."""
+    import time
+    prob, theta = ude.synthetic.config_c1()
+    res = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("UDE_ADAM_GRAPH", flag)
+        with ude.Engine(prob) as eng:
+            eng.adam(theta, 0.025, 3)                       # warm-up (plan, module load)
+            t0 = time.perf_counter()
+            th, tr = eng.adam(theta, 0.025, 200)
+            res[flag] = (th, tr, time.perf_counter() - t0, eng.adam_used_graph())
+    assert res["1"][3] and not res["0"][3]
+    assert np.array_equal(res["1"][0], res["0"][0]) and np.array_equal(res["1"][1], res["0"][1])
+    assert res["1"][1][-1, 0] < res["1"][1][0, 0]
+    print("C1 (59 segments), 200 Adam iterations: graph %.2f ms, plain loop %.2f ms" % (1e3 * res["1"][2], 1e3 * res["0"][2]))

@@ -27,7 +27,7 @@ UDE_NONFINITE = -7
 EXPORTS = ["ude_abi_version", "ude_device_count", "ude_create", "ude_destroy", "ude_last_error", "ude_set_data",
            "ude_set_model_weights", "ude_set_covariates", "ude_set_targets", "ude_set_skip", "ude_n_theta",
            "ude_n_models", "ude_steps_per_eval", "ude_kernel_name", "ude_launches_per_eval", "ude_loss_grad", "ude_loss_grad_device",
-           "ude_forward", "ude_comm_unique_id", "ude_comm_init", "ude_adam", "ude_profile_begin", "ude_profile_read",
+           "ude_forward", "ude_comm_unique_id", "ude_comm_init", "ude_adam", "ude_adam_used_graph", "ude_profile_begin", "ude_profile_read",
            "ude_measure_fp64_peak"]
 
 
@@ -107,6 +107,8 @@ def load_library():
     lib.ude_comm_init.argtypes = [vp, vp, i32, i32, i32]
     lib.ude_adam.restype = C.c_int
     lib.ude_adam.argtypes = [vp, dp, i64, C.c_double, i32, dp]
+    lib.ude_adam_used_graph.restype = C.c_int
+    lib.ude_adam_used_graph.argtypes = [vp]
     lib.ude_profile_begin.restype = C.c_int
     lib.ude_profile_begin.argtypes = [vp, i32]
     lib.ude_profile_read.restype = C.c_int
@@ -285,6 +287,9 @@ class Engine:
         if n < 0:
             self._check(n)
         return out[:n].astype(np.float64)
+
+    def adam_used_graph(self) -> bool:
+        return bool(self.lib.ude_adam_used_graph(self.handle))
 
     def comm_init(self, unique_id: bytes, n_ranks: int, rank: int):
         buf = C.create_string_buffer(unique_id, 128)

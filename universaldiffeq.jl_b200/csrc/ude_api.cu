@@ -105,6 +105,7 @@ struct ude_handle {
   int grid_grad = 0, grid_fwd = 0;
   long long stash_rows_per_warp = 0;
   size_t smem_bytes = 0, smem_bytes_fwd = 0;
+  int adam_used_graph = 0;
   // multi-GPU
   void* comm = nullptr;
   int n_ranks = 1, rank = 0;
@@ -208,6 +209,28 @@ __global__ void ude_adam_update(double* __restrict__ theta, double* __restrict__
     m[i] = mi; v[i] = vi;
     theta[i] -= eta * (mi / c1) / (sqrt(vi / c2) + 1e-8);
   }
+}
+
+// Graph-replayable variants: the bias-correction state (beta1^t, beta2^t) and the iteration counter live on the device,
+// so one captured iteration can be replayed n_iter times with no host-side parameter changes.
+__global__ void ude_adam_update_dev(double* __restrict__ theta, double* __restrict__ m, double* __restrict__ v,
+                                    const double* __restrict__ g, long long n, double eta, const double* __restrict__ state) {
+  // __dmul_rn: no FMA contraction, so the correction factors are bit-identical to the host loop's b *= beta; 1 - b
+  const double c1 = 1.0 - __dmul_rn(state[0], 0.9), c2 = 1.0 - __dmul_rn(state[1], 0.999);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const double gi = g[i];
+    const double mi = 0.9 * m[i] + 0.1 * gi;
+    const double vi = 0.999 * v[i] + 0.001 * gi * gi;
+    m[i] = mi; v[i] = vi;
+    theta[i] -= eta * (mi / c1) / (sqrt(vi / c2) + 1e-8);
+  }
+}
+__global__ void ude_adam_advance(double* __restrict__ state, const double* __restrict__ loss, double* __restrict__ trace, int M) {
+  const long long it = (long long)state[2];
+  for (int m = threadIdx.x; m < M; m += blockDim.x) trace[it * M + m] = loss[m];
+  __syncthreads();
+  if (threadIdx.x == 0) { state[0] *= 0.9; state[1] *= 0.999; state[2] = (double)(it + 1); }
 }
 
 __global__ void ude_dfma_peak(double* out, int iters, double a, double b) {
@@ -823,7 +846,46 @@ int ude_adam(ude_handle* h, double* theta, int64_t n_theta, double step_size, in
   UDE_CUDA_TRY(h, cudaMemcpyAsync(h->d_theta.p, theta, n * sizeof(double), cudaMemcpyHostToDevice, s));
   double b1t = 1.0, b2t = 1.0;
   const int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)h->sm_count * 8);
-  for (int it = 0; it < n_iter; ++it) {
+  if (h->dirty) { int rc = build_plan(h); if (rc != UDE_OK) return rc; }
+  // ---- small models are launch bound (4-5 launches of a few microseconds per iteration): capture ONE iteration in a
+  // CUDA graph and replay it.  Falls through to the plain loop with a communicator, when profiling, or if capture fails.
+  const char* genv = getenv("UDE_ADAM_GRAPH");
+  bool graphed = false;
+  if (n_iter > 1 && !h->comm && h->ev_cap == 0 && !(genv && atoi(genv) == 0)) {
+    DevBuf<double> d_state;
+    UDE_CUDA_TRY(h, d_state.reserve(4));
+    const double st0[4] = {1.0, 1.0, 0.0, 0.0};
+    UDE_CUDA_TRY(h, cudaMemcpyAsync(d_state.p, st0, sizeof st0, cudaMemcpyHostToDevice, s));
+    UDE_CUDA_TRY(h, cudaStreamSynchronize(s));
+    cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
+    bool ok = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    if (ok) {
+      ok = enqueue_eval(h, h->d_theta.p, h->d_loss.p, h->d_grad.p, nullptr, s) == UDE_OK;
+      if (ok) {
+        ude_adam_update_dev<<<blocks, 256, 0, s>>>(h->d_theta.p, h->d_adam_m.p, h->d_adam_v.p, h->d_grad.p, (long long)n, step_size, d_state.p);
+        ude_adam_advance<<<1, 128, 0, s>>>(d_state.p, h->d_loss.p, d_trace.p, (int)M);
+      }
+      const bool ended = cudaStreamEndCapture(s, &graph) == cudaSuccess;
+      ok = ok && ended && graph && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
+    }
+    if (ok) {
+      for (int it = 0; it < n_iter && ok; ++it) ok = cudaGraphLaunch(exec, s) == cudaSuccess;
+      graphed = ok;
+    }
+    if (exec) cudaGraphExecDestroy(exec);
+    if (graph) cudaGraphDestroy(graph);
+    if (!graphed) {            // leave no sticky capture error behind and restart from the caller's theta
+      cudaGetLastError();
+      UDE_CUDA_TRY(h, cudaStreamSynchronize(s));
+      UDE_CUDA_TRY(h, cudaMemsetAsync(h->d_adam_m.p, 0, n * sizeof(double), s));
+      UDE_CUDA_TRY(h, cudaMemsetAsync(h->d_adam_v.p, 0, n * sizeof(double), s));
+      UDE_CUDA_TRY(h, cudaMemcpyAsync(h->d_theta.p, theta, n * sizeof(double), cudaMemcpyHostToDevice, s));
+    } else {
+      UDE_CUDA_TRY(h, cudaStreamSynchronize(s));      // d_state must outlive the replays
+    }
+  }
+  h->adam_used_graph = graphed ? 1 : 0;
+  for (int it = 0; it < n_iter && !graphed; ++it) {
     int rc = enqueue_eval(h, h->d_theta.p, d_trace.p + (size_t)it * M, h->d_grad.p, nullptr, s);
     if (rc != UDE_OK) return rc;
     b1t *= 0.9; b2t *= 0.999;
@@ -835,6 +897,8 @@ int ude_adam(ude_handle* h, double* theta, int64_t n_theta, double step_size, in
   UDE_CUDA_TRY(h, cudaStreamSynchronize(s));
   return UDE_OK;
 }
+
+int ude_adam_used_graph(const ude_handle* h) { return h ? h->adam_used_graph : 0; }
 
 int ude_profile_begin(ude_handle* h, int32_t max_evals) {
   if (!h || max_evals < 0) return UDE_ERR_INVALID;
