@@ -95,7 +95,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -105,10 +105,15 @@ class ClockSampler:
         for ln in self.proc.stdout:
             self.lines.append(ln.strip())
 
-    def stop(self):
+    def mark(self):
+        """index of the next sample: call at the start of the timed region (the sampler is started before warm-up so it is
+        already running by then)"""
+        return len(self.lines)
+
+    def stop(self, first=0):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.06)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -116,7 +121,7 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in self.lines[first:]:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -257,11 +262,12 @@ def main():
     fp64_peak = ude.measure_fp64_peak(local)
 
     # ---- device-resident timing -------------------------------------------------------------------------------
+    clocks = ClockSampler(local)
+    clocks.start()
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
-    clocks = ClockSampler(local)
-    clocks.start()
+    c_first = clocks.mark()
     eng.profile_begin(args.steps)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -271,7 +277,7 @@ def main():
     barrier()
     ms_total = e0.elapsed_time(e1)
     kern_ms = eng.profile_read(args.steps)
-    clk = clocks.stop()
+    clk = clocks.stop(c_first)
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
