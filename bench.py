@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--substeps", type=int, default=4)
     ap.add_argument("--lanes", type=int, default=0)
     ap.add_argument("--hpl", type=int, default=0)
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"], help="f32 = the optional FP32 mode (1e-4 parity bar)")
     ap.add_argument("--ws", type=int, default=0, help="0 auto, 1 register-resident weights, 2 shared-memory weights")
     ap.add_argument("--cpu-sample", type=int, default=0, help="series in the CPU-oracle sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -227,7 +228,8 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     prob, theta0, name = build_problem(ude, args, rank)
-    eng = ude.Engine(prob, device=local, lanes_per_segment=args.lanes, hidden_per_lane=args.hpl, weights_in_smem=args.ws)
+    eng = ude.Engine(prob, device=local, lanes_per_segment=args.lanes, hidden_per_lane=args.hpl, weights_in_smem=args.ws,
+                     dtype=1 if args.dtype == "f32" else 0)
     if world > 1:
         idt = torch.zeros(128, dtype=torch.uint8, device=dev)
         if rank == 0:
@@ -259,7 +261,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    fp64_peak = ude.measure_fp64_peak(local)
+    fp64_peak = ude.measure_fp64_peak(local, f32=(args.dtype == "f32"))     # FP32 FMA peak in the optional FP32 mode
 
     # ---- device-resident timing -------------------------------------------------------------------------------
     clocks = ClockSampler(local)
@@ -365,15 +367,16 @@ def main():
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         hbm_bytes = prob.hbm_bytes_per_eval()
-        roofline = {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+        roofline = {"bound": "fp64" if args.dtype == "f64" else "fp32", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                     "frac": (achieved / fp64_peak) if achieved else None, "traffic": traffic,
-                    "peak_source": "measured live: ude_measure_fp64_peak (DFMA chain, 8-way ILP, 64 warps/SM); vendor 37.2",
+                    "peak_source": ("measured live: ude_measure_fp64_peak (DFMA chain, 8-way ILP, 64 warps/SM); vendor 37.2" if args.dtype == "f64"
+                                    else "measured live: ude_measure_fp32_peak (FFMA chain, 8-way ILP, 64 warps/SM)"),
                     "flops_per_step": flops_step, "kernel": eng_kernel_name(eng), "kernel_ms": kms,
                     "kernel_share_of_step": (kms / ms_step) if kms else None,
                     "hbm_algorithmic_bytes": hbm_bytes, "hbm_achieved_gbs": (hbm_bytes / (kms * 1e-3) * 1e-9) if kms else None,
                     "hbm_peak_gbs": hbm_peak, "hbm_peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"}
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-               "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+               "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
                "data": "synthetic",
                "config": {"workload": name, "solver": args.solver, "substeps": args.substeps,
                           "rk_steps_per_eval_per_gpu": steps_per_eval, "segments_per_gpu": prob.count_segments(),
@@ -391,7 +394,7 @@ def main():
 
 def eng_kernel_name(eng):
     nm = eng.kernel_name()
-    fam = "ude_mma_kernel (FP64 DMMA m8n8k4)" if "mma" in nm else "ude_seg_kernel (DFMA + warp shuffles)"
+    fam = "ude_mma_kernel (FP64 DMMA m8n8k4)" if "mma" in nm else ("ude_seg_kernel (FFMA + warp shuffles)" if nm.startswith("f32") else "ude_seg_kernel (DFMA + warp shuffles)")
     return f"{fam} <{nm}>: fused RK forward + loss + discrete adjoint"
 
 

@@ -158,6 +158,8 @@ int ude_profile_read(ude_handle* h, float* ms_out, int32_t capacity);
 
 /* Measured FP64 FMA throughput of the device (TFLOP/s): the roofline denominator bench.py reports against. */
 int ude_measure_fp64_peak(int32_t device, double* tflops);
+/* Same for FP32 FMA: the denominator for handles created with dtype = UDE_F32. */
+int ude_measure_fp32_peak(int32_t device, double* tflops);
 
 #ifdef __cplusplus
 }

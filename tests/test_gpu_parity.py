@@ -199,3 +199,22 @@ def test_adam_cuda_graph_equals_plain_loop(ude, monkeypatch):
     assert np.array_equal(res["1"][0], res["0"][0]) and np.array_equal(res["1"][1], res["0"][1])
     assert res["1"][1][-1, 0] < res["1"][1][0, 0]
     print("C1 (59 segments), 200 Adam iterations: graph %.2f ms, plain loop %.2f ms" % (1e3 * res["1"][2], 1e3 * res["0"][2]))
+
+
+TOL32 = 1e-4   # relative, optional FP32 mode (north_star)
+
+
+@pytest.mark.parametrize("rhs,hidden,loss", [("node_d2", 10, "multi_shoot"), ("node_d2", 10, "cond_lik"), ("node_d4x1", 10, "multi_shoot"),
+                                             ("node_d4x1", 32, "multi_shoot"), ("node_d4x1", 32, "mse"), ("node_d4x1", 32, "deriv_match"),
+                                             ("node_time_d3", 10, "cond_lik"), ("lv_ude_abs", 10, "cond_lik"), ("lv_ude", 10, "shoot_theta"),
+                                             ("node_d8", 128, "cond_lik"), ("node_d8", 20, "multi_shoot")])
+def test_parity_fp32_mode(ude, rhs, hidden, loss):
+    """FP32 arithmetic (times, covariates, loss terms, seeds and reductions in FP64) against the FP64 oracle: 1e-4."""
+    for solver in (0, 1):
+        prob, theta = cases.make_case(rhs, loss, solver, hidden=hidden, lengths=(14, 1, 9, 2, 30, 6, 11), skip=(loss == "cond_lik"))
+        L_ref, g_ref = oracle.loss_grad(prob, theta)
+        with ude.Engine(prob, dtype=1) as eng:
+            assert eng.kernel_name().startswith("f32_")
+            L, g = eng.loss_grad(theta)
+        assert np.max(np.abs(L - L_ref) / np.abs(L_ref)) < TOL32, (L, L_ref)
+        assert cases.relerr(g, g_ref) < TOL32, cases.relerr(g, g_ref)

@@ -1,5 +1,4 @@
-for k in mma_h32 t8b2 t8b3; do
-UDE_KERNEL=$k python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e --no-other-configs > gpurun_out/b.json 2> gpurun_out/b.err
+python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+python bench.py --steps 10 --warmup 3 > gpurun_out/bench_full.json 2> gpurun_out/b.err
 python -c "
-import json; d=json.load(open('gpurun_out/b.json')); print('$k', '%.3e steps/s' % d['value'], 'ms/step', round(d['ms_per_step'],3), 'frac', round(d['roofline']['frac'],4), d['roofline']['kernel'][:60], d['config']['grad_l1'])" || tail -5 gpurun_out/b.err
-done
+import json; d=json.load(open('gpurun_out/bench_full.json')); print('f64 c3', '%.3e' % d['value'], 'e2e %.3e' % d['e2e']['value'], d['roofline']['frac'], d['cpu_baseline']['value'], d['clocks'])" || tail -5 gpurun_out/b.err

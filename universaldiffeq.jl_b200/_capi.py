@@ -28,7 +28,7 @@ EXPORTS = ["ude_abi_version", "ude_device_count", "ude_create", "ude_destroy", "
            "ude_set_model_weights", "ude_set_covariates", "ude_set_targets", "ude_set_skip", "ude_n_theta",
            "ude_n_models", "ude_steps_per_eval", "ude_kernel_name", "ude_launches_per_eval", "ude_loss_grad", "ude_loss_grad_device",
            "ude_forward", "ude_comm_unique_id", "ude_comm_init", "ude_adam", "ude_adam_used_graph", "ude_profile_begin", "ude_profile_read",
-           "ude_measure_fp64_peak"]
+           "ude_measure_fp64_peak", "ude_measure_fp32_peak"]
 
 
 class UdeDesc(C.Structure):
@@ -115,6 +115,8 @@ def load_library():
     lib.ude_profile_read.argtypes = [vp, dp, i32]
     lib.ude_measure_fp64_peak.restype = C.c_int
     lib.ude_measure_fp64_peak.argtypes = [i32, C.POINTER(C.c_double)]
+    lib.ude_measure_fp32_peak.restype = C.c_int
+    lib.ude_measure_fp32_peak.argtypes = [i32, C.POINTER(C.c_double)]
     if lib.ude_abi_version() != ABI_VERSION:
         raise RuntimeError("libude_cuda ABI version mismatch")
     _LIB = lib
@@ -125,12 +127,13 @@ def _ptr(a: Optional[np.ndarray]):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
-def make_desc(p: Problem, device: int = 0, lanes_per_segment: int = 0, hidden_per_lane: int = 0, weights_in_smem: int = 0) -> UdeDesc:
+def make_desc(p: Problem, device: int = 0, lanes_per_segment: int = 0, hidden_per_lane: int = 0, weights_in_smem: int = 0,
+              dtype: int = 0) -> UdeDesc:
     d = UdeDesc()
     d.abi_version = ABI_VERSION
     d.struct_bytes = C.sizeof(UdeDesc)
     d.device = device
-    d.dtype = 0
+    d.dtype = dtype            # 0 = UDE_F64, 1 = UDE_F32 (arithmetic in FP32, reductions / times / loss terms in FP64)
     for name in ("solver", "substeps", "rhs_kind", "d", "n_cov", "nn_in", "nn_hidden", "nn_out", "n_scalars",
                  "off_w1", "off_b1", "off_w2", "off_b2", "n_pm", "time_scale", "time_shift", "loss_kind", "pred_length",
                  "shoot_first_scored", "remove_ends", "preroll_eps"):
@@ -165,10 +168,10 @@ def get_unique_id() -> bytes:
     return buf.raw
 
 
-def measure_fp64_peak(device: int = 0) -> float:
+def measure_fp64_peak(device: int = 0, f32: bool = False) -> float:
     lib = load_library()
     out = C.c_double(0.0)
-    rc = lib.ude_measure_fp64_peak(device, C.byref(out))
+    rc = (lib.ude_measure_fp32_peak if f32 else lib.ude_measure_fp64_peak)(device, C.byref(out))
     if rc != UDE_OK:
         raise UdeError(rc, lib.ude_last_error(None).decode())
     return float(out.value)
@@ -177,11 +180,12 @@ def measure_fp64_peak(device: int = 0) -> float:
 class Engine:
     """One ude_handle: the batched loss-and-gradient evaluator of a finalized Problem on one GPU."""
 
-    def __init__(self, p: Problem, device: int = 0, lanes_per_segment: int = 0, hidden_per_lane: int = 0, weights_in_smem: int = 0):
+    def __init__(self, p: Problem, device: int = 0, lanes_per_segment: int = 0, hidden_per_lane: int = 0, weights_in_smem: int = 0,
+                 dtype: int = 0):
         self.lib = load_library()
         self.problem = p
         self.handle = C.c_void_p()
-        desc = make_desc(p, device, lanes_per_segment, hidden_per_lane, weights_in_smem)
+        desc = make_desc(p, device, lanes_per_segment, hidden_per_lane, weights_in_smem, dtype)
         rc = self.lib.ude_create(C.byref(desc), C.byref(self.handle))
         if rc != UDE_OK:
             raise UdeError(rc, self.lib.ude_last_error(None).decode())

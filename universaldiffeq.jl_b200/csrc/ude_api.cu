@@ -233,18 +233,19 @@ __global__ void ude_adam_advance(double* __restrict__ state, const double* __res
   if (threadIdx.x == 0) { state[0] *= 0.9; state[1] *= 0.999; state[2] = (double)(it + 1); }
 }
 
-__global__ void ude_dfma_peak(double* out, int iters, double a, double b) {
-  double acc[8];
+template <class T>
+__global__ void ude_fma_peak(T* out, int iters, T a, T b) {
+  T acc[8];
 #pragma unroll
   for (int c = 0; c < 8; ++c) acc[c] = threadIdx.x * 1e-3 + c;
   for (int i = 0; i < iters; ++i) {
 #pragma unroll
     for (int c = 0; c < 8; ++c) acc[c] = fma(acc[c], a, b);
   }
-  double s = 0;
+  T s = 0;
 #pragma unroll
   for (int c = 0; c < 8; ++c) s += acc[c];
-  if (s == 123.456) out[0] = s;
+  if (s == (T)123.456) out[0] = s;
 }
 
 // ---- segment table -------------------------------------------------------------------------------------------------
@@ -261,10 +262,11 @@ int build_plan(ude_handle* h) {
     if (e.solver != D.solver || e.lk != lk || e.G * e.HPL < D.nn_hidden) continue;
     if (D.lanes_per_segment > 0 && e.G != D.lanes_per_segment) continue;
     if (D.hidden_per_lane > 0 && e.HPL != D.hidden_per_lane) continue;
+    if (e.dtype != D.dtype) continue;
     if (e.single_model_only && h->n_models != 1) continue;
     if (const char* want = getenv("UDE_KERNEL")) { if (*want && !strstr(e.name, want)) continue; }   // tuning aid: pick a specialisation by name
-    if (D.weights_in_smem == 1 && e.ws_doubles != 0) continue;
-    if (D.weights_in_smem == 2 && e.ws_doubles == 0) continue;
+    if (D.weights_in_smem == 1 && e.ws_bytes != 0) continue;
+    if (D.weights_in_smem == 2 && e.ws_bytes == 0) continue;
     const KernelEntry*& slot = e.grad ? best_g : best_f;
     // priority first (set per specialisation from measurements), then the smallest padded hidden width
     auto key = [](const KernelEntry* k) { return (long long)k->priority * 100000 + (long long)k->G * k->HPL; };
@@ -376,7 +378,7 @@ int build_plan(ude_handle* h) {
   // dynamic smem: block partial row (single model) padded to 16 B + per-warp two-step TMA staging ring of the stash
   const size_t red_doubles = (size_t)(((h->n_models == 1 ? D.n_pm + 1 : 0) + 1) / 2 * 2);
   auto smem_for = [&](const KernelEntry* k) {
-    return (red_doubles + (size_t)k->block_doubles + (size_t)(ude::kBlockThreads / 32) * (size_t)k->warp_doubles) * sizeof(double);
+    return red_doubles * sizeof(double) + (size_t)k->block_bytes + (size_t)(ude::kBlockThreads / 32) * (size_t)k->warp_bytes;
   };
   h->smem_bytes = smem_for(h->k_grad);
   h->smem_bytes_fwd = smem_for(h->k_fwd);
@@ -400,11 +402,11 @@ int build_plan(ude_handle* h) {
   size_t free_b = 0, total_b = 0;
   UDE_CUDA_TRY(h, cudaMemGetInfo(&free_b, &total_b));
   while (h->grid_grad > h->sm_count &&
-         (double)h->grid_grad * wpb * h->stash_rows_per_warp * 256.0 > 0.5 * (double)free_b)
+         (double)h->grid_grad * wpb * h->stash_rows_per_warp * 32.0 * h->k_grad->elem_bytes > 0.5 * (double)free_b)
     h->grid_grad -= h->sm_count;
-  const size_t stash_doubles = (size_t)h->grid_grad * wpb * (size_t)h->stash_rows_per_warp * 32;
-  if ((double)stash_doubles * 8.0 > 0.8 * (double)free_b) return fail(h, UDE_ERR_CUDA, "reverse-sweep stash does not fit in device memory");
-  UDE_CUDA_TRY(h, h->d_stash.reserve(stash_doubles));
+  const size_t stash_bytes = (size_t)h->grid_grad * wpb * (size_t)h->stash_rows_per_warp * 32 * (size_t)h->k_grad->elem_bytes;
+  if ((double)stash_bytes > 0.8 * (double)free_b) return fail(h, UDE_ERR_CUDA, "reverse-sweep stash does not fit in device memory");
+  UDE_CUDA_TRY(h, h->d_stash.reserve((stash_bytes + 7) / 8));
   UDE_CUDA_TRY(h, h->d_block_part.reserve((size_t)std::max(h->grid_grad, h->grid_fwd) * (size_t)(D.n_pm + 1) * std::max<size_t>(1, h->chunks.size())));
   if (h->chunks.size() > 1 && !h->s_h2d) {
     UDE_CUDA_TRY(h, cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
@@ -546,7 +548,7 @@ int ude_create(const ude_desc* desc, ude_handle** out) {
   if (desc->d < 1 || desc->d > UDE_MAX_D || desc->nn_out < 1 || desc->nn_out > UDE_MAX_D || desc->nn_hidden < 1 ||
       desc->substeps < 1 || desc->n_scalars < 0 || desc->n_scalars > UDE_MAX_SCALARS || desc->n_cov < 0)
     return fail(nullptr, UDE_ERR_INVALID, "bad model dimensions");
-  if (desc->dtype != UDE_F64) return fail(nullptr, UDE_ERR_UNSUPPORTED, "only UDE_F64 is compiled in this build");
+  if (desc->dtype != UDE_F64 && desc->dtype != UDE_F32) return fail(nullptr, UDE_ERR_INVALID, "bad dtype");
   if (desc->solver != UDE_RK4 && desc->solver != UDE_TSIT5) return fail(nullptr, UDE_ERR_INVALID, "bad solver");
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
@@ -924,7 +926,7 @@ int ude_profile_read(ude_handle* h, float* ms_out, int32_t capacity) {
   return n;
 }
 
-int ude_measure_fp64_peak(int32_t device, double* tflops) {
+static int measure_fma_peak(int32_t device, double* tflops, bool f32) {
   if (!tflops) return UDE_ERR_INVALID;
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) { cudaGetLastError(); return fail(nullptr, UDE_ERR_NO_DEVICE, "no such CUDA device"); }
@@ -937,7 +939,8 @@ int ude_measure_fp64_peak(int32_t device, double* tflops) {
   float best = 1e30f;
   for (int r = 0; r < 6; ++r) {
     cudaEventRecord(e0);
-    ude_dfma_peak<<<blocks, threads>>>(d_out, iters, 1.0000001, 1e-9);
+    if (f32) ude_fma_peak<float><<<blocks, threads>>>((float*)d_out, iters, 1.0000001f, 1e-9f);
+    else ude_fma_peak<double><<<blocks, threads>>>(d_out, iters, 1.0000001, 1e-9);
     cudaEventRecord(e1); cudaEventSynchronize(e1);
     float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
     if (r > 0 && ms < best) best = ms;
@@ -948,6 +951,9 @@ int ude_measure_fp64_peak(int32_t device, double* tflops) {
   *tflops = 2.0 * 8 * (double)iters * blocks * threads / (best * 1e-3) * 1e-12;
   return UDE_OK;
 }
+
+int ude_measure_fp64_peak(int32_t device, double* tflops) { return measure_fma_peak(device, tflops, false); }
+int ude_measure_fp32_peak(int32_t device, double* tflops) { return measure_fma_peak(device, tflops, true); }
 
 }  // extern "C"
 #pragma GCC visibility pop

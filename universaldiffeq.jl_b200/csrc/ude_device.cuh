@@ -48,7 +48,7 @@ struct DevProblem {
   const double* theta; double* grad; double* traj_out;
   double* block_part;   // [grid][n_pm + 1]: per-block gradient of process_model and loss (n_models == 1)
   double* model_loss;   // [n_models], atomics                                       (n_models  > 1)
-  double* stash; long long stash_rows_per_warp;
+  void* stash; long long stash_rows_per_warp;      // rows of 32 elements of the kernel's arithmetic type
   int stash_discard;    // 1: records are discarded from L2 (no write-back) once the reverse sweep has consumed them
 };
 
@@ -95,14 +95,14 @@ template <> struct Tab<1> {   // Tsit5 stages 1..6 (OrdinaryDiffEq Tsit5Constant
 __host__ __device__ constexpr int next_pow2(int n) { int p = 1; while (p < n) p <<= 1; return p; }
 __host__ __device__ constexpr int ilog2(int n) { int l = 0; while (n > 1) { n >>= 1; ++l; } return l; }
 
-template <int G, int N>
-__device__ __forceinline__ void group_allreduce(double (&v)[N], int lane) {
+template <int G, int N, class TV>
+__device__ __forceinline__ void group_allreduce(TV (&v)[N], int lane) {
   if constexpr (G == 1) { return; }
   else {
     constexpr int NP = next_pow2(N);
-    double w[NP];
+    TV w[NP];
 #pragma unroll
-    for (int i = 0; i < NP; ++i) w[i] = (i < N) ? v[i] : 0.0;
+    for (int i = 0; i < NP; ++i) w[i] = (i < N) ? v[i] : TV(0);
     // reduce-scatter
     int cnt = NP;
 #pragma unroll
@@ -113,8 +113,8 @@ __device__ __forceinline__ void group_allreduce(double (&v)[N], int lane) {
 #pragma unroll
         for (int i = 0; i < NP / 2; ++i) {
           if (i < half) {
-            double send = up ? w[i] : w[i + half];
-            double keep = up ? w[i + half] : w[i];
+            TV send = up ? w[i] : w[i + half];
+            TV keep = up ? w[i + half] : w[i];
             w[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
           }
         }
@@ -130,7 +130,7 @@ __device__ __forceinline__ void group_allreduce(double (&v)[N], int lane) {
     constexpr int ns = ilog2(NP / cnt_final);
     constexpr int split_mask = (G - 1) & ~((G >> ns) - 1);     // lane bits consumed by the splits
     const int keep = lane & ~split_mask;
-    double out[N];
+    TV out[N];
 #pragma unroll
     for (int e = 0; e < N; ++e) {
       constexpr int dummy = 0; (void)dummy;

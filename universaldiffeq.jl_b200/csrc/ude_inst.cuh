@@ -1,30 +1,55 @@
-// Helper for the ude_inst_*.cu translation units: instantiate ude_seg_kernel for one (RHS, G, HPL) combination
-// (both solvers, with and without the reverse sweep) and register the four kernels.
+// Helper for the ude_inst_*.cu translation units: instantiate the kernels of one (RHS, G, HPL, weight storage)
+// combination -- both solvers, the three loss families, with and without the reverse sweep -- and register them.
 #pragma once
 #include "ude_kernel.cuh"
 #include "ude_kernel_mma.cuh"
 #include "ude_registry.h"
 
 namespace ude {
-template <class R, int G, int HPL, int MINB, int SOLVER, int LK, bool WS>
+// the two typed copies of the lane-per-hidden-unit family
+struct F64 {
+  using real = double;
+  static constexpr int DTYPE = UDE_F64;
+  template <class R, int G, int HPL> using Geo = f64::Geo<R, G, HPL>;
+  template <class R, int G, int HPL, int SOLVER, int LK, bool GRAD, int MINB, bool WS>
+  static const void* kernel() { return (const void*)f64::ude_seg_kernel<R, G, HPL, SOLVER, LK, GRAD, MINB, WS>; }
+};
+struct F32 {
+  using real = float;
+  static constexpr int DTYPE = UDE_F32;
+  template <class R, int G, int HPL> using Geo = f32::Geo<R, G, HPL>;
+  template <class R, int G, int HPL, int SOLVER, int LK, bool GRAD, int MINB, bool WS>
+  static const void* kernel() { return (const void*)f32::ude_seg_kernel<R, G, HPL, SOLVER, LK, GRAD, MINB, WS>; }
+};
+
+template <class NS, class R, int G, int HPL, int MINB, int SOLVER, int LK, bool WS>
 void register_one(const char* name, int priority) {
-  using GG = Geo<R, G, HPL>;
-  const int wsd = WS ? G * GG::WREC2 * 2 : 0;
-  const int ring = (LK != LK_DM) ? 2 * Tab<SOLVER>::S * GG::ROWS * 32 : 0;
-  kernel_registry().push_back(KernelEntry{R::KIND, R::D, R::NX, R::DIN, R::DOUT, G, HPL, SOLVER, LK, 1, GG::ROWS, wsd, 0, wsd + ring, 0, 32 / G, 1, priority,
-                                          (const void*)ude_seg_kernel<R, G, HPL, SOLVER, LK, true, MINB, WS>, name});
-  kernel_registry().push_back(KernelEntry{R::KIND, R::D, R::NX, R::DIN, R::DOUT, G, HPL, SOLVER, LK, 0, GG::ROWS, wsd, 0, wsd, 0, 32 / G, 1, priority,
-                                          (const void*)ude_seg_kernel<R, G, HPL, SOLVER, LK, false, MINB, WS>, name});
+  using GG = typename NS::template Geo<R, G, HPL>;
+  const int eb = (int)sizeof(typename NS::real);
+  const int wsb = WS ? G * GG::WREC2 * 2 * eb : 0;
+  const int ring = (LK != LK_DM) ? 2 * Tab<SOLVER>::S * GG::ROWS * 32 * eb : 0;
+  kernel_registry().push_back(KernelEntry{R::KIND, R::D, R::NX, R::DIN, R::DOUT, NS::DTYPE, G, HPL, SOLVER, LK, 1, GG::ROWS, eb, wsb, 0,
+                                          wsb + ring, 0, 32 / G, 1, priority,
+                                          NS::template kernel<R, G, HPL, SOLVER, LK, true, MINB, WS>(), name});
+  kernel_registry().push_back(KernelEntry{R::KIND, R::D, R::NX, R::DIN, R::DOUT, NS::DTYPE, G, HPL, SOLVER, LK, 0, GG::ROWS, eb, wsb, 0,
+                                          wsb, 0, 32 / G, 1, priority,
+                                          NS::template kernel<R, G, HPL, SOLVER, LK, false, MINB, WS>(), name});
 }
+template <class NS, class R, int G, int HPL, int MINB, bool WS = false>
+void register_combo_t(const char* name, int priority) {
+  register_one<NS, R, G, HPL, MINB, 0, LK_STATE, WS>(name, priority);
+  register_one<NS, R, G, HPL, MINB, 0, LK_TRAJ, WS>(name, priority);
+  register_one<NS, R, G, HPL, MINB, 0, LK_DM, WS>(name, priority);
+  register_one<NS, R, G, HPL, MINB, 1, LK_STATE, WS>(name, priority);
+  register_one<NS, R, G, HPL, MINB, 1, LK_TRAJ, WS>(name, priority);
+  register_one<NS, R, G, HPL, MINB, 1, LK_DM, WS>(name, priority);
+}
+// FP64 (R is an f64:: trait, found through `using namespace f64`)
 template <class R, int G, int HPL, int MINB, bool WS = false>
-void register_combo(const char* name, int priority) {
-  register_one<R, G, HPL, MINB, 0, LK_STATE, WS>(name, priority);
-  register_one<R, G, HPL, MINB, 0, LK_TRAJ, WS>(name, priority);
-  register_one<R, G, HPL, MINB, 0, LK_DM, WS>(name, priority);
-  register_one<R, G, HPL, MINB, 1, LK_STATE, WS>(name, priority);
-  register_one<R, G, HPL, MINB, 1, LK_TRAJ, WS>(name, priority);
-  register_one<R, G, HPL, MINB, 1, LK_DM, WS>(name, priority);
-}
+void register_combo(const char* name, int priority) { register_combo_t<F64, R, G, HPL, MINB, WS>(name, priority); }
+// FP32 (pass the f32:: trait, e.g. register_combo_f32<f32::RhsNode<4, 1>, 8, 4, 3>(...))
+template <class R, int G, int HPL, int MINB, bool WS = false>
+void register_combo_f32(const char* name, int priority) { register_combo_t<F32, R, G, HPL, MINB, WS>(name, priority); }
 
 // tensor-core (FP64 DMMA) family: NODE right-hand sides, 8 segments per task, HW warps per task each owning HT hidden
 // tiles (hidden width padded to 8*HT*HW)
@@ -33,11 +58,11 @@ void register_mma_one(const char* name, int priority) {
   using MG = MmaGeo<D, NX, HT, HW, TB>;
   // registry fields G / HPL are reused as "segments per warp-task = 32/G" and capacity G*HPL >= nn_hidden
   const int G = 4, HPLcap = 2 * HT * HW;
-  kernel_registry().push_back(KernelEntry{UDE_RHS_NODE, D, NX, D + NX, D, G, HPLcap, SOLVER, LK, 1, MG::REC / 32, 0,
-                                          MmaSmem<MG, LK, true>::BLOCK, MmaSmem<MG, LK, true>::WARP, 1, 8, HW, priority,
+  kernel_registry().push_back(KernelEntry{UDE_RHS_NODE, D, NX, D + NX, D, UDE_F64, G, HPLcap, SOLVER, LK, 1, MG::REC / 32, 8, 0,
+                                          MmaSmem<MG, LK, true>::BLOCK * 8, MmaSmem<MG, LK, true>::WARP * 8, 1, 8, HW, priority,
                                           (const void*)ude_mma_kernel<D, NX, HT, HW, SOLVER, LK, true, MINB, TB>, name});
-  kernel_registry().push_back(KernelEntry{UDE_RHS_NODE, D, NX, D + NX, D, G, HPLcap, SOLVER, LK, 0, MG::REC / 32, 0,
-                                          MmaSmem<MG, LK, false>::BLOCK, MmaSmem<MG, LK, false>::WARP, 1, 8, HW, priority,
+  kernel_registry().push_back(KernelEntry{UDE_RHS_NODE, D, NX, D + NX, D, UDE_F64, G, HPLcap, SOLVER, LK, 0, MG::REC / 32, 8, 0,
+                                          MmaSmem<MG, LK, false>::BLOCK * 8, MmaSmem<MG, LK, false>::WARP * 8, 1, 8, HW, priority,
                                           (const void*)ude_mma_kernel<D, NX, HT, HW, SOLVER, LK, false, MINB, TB>, name});
 }
 template <int D, int NX, int HT, int MINB, int HW = 1, int TB = 4>

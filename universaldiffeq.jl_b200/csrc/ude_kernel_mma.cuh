@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) ude_mma_kernel(const DevP
   const int S = P.substeps;
   constexpr uint32_t kRecBytes = MG::REC * 8;
   // stash: one record per RK stage
-  double* __restrict__ stash = GRAD ? P.stash + warp_global * P.stash_rows_per_warp * 32 : nullptr;
+  double* __restrict__ stash = GRAD ? reinterpret_cast<double*>(P.stash) + warp_global * P.stash_rows_per_warp * 32 : nullptr;
 
   ude_load_exp2_tab(s_tab);
   for (long long k = threadIdx.x; k <= P.n_pm; k += blockDim.x) s_red[k] = 0.0;

@@ -166,6 +166,12 @@ __device__ __forceinline__ void ude_tanh_tab_vec(const double (&x)[N], double (&
   for (int i = 0; i < N; ++i) out[i] = copysign(fma(e[i], y[i], q[i]), x[i]);
 }
 
+// type-dispatched front end used by the typed kernel body
+template <int N>
+__device__ __forceinline__ void ude_tanh_vec(const double (&x)[N], double (&out)[N], const double* __restrict__ s_tab) {
+  ude_tanh_tab_vec<N>(x, out, s_tab);
+}
+
 // single-precision twin for the optional FP32 mode (1e-4 parity bar): hardware tanh is too coarse
 // (2^-11), so use the same E/(E+2) form with ex2.approx; ~1e-6 relative.
 __device__ __forceinline__ float ude_tanhf(float x) {
@@ -177,4 +183,10 @@ __device__ __forceinline__ float ude_tanhf(float x) {
   float ys = fabsf(x) * (1.0f + x2 * (-0.33333334f + x2 * 0.13333334f));
   y = (t < 0.0625f) ? ys : y;
   return copysignf(y, x);
+}
+
+template <int N>
+__device__ __forceinline__ void ude_tanh_vec(const float (&x)[N], float (&out)[N], const double* __restrict__) {
+#pragma unroll
+  for (int i = 0; i < N; ++i) out[i] = ude_tanhf(x[i]);
 }
