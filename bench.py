@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--substeps", type=int, default=4)
     ap.add_argument("--lanes", type=int, default=0)
     ap.add_argument("--hpl", type=int, default=0)
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N>1: fused finalize + peer-memory exchange kernel (default) or finalize + ncclAllReduce + scatter")
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"], help="f32 = the optional FP32 mode (1e-4 parity bar)")
     ap.add_argument("--ws", type=int, default=0, help="0 auto, 1 register-resident weights, 2 shared-memory weights")
     ap.add_argument("--cpu-sample", type=int, default=0, help="series in the CPU-oracle sample (0 = auto)")
@@ -230,12 +232,22 @@ def main():
     prob, theta0, name = build_problem(ude, args, rank)
     eng = ude.Engine(prob, device=local, lanes_per_segment=args.lanes, hidden_per_lane=args.hpl, weights_in_smem=args.ws,
                      dtype=1 if args.dtype == "f32" else 0)
+    exchange = "none"
     if world > 1:
-        idt = torch.zeros(128, dtype=torch.uint8, device=dev)
-        if rank == 0:
-            idt.copy_(torch.frombuffer(bytearray(ude.get_unique_id()), dtype=torch.uint8))
-        dist.broadcast(idt, 0)
-        eng.comm_init(bytes(idt.cpu().numpy().tobytes()), world, rank)
+        if args.exchange == "peer":
+            # fused finalize + allreduce over peer memory: the ranks swap the IPC descriptions of their exchange buffers
+            mine = torch.frombuffer(bytearray(eng.peer_export(world)), dtype=torch.uint8).to(dev)
+            allb = [torch.zeros(128, dtype=torch.uint8, device=dev) for _ in range(world)]
+            dist.all_gather(allb, mine)
+            eng.peer_attach([b.cpu().numpy().tobytes() for b in allb], world, rank)
+            exchange = "fused finalize + peer-memory allreduce (ude_finalize_exchange)"
+        else:
+            idt = torch.zeros(128, dtype=torch.uint8, device=dev)
+            if rank == 0:
+                idt.copy_(torch.frombuffer(bytearray(ude.get_unique_id()), dtype=torch.uint8))
+            dist.broadcast(idt, 0)
+            eng.comm_init(bytes(idt.cpu().numpy().tobytes()), world, rank)
+            exchange = "ncclAllReduce"
         if rank != 0:   # the regulariser is a function of the shared parameters: count it once (rank 0)
             prob.reg_weight = np.zeros_like(prob.reg_weight)
             eng._check(eng.lib.ude_set_model_weights(eng.handle, prob.obs_scale.ctypes.data, prob.proc_scale.ctypes.data,
@@ -382,7 +394,7 @@ def main():
                           "rk_steps_per_eval_per_gpu": steps_per_eval, "segments_per_gpu": prob.count_segments(),
                           "n_theta_per_gpu": n_theta, "loss_value": loss_val, "grad_l1": grad_l1,
                           "l2": "inputs+stash larger than L2 (theta, grad, data = %.0f MB per step)" % (3 * 8 * prob.d * prob.n_cols / 1e6),
-                          "parallelism": f"dp{world} by series, one NCCL allreduce of {prob.n_pm + 1} doubles per step" if world > 1 else "single GPU"},
+                          "parallelism": f"dp{world} by series, {prob.n_pm + 1} doubles exchanged per step: {exchange}" if world > 1 else "single GPU"},
                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
                "gpu_launches": eng.launches_per_eval() * args.steps, "clocks": clk, "other_configs": others}
         emit(out)

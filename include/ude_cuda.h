@@ -145,6 +145,20 @@ int ude_comm_init(ude_handle* h, const void* id_bytes, int32_t n_bytes, int32_t 
 /* Device-resident Adam (Optimisers.jl semantics: beta=(0.9,0.999), eps=1e-8, bias-corrected), SURVEY.md 8f row 1.
  * Runs n_iter iterations of loss_grad + update without leaving the device; theta is read and written back.
  * loss_trace (n_iter doubles per model, may be NULL) receives the loss before each update. */
+/* Fused exchange over peer memory (NVLink / NVSwitch P2P) -- replaces the NCCL allreduce of ude_comm_init by ONE kernel
+ * that finalises the block reduction, pushes [loss | shared process-model gradient] into every rank's exchange buffer
+ * with peer stores, and sums the n_ranks contributions in rank order (bit-identical on all ranks).
+ *   1. every rank: ude_peer_export(h, n_ranks, blob, 128)   -> allocates the rank's exchange buffer, describes it in blob
+ *   2. the host exchanges the blobs (any transport; bench.py uses torch.distributed all_gather)
+ *   3. every rank: ude_peer_attach(h, all_blobs, n_ranks, rank)   (all_blobs: n_ranks x 128 B in rank order)
+ * Ranks are one process per GPU (CUDA IPC) or threads of one process with one GPU each.  Two ranks on the same GPU are
+ * refused.  A rank that waits longer than UDE_PEER_TIMEOUT_MS (default 20000) for a peer returns NaN loss/gradient
+ * (status UDE_NONFINITE) instead of hanging. */
+#define UDE_MAX_PEERS 16
+#define UDE_PEER_BLOB_BYTES 128
+int ude_peer_export(ude_handle* h, int32_t n_ranks, void* blob, int32_t n_bytes);
+int ude_peer_attach(ude_handle* h, const void* blobs, int32_t n_ranks, int32_t rank);
+
 int ude_adam(ude_handle* h, double* theta, int64_t n_theta, double step_size, int32_t n_iter, double* loss_trace);
 /* 1 if the last ude_adam call replayed a captured CUDA graph (one iteration = memset + segment kernel + finalize + update),
  * which is what makes small, launch-bound models train at kernel speed; UDE_ADAM_GRAPH=0 disables it. */

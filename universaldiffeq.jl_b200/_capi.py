@@ -28,7 +28,7 @@ EXPORTS = ["ude_abi_version", "ude_device_count", "ude_create", "ude_destroy", "
            "ude_set_model_weights", "ude_set_covariates", "ude_set_targets", "ude_set_skip", "ude_n_theta",
            "ude_n_models", "ude_steps_per_eval", "ude_kernel_name", "ude_launches_per_eval", "ude_loss_grad", "ude_loss_grad_device",
            "ude_forward", "ude_comm_unique_id", "ude_comm_init", "ude_adam", "ude_adam_used_graph", "ude_profile_begin", "ude_profile_read",
-           "ude_measure_fp64_peak", "ude_measure_fp32_peak"]
+           "ude_measure_fp64_peak", "ude_measure_fp32_peak", "ude_peer_export", "ude_peer_attach"]
 
 
 class UdeDesc(C.Structure):
@@ -115,6 +115,10 @@ def load_library():
     lib.ude_profile_read.argtypes = [vp, dp, i32]
     lib.ude_measure_fp64_peak.restype = C.c_int
     lib.ude_measure_fp64_peak.argtypes = [i32, C.POINTER(C.c_double)]
+    lib.ude_peer_export.restype = C.c_int
+    lib.ude_peer_export.argtypes = [vp, i32, vp, i32]
+    lib.ude_peer_attach.restype = C.c_int
+    lib.ude_peer_attach.argtypes = [vp, vp, i32, i32]
     lib.ude_measure_fp32_peak.restype = C.c_int
     lib.ude_measure_fp32_peak.argtypes = [i32, C.POINTER(C.c_double)]
     if lib.ude_abi_version() != ABI_VERSION:
@@ -294,6 +298,21 @@ class Engine:
 
     def adam_used_graph(self) -> bool:
         return bool(self.lib.ude_adam_used_graph(self.handle))
+
+    def peer_export(self, n_ranks: int) -> bytes:
+        """Allocate this rank's exchange buffer; returns the 128-byte blob the other ranks attach with."""
+        buf = C.create_string_buffer(128)
+        self._check(self.lib.ude_peer_export(self.handle, n_ranks, buf, 128))
+        return buf.raw
+
+    def peer_attach(self, blobs, n_ranks: int, rank: int):
+        """blobs: the n_ranks exported blobs in rank order.  From here on loss_grad / adam finish with the fused
+        finalize + peer-memory exchange kernel instead of an NCCL allreduce."""
+        raw = b"".join(bytes(b) for b in blobs)
+        if len(raw) != 128 * n_ranks:
+            raise ValueError("need n_ranks blobs of 128 bytes")
+        buf = C.create_string_buffer(raw, len(raw))
+        self._check(self.lib.ude_peer_attach(self.handle, buf, n_ranks, rank))
 
     def comm_init(self, unique_id: bytes, n_ranks: int, rank: int):
         buf = C.create_string_buffer(unique_id, 128)

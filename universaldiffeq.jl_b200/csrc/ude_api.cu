@@ -2,6 +2,7 @@
 // point that computes fails with UDE_ERR_NO_DEVICE / UDE_ERR_CUDA when no Blackwell GPU is usable.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <cmath>
@@ -109,6 +110,14 @@ struct ude_handle {
   // multi-GPU
   void* comm = nullptr;
   int n_ranks = 1, rank = 0;
+  // fused finalize + allreduce over peer memory (ude_peer_export / ude_peer_attach)
+  void* x_local = nullptr;              // this rank's exchange buffer (cudaMalloc; exported by IPC handle)
+  size_t x_bytes = 0;
+  int x_ranks = 0, x_blocks = 0;
+  long long x_stride = 0;
+  void* x_peer[UDE_MAX_PEERS] = {};     // every rank's buffer mapped here (x_peer[rank] == x_local)
+  bool x_opened[UDE_MAX_PEERS] = {};    // mapped with cudaIpcOpenMemHandle (to be closed)
+  bool x_attached = false;
   // host-buffer path: series chunks whose H2D / kernel / D2H overlap (built with the plan)
   struct Chunk { int64_t task_begin, task_end, up_lo, up_hi, dn_lo, dn_hi; };
   std::vector<Chunk> chunks;
@@ -196,6 +205,107 @@ __global__ void ude_scatter_reduced(const double* __restrict__ red, long long n_
   const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (k < n_pm) { if (grad_pm && !(k >= series_lo && k < series_hi)) grad_pm[k] = red[1 + k]; }
   else if (k == n_pm) loss_out[0] = red[0];
+}
+
+
+// ---- finalize fused with the cross-GPU exchange ("fuse with the grid-level reduction epilogue") --------
+// One launch does what ude_finalize_single + ncclAllReduce + ude_scatter_reduced do in three: each block reduces its 32
+// columns of the per-block rows (same fixed order), PUSHES the partial sums straight into every rank's exchange buffer
+// with peer stores over NVLink, raises a per-(sender, block) flag, waits for the same block of every other rank and
+// adds the n_ranks contributions in rank order -- so all ranks hold bit-identical sums.
+// Exchange buffer of a rank (x): slots  [2 parities][n_ranks senders][stride]  doubles,
+//                                flags  [2 parities][n_ranks senders][n_blocks] epoch numbers,
+//                                epoch  [n_blocks]  (this rank's own call counter, device-resident so that the launch
+//                                                    has no per-call argument and can sit in a captured graph),
+//                                status [1]         (non-zero: a wait ran out of time).
+// Parity double-buffering is enough: a sender reaches epoch e+2 only after it saw this rank's flag of epoch e+1, which
+// this rank raises after its epoch-e launch has finished reading.
+struct PeerTable {
+  double* slot[UDE_MAX_PEERS];
+  unsigned long long* flag[UDE_MAX_PEERS];
+  unsigned long long* epoch;       // local
+  unsigned long long* status;      // local
+  long long stride;
+  int n_ranks, rank, n_blocks;
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+__global__ void ude_finalize_exchange(const double* __restrict__ block_part, int n_blocks, long long n_pm, long long n_shared,
+                                      const double* __restrict__ pm, long long off_w1, long long n_w1, long long off_w2,
+                                      long long n_w2, const double* __restrict__ reg_weight,
+                                      double* __restrict__ grad_pm, double* __restrict__ loss_out, PeerTable T,
+                                      unsigned long long timeout_ns) {
+  // exchange index j: j < n_shared -> process-model entry j; j == n_shared -> the loss (column n_pm of the block rows).
+  // The rank-local per-series tail [n_shared, n_pm) was produced by atomics and takes no part (ranks may own different
+  // numbers of series, so the grid covers the exchanged entries only and is the same on every rank).
+  __shared__ double sh[8][33];
+  const int x = threadIdx.x, y = threadIdx.y;
+  const long long j = (long long)blockIdx.x * 32 + x;
+  const bool live = j <= n_shared;
+  const long long k = j < n_shared ? j : n_pm;
+  const double rw = reg_weight ? reg_weight[0] : 0.0;
+  const unsigned long long epoch = T.epoch[blockIdx.x] + 1;
+  const int par = (int)(epoch & 1);
+  double acc = 0.0;
+  if (live) {
+    for (int b = y; b < n_blocks; b += 8) acc += block_part[(long long)b * (n_pm + 1) + k];
+    if (k == n_pm && rw != 0.0) {
+      double r = 0.0;
+      for (long long i = y; i < n_w1; i += 8) { double v = pm[off_w1 + i]; r = fma(v, v, r); }
+      for (long long i = y; i < n_w2; i += 8) { double v = pm[off_w2 + i]; r = fma(v, v, r); }
+      acc = fma(rw, r, acc);
+    }
+  }
+  sh[y][x] = acc;
+  __syncthreads();
+  if (y == 0 && live) {
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += sh[i][x];
+    if (k < n_pm) {
+      const bool isw = (k >= off_w1 && k < off_w1 + n_w1) || (k >= off_w2 && k < off_w2 + n_w2);
+      if (isw && rw != 0.0) s = fma(2.0 * rw, pm[k], s);
+    }
+    const long long at = ((long long)par * T.n_ranks + T.rank) * T.stride + j;
+    for (int r = 0; r < T.n_ranks; ++r) T.slot[(r + T.rank) % T.n_ranks][at] = s;    // peer stores, staggered start
+    __threadfence_system();
+  }
+  __syncthreads();
+  const long long fat = ((long long)par * T.n_ranks) * T.n_blocks + blockIdx.x;
+  if (y == 0 && x < T.n_ranks) {
+    // lane x raises this rank's flag at rank x, then waits for rank x's flag here
+    st_release_sys(T.flag[x] + fat + (long long)T.rank * T.n_blocks, epoch);
+    const unsigned long long* mine = T.flag[T.rank] + fat + (long long)x * T.n_blocks;
+    const unsigned long long t0 = global_ns();
+    while (ld_acquire_sys(mine) < epoch) {
+      if (global_ns() - t0 > timeout_ns) { atomicExch(T.status, 1ull); break; }
+      __nanosleep(200);
+    }
+  }
+  __syncthreads();
+  if (y == 0 && live) {
+    const volatile double* in = T.slot[T.rank] + (long long)par * T.n_ranks * T.stride + j;
+    double tot = 0.0;
+    for (int r = 0; r < T.n_ranks; ++r) tot += in[(long long)r * T.stride];
+    if (*((volatile unsigned long long*)T.status) != 0ull) tot = __longlong_as_double(0x7ff8000000000000LL);   // NaN: the caller sees UDE_NONFINITE
+    if (k == n_pm) loss_out[0] = tot;
+    else if (grad_pm) grad_pm[k] = tot;
+  }
+  __syncthreads();
+  if (x == 0 && y == 0) T.epoch[blockIdx.x] = epoch;
 }
 
 // Optimisers.jl Adam: m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2; theta -= eta * (m/(1-b1^t)) / (sqrt(v/(1-b2^t)) + eps)
@@ -421,7 +531,7 @@ int build_plan(ude_handle* h) {
   }
   UDE_CUDA_TRY(h, h->d_model_loss.reserve((size_t)h->n_models));
   UDE_CUDA_TRY(h, h->d_red.reserve((size_t)D.n_pm + 2));
-  if (h->comm && D.has_series_param && D.off_series_param + h->n_series != D.n_pm)
+  if ((h->comm || h->x_attached) && D.has_series_param && D.off_series_param + h->n_series != D.n_pm)
     return fail(h, UDE_ERR_INVALID, "multi-GPU: the per-series parameter vector must be the last entry of process_model");
   UDE_CUDA_TRY(h, cudaStreamSynchronize(h->stream));   // segs came from a local vector
   h->dirty = false;
@@ -498,13 +608,32 @@ int finalize_eval(ude_handle* h, const double* d_theta, double* d_loss, double* 
   if (h->n_models == 1) {
     const long long pmb = (long long)D.d * h->n_cols;
     const long long slo = D.has_series_param ? D.off_series_param : -1, shi = D.has_series_param ? slo + h->n_series : -1;
-    const bool use_comm = h->comm != nullptr;
+    const bool use_comm = h->comm != nullptr && !h->x_attached;
     // with a communicator the reduce buffer is [loss | shared process-model gradient]: the per-series vector (which
     // must be the tail of process_model) is rank-local and stays out of the exchange
     const long long n_shared = D.has_series_param ? D.off_series_param : D.n_pm;
     double* gp = use_comm ? h->d_red.p + 1 : (want_grad ? d_grad + pmb : h->d_red.p + 1);
     double* lp = use_comm ? h->d_red.p : d_loss;
     const int nb = (int)((D.n_pm + 1 + 31) / 32);
+    if (h->x_attached) {
+      PeerTable T;
+      const size_t slots = 2ull * h->x_ranks * (size_t)h->x_stride;                 // doubles
+      const size_t flags = 2ull * h->x_ranks * (size_t)h->x_blocks;                 // u64
+      for (int r = 0; r < UDE_MAX_PEERS; ++r) {
+        T.slot[r] = r < h->x_ranks ? (double*)h->x_peer[r] : nullptr;
+        T.flag[r] = r < h->x_ranks ? (unsigned long long*)h->x_peer[r] + slots : nullptr;
+      }
+      T.epoch = (unsigned long long*)h->x_local + slots + flags;
+      T.status = T.epoch + h->x_blocks;
+      T.stride = h->x_stride; T.n_ranks = h->x_ranks; T.rank = h->rank; T.n_blocks = h->x_blocks;
+      const char* te = getenv("UDE_PEER_TIMEOUT_MS");
+      const unsigned long long tmo = (unsigned long long)(te ? atoll(te) : 20000) * 1000000ull;
+      ude_finalize_exchange<<<h->x_blocks, dim3(32, 8), 0, s>>>(h->d_block_part.p, grid, D.n_pm, n_shared, d_theta + pmb, D.off_w1, n_w1,
+                                                                D.off_w2, n_w2, h->d_reg_weight.p, want_grad ? d_grad + pmb : nullptr,
+                                                                d_loss, T, tmo);
+      UDE_CUDA_TRY(h, cudaGetLastError());
+      return UDE_OK;
+    }
     // rank r > 0 must not add the regulariser again: only rank 0 carries it (host passes reg_weight = 0 elsewhere)
     ude_finalize_single<<<nb, dim3(32, 8), 0, s>>>(h->d_block_part.p, grid, D.n_pm, d_theta + pmb, D.off_w1, n_w1, D.off_w2, n_w2,
                                                    slo, shi, h->d_reg_weight.p, gp, lp, 0);
@@ -577,6 +706,8 @@ int ude_destroy(ude_handle* h) {
   if (!h) return UDE_OK;
   cudaSetDevice(h->device);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  for (int r = 0; r < UDE_MAX_PEERS; ++r) if (h->x_opened[r] && h->x_peer[r]) cudaIpcCloseMemHandle(h->x_peer[r]);
+  if (h->x_local) cudaFree(h->x_local);
   if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
   if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
   if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
@@ -713,7 +844,8 @@ int64_t ude_steps_per_eval(const ude_handle* h) {
 }
 int32_t ude_launches_per_eval(const ude_handle* h) {
   if (!h) return 0;
-  return (h->n_models == 1) ? (h->comm ? 3 : 2) : 2;     // segment kernel + finalize (+ scatter after the allreduce)
+  // segment kernel + finalize (+ scatter after the NCCL allreduce; the fused peer exchange needs no extra launch)
+  return (h->n_models == 1) ? ((h->comm && !h->x_attached) ? 3 : 2) : 2;
 }
 
 int ude_loss_grad_device(ude_handle* h, const double* d_theta, double* d_loss, double* d_grad, void* stream) {
@@ -831,6 +963,69 @@ int ude_comm_init(ude_handle* h, const void* id_bytes, int32_t n_bytes, int32_t 
   return UDE_OK;
 }
 
+struct PeerBlob {            // UDE_PEER_BLOB_BYTES
+  unsigned long long magic;
+  long long pid;
+  int device, n_ranks;
+  unsigned long long ptr, bytes;
+  cudaIpcMemHandle_t ipc;    // 64 B
+  char pad[UDE_PEER_BLOB_BYTES - 8 - 8 - 8 - 16 - 64];
+};
+static_assert(sizeof(PeerBlob) == UDE_PEER_BLOB_BYTES, "peer blob layout");
+static const unsigned long long kPeerMagic = 0x5544455f50454552ull;   // "UDE_PEER"
+
+int ude_peer_export(ude_handle* h, int32_t n_ranks, void* blob, int32_t n_bytes) {
+  if (!h) return UDE_ERR_INVALID;
+  if (!blob || n_bytes < UDE_PEER_BLOB_BYTES || n_ranks < 2 || n_ranks > UDE_MAX_PEERS) return fail(h, UDE_ERR_INVALID, "bad peer arguments (2 <= n_ranks <= 16, 128-byte blob)");
+  if (h->n_models != 1 && h->have_data) return fail(h, UDE_ERR_INVALID, "many-model handles shard by model and need no exchange");
+  if (h->x_local) return fail(h, UDE_ERR_STATE, "ude_peer_export was already called on this handle");
+  UDE_CUDA_TRY(h, cudaSetDevice(h->device));
+  const long long n_shared = h->desc.has_series_param ? h->desc.off_series_param : h->desc.n_pm;
+  const int nb = (int)((n_shared + 1 + 31) / 32);      // identical on every rank (the per-series tail is not exchanged)
+  h->x_ranks = n_ranks; h->x_blocks = nb; h->x_stride = (long long)nb * 32;
+  h->x_bytes = 8ull * (2ull * n_ranks * (size_t)h->x_stride + 2ull * n_ranks * (size_t)nb + (size_t)nb + 1);
+  UDE_CUDA_TRY(h, cudaMalloc(&h->x_local, h->x_bytes));
+  UDE_CUDA_TRY(h, cudaMemset(h->x_local, 0, h->x_bytes));
+  UDE_CUDA_TRY(h, cudaDeviceSynchronize());
+  PeerBlob b; memset(&b, 0, sizeof b);
+  b.magic = kPeerMagic; b.pid = (long long)getpid(); b.device = h->device; b.n_ranks = n_ranks;
+  b.ptr = (unsigned long long)h->x_local; b.bytes = h->x_bytes;
+  UDE_CUDA_TRY(h, cudaIpcGetMemHandle(&b.ipc, h->x_local));
+  memcpy(blob, &b, sizeof b);
+  return UDE_OK;
+}
+
+int ude_peer_attach(ude_handle* h, const void* blobs, int32_t n_ranks, int32_t rank) {
+  if (!h) return UDE_ERR_INVALID;
+  if (!blobs || !h->x_local || n_ranks != h->x_ranks || rank < 0 || rank >= n_ranks) return fail(h, UDE_ERR_INVALID, "ude_peer_attach: call ude_peer_export first, with the same n_ranks");
+  if (h->x_attached) return fail(h, UDE_ERR_STATE, "peers are already attached");
+  UDE_CUDA_TRY(h, cudaSetDevice(h->device));
+  const PeerBlob* B = (const PeerBlob*)blobs;
+  if (B[rank].magic != kPeerMagic || B[rank].ptr != (unsigned long long)h->x_local || B[rank].pid != (long long)getpid())
+    return fail(h, UDE_ERR_INVALID, "ude_peer_attach: blobs[rank] is not this handle's export");
+  for (int r = 0; r < n_ranks; ++r) {
+    const PeerBlob& b = B[r];
+    if (b.magic != kPeerMagic || b.n_ranks != n_ranks || b.bytes != h->x_bytes) return fail(h, UDE_ERR_INVALID, "ude_peer_attach: peer blob mismatch (different model or world size)");
+    if (r == rank) { h->x_peer[r] = h->x_local; continue; }
+    if (b.pid == (long long)getpid()) {          // a thread of this process driving another GPU
+      if (b.device == h->device) return fail(h, UDE_ERR_INVALID, "two ranks on one GPU are not supported");
+      int can = 0; cudaDeviceCanAccessPeer(&can, h->device, b.device);
+      if (!can) return fail(h, UDE_ERR_CUDA, "no peer access between the ranks' GPUs");
+      cudaError_t e = cudaDeviceEnablePeerAccess(b.device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(h, UDE_ERR_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+      cudaGetLastError();
+      h->x_peer[r] = (void*)b.ptr;
+    } else {
+      void* p = nullptr;
+      cudaError_t e = cudaIpcOpenMemHandle(&p, b.ipc, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) { cudaGetLastError(); return fail(h, UDE_ERR_CUDA, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e)); }
+      h->x_peer[r] = p; h->x_opened[r] = true;
+    }
+  }
+  h->n_ranks = n_ranks; h->rank = rank; h->x_attached = true; h->dirty = true;
+  return UDE_OK;
+}
+
 int ude_adam(ude_handle* h, double* theta, int64_t n_theta, double step_size, int32_t n_iter, double* loss_trace) {
   if (!h) return UDE_ERR_INVALID;
   if (!theta || n_iter < 0) return fail(h, UDE_ERR_INVALID, "bad argument");
@@ -853,7 +1048,7 @@ int ude_adam(ude_handle* h, double* theta, int64_t n_theta, double step_size, in
   // CUDA graph and replay it.  Falls through to the plain loop with a communicator, when profiling, or if capture fails.
   const char* genv = getenv("UDE_ADAM_GRAPH");
   bool graphed = false;
-  if (n_iter > 1 && !h->comm && h->ev_cap == 0 && !(genv && atoi(genv) == 0)) {
+  if (n_iter > 1 && (!h->comm || h->x_attached) && h->ev_cap == 0 && !(genv && atoi(genv) == 0)) {
     DevBuf<double> d_state;
     UDE_CUDA_TRY(h, d_state.reserve(4));
     const double st0[4] = {1.0, 1.0, 0.0, 0.0};
