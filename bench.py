@@ -86,57 +86,79 @@ def build_problem(ude, args, rank, n_override=None):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock / power / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe).  NVML is polled from a
+    thread of this process every 10 ms (the same counters nvidia-smi prints; a piped `nvidia-smi -lms` delivers its lines
+    in 4 KB bursts, too late to attribute them to a 100 ms window); nvidia-smi once at the end is the fallback."""
 
     def __init__(self, index):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                index = int(vis.split(",")[index])
+            except Exception:
+                pass
         self.index = index
-        self.proc = None
-        self.lines = []
+        self.samples = []          # (sm_mhz, sm_max_mhz, power_w, reason_mask)
+        self.run = False
+        self.nv = None
+        self.t = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.run = True
+            self.t = threading.Thread(target=self._poll, daemon=True)
             self.t.start()
         except Exception:
-            self.proc = None
+            self.nv = None
 
-    def _read(self):
-        for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+    def _poll(self):
+        nv = self.nv
+        while self.run:
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                rs = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.samples.append((sm, self.mx, pw, rs))
+            except Exception:
+                pass
+            time.sleep(0.01)
 
     def mark(self):
-        """index of the next sample: call at the start of the timed region (the sampler is started before warm-up so it is
-        already running by then)"""
-        return len(self.lines)
+        """index of the next sample: call at the start of the timed region (the sampler starts before warm-up)"""
+        return len(self.samples)
 
     def stop(self, first=0):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.06)
-        self.proc.terminate()
+        if self.nv is None:
+            return self._smi_once()
+        self.run = False
+        self.t.join(timeout=1)
+        nv = self.nv
+        rows = self.samples[first:] or self.samples[-1:]
+        names = [("hw_slowdown", nv.nvmlClocksThrottleReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown),
+                 ("sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksThrottleReasonSwPowerCap)]
+        reasons = sorted({nm for r in rows for nm, bit in names if r[3] & bit})
+        sm = [r[0] for r in rows]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": rows[0][1] if rows else None,
+                "power_w_max": max(r[2] for r in rows) if rows else None, "samples": len(sm), "reasons": reasons, "source": "nvml"}
+
+    def _smi_once(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.proc.wait(timeout=2)
+            out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                 capture_output=True, text=True, timeout=20).stdout.strip().splitlines()[0]
+            f = [x.strip() for x in out.split(",")]
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            return {"sm_mhz": float(f[0]), "sm_max_mhz": float(f[1]), "power_w_max": float(f[2]), "samples": 1,
+                    "reasons": sorted(nm for nm, v in zip(names, f[3:7]) if v.lower().startswith("active")),
+                    "source": "nvidia-smi after the timed region (NVML unavailable)"}
         except Exception:
-            self.proc.kill()
-        sm, mx, pw, reasons = [], [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines[first:]:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
 
 
 def cpu_oracle_rate(ude, args, n_sample, threads, min_seconds=12.0, max_reps=400):

@@ -23,11 +23,11 @@ def main():
     worst = 0.0
     for kind in ("series", "series_param", "wide"):
         if kind == "series":
-            prob, theta = cases.make_case("node_d4x1", "multi_shoot", 0, lengths=(9, 4, 7, 1, 12, 6, 3, 8, 5, 11), hidden=32, reg=1e-3)
+            prob, theta = cases.make_case("node_d4x1", "multi_shoot", 0, lengths=(9, 4, 7, 1, 12, 6, 3, 8, 5, 11, 2, 10, 6, 7, 3, 9, 4), hidden=32, reg=1e-3)
         elif kind == "series_param":
-            prob, theta = cases.make_case("series_growth_d1", "mse", 1, lengths=(9, 4, 7, 5, 6, 3, 8))
+            prob, theta = cases.make_case("series_growth_d1", "mse", 1, lengths=(9, 4, 7, 5, 6, 3, 8, 4, 5, 6, 7, 8, 9, 3, 4, 5, 6, 7))
         else:
-            prob, theta = cases.make_case("node_d8", "cond_lik", 0, lengths=(6, 5, 9, 4, 7, 3, 8, 2), hidden=128)
+            prob, theta = cases.make_case("node_d8", "cond_lik", 0, lengths=(6, 5, 9, 4, 7, 3, 8, 2, 6, 5, 4, 3, 7, 8, 9, 2, 5), hidden=128)
         L_ref, g_ref = oracle.loss_grad(prob, theta)
         sh = ude.sharding.shard_problem(prob, theta, rank, world)
         n_u = sh.uhat_slices[0][1] - sh.uhat_slices[0][0]
