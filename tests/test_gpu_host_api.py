@@ -123,3 +123,34 @@ def test_ensemble_times_folds_in_one_handle(ude):
         solo = ude.NODE(tr[mi], hidden_units=10, seed=[1, 7, 9][mi // 2])
         ude.train_(solo, "conditional likelihood", verbose=False, optim_options=opts)
         assert np.max(np.abs(solo.parameters - models[mi].parameters)) < 1e-9
+
+
+def test_leave_future_out_predict_matches_oracle_steps(ude):
+    """leave_future_out_predict (src/CrossValidation.jl:608-640; the reference's test only checks it runs,
+    test/cross_validation.jl:62): every one-step change must equal the oracle's flow from the observed start."""
+    from oracle import ude_oracle_np as onp
+    df = ude.LotkaVolterra(plot=False, datasize=26)
+    model = ude.NODE(df, hidden_units=10, seed=5)
+    fitted = []
+
+    def training(m):
+        ude.train_(m, "conditional likelihood", verbose=False, optim_options=dict(maxiter=3, step_size=0.01))
+        fitted.append(m)
+
+    summary, raw = ude.leave_future_out_predict(model, training, 3, 2)
+    assert list(summary.columns) == ["variable", "MSE", "MSE_SE", "MAE", "MAE_SE", "correlation", "count"]
+    assert list(summary["count"]) == [6, 6] and len(raw) == 12 and len(fitted) == 2
+    d = df.sort_values("time").reset_index(drop=True)
+    n = len(d)
+    for fold, m in enumerate(fitted):
+        i = 3 * (fold + 1)
+        test = d.iloc[n - i - 1: n - i + 3]
+        prob = ude.default_loss(m)
+        tt = test["time"].to_numpy(); Y = test[["x1", "x2"]].to_numpy().T
+        for j in range(3):
+            p1 = np.real(onp.flow(prob, m.process_model, 0, 0, Y[:, j], tt[j], tt[j + 1]))
+            for v, name in enumerate(["x1", "x2"]):
+                row = raw[(raw["time"] == tt[j + 1]) & (raw["variable"] == name)]
+                assert len(row) == 1
+                assert abs(row["predicted"].iloc[0] - (p1[v] - Y[v, j])) < 1e-10
+                assert abs(row["observed"].iloc[0] - (Y[v, j + 1] - Y[v, j])) < 1e-14

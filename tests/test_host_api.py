@@ -115,3 +115,21 @@ def test_stack_models_is_independent_folds(ude):
         Li, gi = oracle.loss_grad(ude.conditional_likelihood(f), f.parameters)
         lo = int(big.theta_base[i])
         assert abs(L[i] - Li[0]) < 1e-12 * abs(Li[0]) and np.allclose(g[lo:lo + gi.shape[0]], gi, rtol=1e-12, atol=1e-14)
+
+
+def test_simulated_data_sets(ude):
+    """LotkaVolterra / LorenzLotkaVolterra / simulate_coral_data (src/SimulateData.jl:21-55, :80-118, :244-276): shapes, columns,
+    determinism in the seed, and the noise-free limit against SciPy's adaptive solver."""
+    from scipy.integrate import solve_ivp
+    df = ude.LotkaVolterra(plot=False, seed=7, datasize=40, T=2.0, sigma=0.0)
+    assert list(df.columns) == ["time", "x1", "x2"] and len(df) == 40
+    sol = solve_ivp(lambda t, u: [4 * u[0] - 5 * u[0] * u[1], 0.75 * 5 * u[0] * u[1] - 5 * u[1]], (0, 2.0), [1.0, 0.5],
+                    t_eval=df["time"].to_numpy(), rtol=1e-10, atol=1e-12)
+    assert np.max(np.abs(sol.y[0] - df["x1"])) < 1e-5 and np.max(np.abs(sol.y[1] - df["x2"])) < 1e-5
+    a, b = ude.LotkaVolterra(seed=1), ude.LotkaVolterra(seed=1)
+    assert a.equals(b) and not a.equals(ude.LotkaVolterra(seed=2))
+    data, X = ude.LorenzLotkaVolterra(plot=False, datasize=30)
+    assert list(data.columns) == ["time", "x1", "x2"] and list(X.columns) == ["time", "X"] and len(X) == 30
+    assert np.all(np.isfinite(data.to_numpy())) and np.all(np.isfinite(X.to_numpy()))
+    data, X = ude.simulate_coral_data()
+    assert list(data.columns) == ["time", "A", "C"] and len(data) == 125 and data["time"].iloc[-1] == 249

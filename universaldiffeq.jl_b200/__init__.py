@@ -4,7 +4,7 @@ Host-side mirror of the reference's API for the hot path only (SURVEY.md section
 train!, cross-validation drivers, all calling libude_cuda.so through its C ABI (include/ude_cuda.h).
 The directory name carries a dot, so import it through the repo-root shim:  ``import ude_b200 as ude``.
 """
-from . import problem, synthetic, sharding  # noqa: F401
+from . import problem, synthetic, sharding, simulate  # noqa: F401
 from .problem import Problem  # noqa: F401
 from . import _capi  # noqa: F401
 from ._capi import Engine, UdeError, device_count, measure_fp64_peak, get_unique_id, load_library, LIB_PATH  # noqa: F401
@@ -12,4 +12,6 @@ from .models import (CustomDerivatives, NODE, MultiNODE, MultiCustomDerivatives,
                      LV_UDE, LV_UDE_X, LV_UDE_ABS, FISHERY, node_rhs, node_time_rhs, nn_decay_rhs, series_growth_rhs, UDE)
 from .training import (train_, gradient_descent_, conditional_likelihood, default_loss, multiple_shooting_loss, shooting_loss,  # noqa: F401
                        derivative_matching_loss, errors_to_matrix, build_problem, predictions, forecast, adam_host)
-from .cross_validation import leave_future_out, leave_future_out_batched, summarize_leave_future_out, kfold_cv, stack_models  # noqa: F401
+from .cross_validation import (leave_future_out, leave_future_out_batched, leave_future_out_predict, summarize_leave_future_out,  # noqa: F401
+                               kfold_cv, stack_models)
+from .simulate import LotkaVolterra, LorenzLotkaVolterra, simulate_coral_data  # noqa: F401

@@ -149,6 +149,38 @@ def leave_future_out_batched(model: UDE, k: int, skip: int = 1, loss_function="c
     return models, train, test, forecasts, trace
 
 
+def leave_future_out_predict(model: UDE, training: Callable[[UDE], None], n_per_fold: int, k_folds: int, device=0):
+    """leave_future_out_predict(model, training!, n_per_fold, k_folds) (src/CrossValidation.jl:608-640): fold i trains on
+    data[1:end-i*n_per_fold] and is scored on one-step-ahead CHANGES over the following n_per_fold intervals (the last
+    training-side point is included as the first start).  Returns (summary, raw) like summarize_cv_results (:525-564):
+    per variable MSE, MSE_SE, MAE, MAE_SE, correlation, count; raw has time, variable, observed, predicted, AE, SE."""
+    from .training import predictions
+    if model.multi:
+        raise NotImplementedError("leave_future_out_predict is defined for single-series models in the reference")
+    data = model.data_frame.sort_values(model.time_column_name).reset_index(drop=True)
+    n = len(data)
+    rows = []
+    for i in range(n_per_fold, n_per_fold * k_folds + 1, n_per_fold):
+        train_i, test_i = data.iloc[: n - i], data.iloc[n - i - 1: n - i + n_per_fold]
+        m = model.constructor(train_i)
+        training(m)
+        inits, obs, preds = predictions(m, test_i, device=device)
+        tt = np.sort(test_i[model.time_column_name].to_numpy(dtype=np.float64))[1:]
+        for v, name in enumerate(model.varnames):
+            for j in range(tt.shape[0]):
+                rows.append((tt[j], name, obs[v, j] - inits[v, j], preds[v, j] - inits[v, j]))
+    raw = pd.DataFrame(rows, columns=[model.time_column_name, "variable", "observed", "predicted"])
+    raw["AE"] = (raw.observed - raw.predicted).abs()
+    raw["SE"] = (raw.observed - raw.predicted) ** 2
+    se = lambda x: x.std(ddof=1) / np.sqrt(len(x)) if len(x) > 1 else 0.0          # noqa: E731
+    out = []
+    for name, g in raw.groupby("variable", sort=False):
+        cor = np.corrcoef(g.observed, g.predicted)[0, 1] if len(g) > 1 else np.nan
+        out.append((name, g.SE.mean(), se(g.SE), g.AE.mean(), se(g.AE), cor, len(g)))
+    summary = pd.DataFrame(out, columns=["variable", "MSE", "MSE_SE", "MAE", "MAE_SE", "correlation", "count"])
+    return summary, raw
+
+
 def kfold_cv(model: UDE, training: Callable[[UDE, float], None], k: int = 10):
     """kfold_cv (src/CrossValidation.jl:167-195): k single-interval hold-outs via the t_skip loss variant; `training(model, t_skip)`
     must fit with that interval left out.  Returns the one-step prediction errors at the skipped intervals."""

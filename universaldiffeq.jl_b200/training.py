@@ -213,11 +213,31 @@ def gradient_descent_(model: UDE, step_size=0.05, maxiter=500, verbose=False, de
     return train_(model, "default", verbose=verbose, optim_options=dict(step_size=step_size, maxiter=maxiter), device=device)
 
 
-def predictions(model: UDE, device=0):
-    """One-step-ahead predictions F(uhat_{t-1}) for every column (src/ModelTesting.jl:181-195)."""
-    prob = default_loss(model)
-    with Engine(prob, device=device) as eng:
-        return eng.forward(model.parameters)
+def predictions(model: UDE, test_data=None, device=0):
+    """predictions(UDE) -> one-step-ahead predictions F(uhat_{t-1}) for every column (src/ModelTesting.jl:181-195).
+    predictions(UDE, test_data) -> (inits, obs, preds): one step ahead between consecutive rows of `test_data`, started
+    from the observed values (src/ModelTesting.jl:245-260).  All intervals are one batch of segments on the GPU."""
+    if test_data is None:
+        prob = default_loss(model)
+        with Engine(prob, device=device) as eng:
+            return eng.forward(model.parameters)
+    if model.multi:
+        raise NotImplementedError("predictions(model, test_data) is defined for single-series models in the reference")
+    cols = [model.time_column_name] + list(model.varnames)
+    missing = [c for c in cols if c not in test_data.columns]
+    if missing:
+        raise ValueError(f"test data is missing columns {missing}")
+    td = test_data.sort_values(model.time_column_name)
+    m2 = copy.copy(model)
+    m2.times = td[model.time_column_name].to_numpy(dtype=np.float64)
+    m2.data = np.asfortranarray(td[list(model.varnames)].to_numpy(dtype=np.float64).T)
+    pr = m2.base_problem()
+    pr.loss_kind = P.LOSS_STATE_SPACE
+    pr.finalize()
+    theta = np.concatenate([np.asarray(m2.data).reshape(-1, order="F"), model.process_model])
+    with Engine(pr, device=device) as eng:
+        pred = eng.forward(theta)
+    return np.asarray(m2.data)[:, :-1].copy(), np.asarray(m2.data)[:, 1:].copy(), pred[:, 1:].copy()
 
 
 def forecast(model: UDE, u0, t0, times, series=0, device=0):
