@@ -218,3 +218,56 @@ def test_parity_fp32_mode(ude, rhs, hidden, loss):
             L, g = eng.loss_grad(theta)
         assert np.max(np.abs(L - L_ref) / np.abs(L_ref)) < TOL32, (L, L_ref)
         assert cases.relerr(g, g_ref) < TOL32, cases.relerr(g, g_ref)
+
+
+@pytest.mark.parametrize("name", ["c2", "c3", "c4", "c5"])
+def test_full_size_configs_sampled_and_additive(ude, name):
+    """BASELINE.json's configurations at FULL size (C2 10^4 series, C3 10^5 series, C4 10^4 models, C5 10^6 segments),
+    where the oracle cannot evaluate the whole problem in test time.  Size-independent properties instead:
+      * a series' uhat gradient depends on that series and the shared parameters only, so contiguous blocks of series cut
+        out of the full problem (sharding.shard_problem) and evaluated by the ORACLE must reproduce those slices of the
+        full-size GPU gradient (1e-10); for the many-model C4 the blocks are whole models: loss and every gradient entry;
+      * loss and shared-parameter gradient are additive over a partition of the series: GPU(first half) + GPU(second
+        half) = GPU(all), the regulariser counted once (1e-11);
+      * the evaluation is bitwise repeatable (single-model handles; many-model handles accumulate per-model sums with
+        FP64 atomics and repeat to rounding)."""
+    prob, theta = ude.synthetic.CONFIGS[name]()
+    theta = theta + 0.01 * np.random.default_rng(11).normal(size=theta.shape)
+    with ude.Engine(prob) as eng:
+        L, g = eng.loss_grad(theta)
+        L2, g2 = eng.loss_grad(theta)
+    if prob.n_models == 1:
+        assert np.array_equal(L, L2) and np.array_equal(g, g2)
+    else:   # many models: per-model sums are FP64 atomics across the warps that share a model -- order-dependent rounding only
+        assert cases.relerr(L, L2) < 1e-13 and cases.relerr(g, g2) < 1e-13
+    assert np.all(np.isfinite(L)) and np.all(np.isfinite(g))
+    rng = np.random.default_rng(5)
+    if prob.n_models > 1:
+        world = prob.n_models // 4
+        for r in [0, world - 1] + list(rng.integers(1, world - 1, 3)):
+            sh = ude.sharding.shard_problem(prob, theta, int(r), world)
+            Lo, go = oracle.loss_grad(sh.problem, sh.theta)
+            m0, m1 = sh.models
+            assert np.max(np.abs(L[m0:m1] - Lo) / np.abs(Lo)) < TOL
+            lo, hi = int(prob.theta_base[m0]), (int(prob.theta_base[m1]) if m1 < prob.n_models else prob.n_theta)
+            assert cases.relerr(g[lo:hi], go) < TOL
+        return
+    world = prob.n_series // 64
+    n_u = prob.d * prob.n_cols
+    for r in [0, world - 1] + list(rng.integers(1, world - 1, 3)):
+        sh = ude.sharding.shard_problem(prob, theta, int(r), world)
+        _, go = oracle.loss_grad(sh.problem, sh.theta)
+        glo, ghi, llo = sh.uhat_slices[0]
+        assert cases.relerr(g[glo:ghi], go[llo:llo + (ghi - glo)]) < TOL, (name, r)
+    parts = []
+    for r in range(2):
+        sh = ude.sharding.shard_problem(prob, theta, r, 2)
+        with ude.Engine(sh.problem) as eng:
+            Lr, gr = eng.loss_grad(sh.theta)
+        parts.append((sh, Lr, gr))
+    assert abs(parts[0][1][0] + parts[1][1][0] - L[0]) < 1e-11 * abs(L[0])
+    pm_sum = sum(gr[sh.uhat_slices[0][1] - sh.uhat_slices[0][0]:][:sh.pm_shared] for sh, _, gr in parts)
+    assert cases.relerr(pm_sum, g[n_u:n_u + parts[0][0].pm_shared]) < 1e-11
+    for sh, _, gr in parts:
+        glo, ghi, llo = sh.uhat_slices[0]
+        assert cases.relerr(gr[llo:llo + (ghi - glo)], g[glo:ghi]) < 1e-12

@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -65,8 +66,11 @@ struct NcclApi {
 };
 NcclApi g_nccl;
 
+std::mutex g_nccl_mutex;
+
 bool nccl_load(std::string& err) {
-  if (g_nccl.lib) return true;
+  std::lock_guard<std::mutex> lock(g_nccl_mutex);      // handles on different host threads may get here together
+  if (g_nccl.lib && g_nccl.AllReduce) return true;
   const char* names[] = {"libnccl.so.2", "libnccl.so"};
   for (const char* nm : names) { g_nccl.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (g_nccl.lib) break; }
   if (!g_nccl.lib) { err = std::string("dlopen(libnccl.so.2) failed: ") + dlerror(); return false; }
