@@ -142,9 +142,6 @@ int ude_forward(ude_handle* h, const double* theta, int64_t n_theta, double* out
 int ude_comm_unique_id(void* id_bytes, int32_t n_bytes);
 int ude_comm_init(ude_handle* h, const void* id_bytes, int32_t n_bytes, int32_t n_ranks, int32_t rank);
 
-/* Device-resident Adam (Optimisers.jl semantics: beta=(0.9,0.999), eps=1e-8, bias-corrected), SURVEY.md 8f row 1.
- * Runs n_iter iterations of loss_grad + update without leaving the device; theta is read and written back.
- * loss_trace (n_iter doubles per model, may be NULL) receives the loss before each update. */
 /* Fused exchange over peer memory (NVLink / NVSwitch P2P) -- replaces the NCCL allreduce of ude_comm_init by ONE kernel
  * that finalises the block reduction, pushes [loss | shared process-model gradient] into every rank's exchange buffer
  * with peer stores, and sums the n_ranks contributions in rank order (bit-identical on all ranks).
@@ -159,10 +156,30 @@ int ude_comm_init(ude_handle* h, const void* id_bytes, int32_t n_bytes, int32_t 
 int ude_peer_export(ude_handle* h, int32_t n_ranks, void* blob, int32_t n_bytes);
 int ude_peer_attach(ude_handle* h, const void* blobs, int32_t n_ranks, int32_t rank);
 
+/* Device-resident Adam (Optimisers.jl semantics: beta=(0.9,0.999), eps=1e-8, bias-corrected), SURVEY.md 8f row 1.
+ * Runs n_iter iterations of loss_grad + update without leaving the device; theta is read and written back.
+ * loss_trace (n_iter doubles per model, may be NULL) receives the loss before each update. */
 int ude_adam(ude_handle* h, double* theta, int64_t n_theta, double step_size, int32_t n_iter, double* loss_trace);
 /* 1 if the last ude_adam call replayed a captured CUDA graph (one iteration = memset + segment kernel + finalize + update),
  * which is what makes small, launch-bound models train at kernel speed; UDE_ADAM_GRAPH=0 disables it. */
 int ude_adam_used_graph(const ude_handle* h);
+
+
+/* Unscented-Kalman-filter marginal likelihood (src/UnscentedKalmanFilter.jl:2-87; LFC.jl:103-127, :427-476):
+ *   loss = - sum_series sum_t loglik_t + reg * (|W1|^2 + |W2|^2),  P_nu = F F' with F = pnu_factor (d x d, column-major),
+ * identity observation model, P_eta fixed, first state = first observation (as the reference).  uhat does not enter the
+ * loss (its gradient is returned as zeros).  The 2d+1 sigma-point predicts of every step run through the same fused RK
+ * kernels as the other losses.  One model per handle, no per-series parameter vector. */
+typedef struct ude_ukf_opts {
+  double alpha, beta, kappa;                 /* reference defaults 1e-3, 2, 0 (src/Optimizers.jl:408) */
+  double reg;                                /* total weight of (|W1|^2 + |W2|^2) */
+  double Peta[UDE_MAX_D * UDE_MAX_D];        /* observation covariance, d x d column-major */
+} ude_ukf_opts;
+int ude_ukf_loss_grad(ude_handle* h, const ude_ukf_opts* opts, const double* theta, int64_t n_theta, const double* pnu_factor,
+                      double* loss, double* grad_theta /* n_theta or NULL */, double* grad_pnu_factor /* d*d or NULL */);
+/* ukf_smoothing: filtered means (d x n_cols) and covariances (d x d x n_cols, may be NULL; zero at a series' first column) */
+int ude_ukf_filter(ude_handle* h, const ude_ukf_opts* opts, const double* theta, int64_t n_theta, const double* pnu_factor,
+                   double* states, double* covariances);
 
 /* Kernel timing for roofline reports: after ude_profile_begin(h, n) the next n evaluations bracket the segment
  * kernel (the dominant launch) with CUDA events on the launching stream; ude_profile_read synchronises and returns

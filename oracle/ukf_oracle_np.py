@@ -1,0 +1,110 @@
+"""NumPy restatement of the reference's unscented-Kalman-filter marginal likelihood.  TEST INFRASTRUCTURE ONLY.
+
+PARITY UNPINNED (no Julia in this image; the reference's tests hold no golden values for this loss).  Follows
+  /root/reference/src/UnscentedKalmanFilter.jl:2-8     sigma_points  (upper Cholesky factor of (lambda+L) Px, weights)
+  /root/reference/src/UnscentedKalmanFilter.jl:10-55   ukf_update    (2L+1 predicts, mean, covariance, gain, log-likelihood with
+                                                                      the literal 3.14159 in the normalising constant)
+  /root/reference/src/UnscentedKalmanFilter.jl:59-87   ukf_smoothing / ukf_likelihood (x1 = y[:,1], Px = P_eta, steps 2..T)
+  /root/reference/src/LossFunctionConstructors.jl:103-127 (UDE)  :427-476 (MultiUDE: regulariser once per series plus once)
+with the one-interval predict F(u, t, dt) of the fixed-step solver (oracle/ude_oracle_np.flow).  dtype-generic: with a
+complex theta the loss is analytic in it (no conj, |.| or comparisons on values), so `complex_step_grad` yields the
+gradient that the CUDA path's hand-written adjoint is tested against.  Pure Python loops: small cases only.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import ude_oracle_np as onp
+
+
+def chol_upper(A):
+    """U upper triangular with U^T U = A, reading only the upper triangle of A (Julia: cholesky(Hermitian(A)).U)."""
+    n = A.shape[0]
+    U = np.zeros((n, n), dtype=A.dtype)
+    for i in range(n):
+        s = A[i, i]
+        for k in range(i):
+            s = s - U[k, i] * U[k, i]
+        U[i, i] = np.sqrt(s)
+        for j in range(i + 1, n):
+            s = A[i, j]
+            for k in range(i):
+                s = s - U[k, i] * U[k, j]
+            U[i, j] = s / U[i, i]
+    return U
+
+
+def weights(L, alpha, beta, kappa):
+    lam = alpha ** 2 * (L - kappa) - L
+    return lam + L, lam / (lam + L), lam / (lam + L) + (1 - alpha ** 2 + beta), 1.0 / (2 * (L + lam))
+
+
+def ukf_update(y, x, Px, f, Pnu, Peta, L, alpha, beta, kappa):
+    c, Wm0, Wc0, Wi = weights(L, alpha, beta, kappa)
+    U = chol_upper(c * Px)
+    pts = [f(x)] + [f(x + U[i, :]) for i in range(L)] + [f(x - U[i, :]) for i in range(L)]
+    m = Wm0 * pts[0]
+    for q in pts[1:]:
+        m = m + Wi * q
+    P1 = Wc0 * np.outer(pts[0] - m, pts[0] - m)
+    for q in pts[1:]:
+        P1 = P1 + Wi * np.outer(q - m, q - m)
+    P1 = P1 + Pnu
+    S = P1 + Peta
+    Sinv = np.linalg.inv(S)
+    K = P1 @ Sinv
+    r = y - m
+    xn = m + K @ r
+    Pn = P1 - K @ P1
+    ll = -0.5 * (r @ (Sinv @ r)) - 0.5 * np.log(np.linalg.det(S)) - L / 2 * np.log(2 * 3.14159)
+    return xn, Pn, ll
+
+
+def filter_series(p, pm, s, Pnu, Peta, alpha, beta, kappa, dtype=float):
+    """(sum of log-likelihood terms, filtered states d x n, covariances d x d x n) of series s."""
+    d = p.d
+    c0, n = int(p.starts[s]), int(p.lengths[s])
+    y = p.data[:, c0:c0 + n]
+    tt = p.times[c0:c0 + n]
+    x = y[:, 0].astype(dtype)
+    Px = np.asarray(Peta, dtype=dtype)
+    xs = np.zeros((d, n), dtype=dtype); Ps = np.zeros((d, d, n), dtype=dtype)
+    xs[:, 0] = x
+    ll = 0
+    for t in range(1, n):
+        f = lambda u, t0=tt[t - 1], t1=tt[t]: onp.flow(p, pm, s, s, u, t0, t1)      # noqa: E731
+        x, Px, l1 = ukf_update(y[:, t], x, Px, f, Pnu, Peta, d, alpha, beta, kappa)
+        ll = ll + l1
+        xs[:, t] = x; Ps[:, :, t] = Px
+    return ll, xs, Ps
+
+
+def loss(p, theta, pnu, Peta, alpha=1e-3, beta=2.0, kappa=0.0, reg_weight=0.0, reg_mult=1.0):
+    """-sum_series loglik + reg_mult * reg_weight * (|W1|^2 + |W2|^2).  theta = [uhat | process_model] of a single-model
+    problem (uhat does not enter); pnu = d x d factor with P_nu = pnu pnu^T.  reg_mult = 1 (UDE) or n_series + 1 (MultiUDE)."""
+    theta = np.asarray(theta); pnu = np.asarray(pnu)
+    dtype = complex if (np.iscomplexobj(theta) or np.iscomplexobj(pnu)) else float
+    d = p.d
+    pm = theta[d * p.n_cols: d * p.n_cols + p.n_pm]
+    Lf = pnu.reshape(d, d, order="F")
+    Pnu = Lf @ Lf.T
+    tot = 0
+    for s in range(p.n_series):
+        tot = tot - filter_series(p, pm, s, Pnu, Peta, alpha, beta, kappa, dtype)[0]
+    w1 = pm[p.off_w1:p.off_w1 + p.nn_hidden * p.nn_in]; w2 = pm[p.off_w2:p.off_w2 + p.nn_out * p.nn_hidden]
+    return tot + reg_mult * reg_weight * (np.sum(w1 * w1) + np.sum(w2 * w2))
+
+
+def complex_step_grad(p, theta, pnu, Peta, eps=1e-30, **kw):
+    """(d loss / d process_model, d loss / d pnu) by complex step."""
+    d = p.d
+    n_u = d * p.n_cols
+    g_pm = np.zeros(p.n_pm); g_nu = np.zeros(d * d)
+    th = np.asarray(theta, dtype=complex); pv = np.asarray(pnu, dtype=complex).reshape(-1, order="F")
+    for k in range(p.n_pm):
+        t2 = th.copy(); t2[n_u + k] += 1j * eps
+        g_pm[k] = np.imag(loss(p, t2, pv.reshape(d, d, order="F"), Peta, **kw)) / eps
+    for k in range(d * d):
+        p2 = pv.copy(); p2[k] += 1j * eps
+        g_nu[k] = np.imag(loss(p, th, p2.reshape(d, d, order="F"), Peta, **kw)) / eps
+    return g_pm, g_nu

@@ -1,0 +1,86 @@
+"""Unscented-Kalman-filter marginal likelihood on the GPU (ude_ukf_loss_grad / ude_ukf_filter) against the NumPy restatement
+(oracle/ukf_oracle_np.py): loss, complex-step gradient w.r.t. process model and process-noise factor, filtered states.
+
+Tolerances.  With alpha = 1 the sigma-point weights are O(1) and the bar is the FP64 bar, 1e-10.  The reference's DEFAULT
+alpha = 1e-3 gives weights Wm0 ~ -1e6, Wi ~ +5e5/L that cancel six digits in the mean and again in the covariance, so two
+correct FP64 implementations whose tanh differs in the last bit agree to ~1e-6 only: that case is tested at 1e-5 and the
+conditioning is part of the reference's algorithm (src/UnscentedKalmanFilter.jl:2-8), not of this implementation."""
+import numpy as np
+import pytest
+
+import cases
+from oracle import ukf_oracle_np as ukf
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(rhs, hidden, lengths, solver, seed=0):
+    prob, theta = cases.make_case(rhs, "cond_lik", solver, hidden=hidden, lengths=lengths, seed=seed)
+    d = prob.d
+    rng = np.random.default_rng(seed + 1)
+    F = 0.3 * np.eye(d) + 0.05 * rng.normal(size=(d, d))
+    Peta = 0.1 * np.eye(d) + 0.02 * np.ones((d, d))
+    return prob, theta, F, Peta
+
+
+@pytest.mark.parametrize("rhs,hidden,lengths", [("node_d2", 5, (7,)), ("node_d2", 5, (6, 3, 1, 4)), ("lv_ude_abs", 4, (6,)),
+                                                ("node_d4x1", 6, (4, 3)), ("node_time_d3", 5, (5, 2)), ("nn_decay_d1", 3, (9,))])
+@pytest.mark.parametrize("solver", [0, 1])
+def test_ukf_parity_alpha_one(ude, rhs, hidden, lengths, solver):
+    prob, theta, F, Peta = _setup(rhs, hidden, lengths, solver)
+    ref = ukf.loss(prob, theta, F, Peta, alpha=1.0, reg_weight=1e-3, reg_mult=2.0)
+    g_pm, g_F = ukf.complex_step_grad(prob, theta, F, Peta, alpha=1.0, reg_weight=1e-3, reg_mult=2.0)
+    with ude.Engine(prob) as eng:
+        L, g, gF = eng.ukf_loss_grad(theta, F, Peta, alpha=1.0, reg=2e-3)
+        L2, _, _ = eng.ukf_loss_grad(theta, F, Peta, alpha=1.0, reg=2e-3, want_grad=False)
+    n_u = prob.d * prob.n_cols
+    assert abs(L - ref) < 1e-10 * abs(ref) and L2 == L
+    assert np.all(g[:n_u] == 0.0)
+    assert cases.relerr(g[n_u:], g_pm) < 1e-10
+    assert cases.relerr(gF.reshape(-1, order="F"), g_F) < 1e-10
+
+
+def test_ukf_reference_default_alpha(ude):
+    prob, theta, F, Peta = _setup("node_d2", 5, (8, 5), 0)
+    ref = ukf.loss(prob, theta, F, Peta, alpha=1e-3)
+    g_pm, g_F = ukf.complex_step_grad(prob, theta, F, Peta, alpha=1e-3)
+    with ude.Engine(prob) as eng:
+        L, g, gF = eng.ukf_loss_grad(theta, F, Peta)
+    n_u = prob.d * prob.n_cols
+    assert abs(L - ref) < 1e-5 * abs(ref)
+    assert cases.relerr(g[n_u:], g_pm) < 1e-4
+    assert cases.relerr(gF.reshape(-1, order="F"), g_F) < 1e-4
+
+
+def test_ukf_filter_states(ude):
+    prob, theta, F, Peta = _setup("node_d2", 5, (7, 4, 1), 0)
+    n_u = prob.d * prob.n_cols
+    pm = theta[n_u:n_u + prob.n_pm]
+    with ude.Engine(prob) as eng:
+        xs, Ps = eng.ukf_filter(theta, F, Peta, alpha=1.0)
+    for s in range(prob.n_series):
+        _, xr, Pr = ukf.filter_series(prob, pm, s, F @ F.T, Peta, 1.0, 2.0, 0.0)
+        c0, n = int(prob.starts[s]), int(prob.lengths[s])
+        assert np.max(np.abs(xs[:, c0:c0 + n] - xr)) < 1e-11
+        assert np.max(np.abs(Ps[:, :, c0:c0 + n] - Pr)) < 1e-11
+
+
+def test_ukf_linear_dynamics_known_answer(ude):
+    """zero network + linear decay: the unscented transform is exact, the loss is the textbook Kalman filter's."""
+    from oracle import ude_oracle_np as onp
+    prob, theta = cases.make_case("nn_decay_d1", "cond_lik", 0, hidden=3, lengths=(9,))
+    n_u = prob.d * prob.n_cols
+    theta[n_u + prob.off_w2: n_u + prob.off_w2 + prob.nn_out * prob.nn_hidden] = 0.0
+    theta[n_u + prob.off_b2: n_u + prob.off_b2 + prob.nn_out] = 0.0
+    pm = theta[n_u:]
+    y, tt = prob.data[0], prob.times
+    x, P, ll = y[0], 0.05, 0.0
+    for t in range(1, len(y)):
+        a = onp.flow(prob, pm, 0, 0, np.array([1.0]), tt[t - 1], tt[t])[0]
+        m, P1 = a * x, a * a * P + 0.04
+        S = P1 + 0.05
+        ll += -0.5 * (y[t] - m) ** 2 / S - 0.5 * np.log(S) - 0.5 * np.log(2 * 3.14159)
+        x, P = m + P1 / S * (y[t] - m), P1 - P1 / S * P1
+    with ude.Engine(prob) as eng:
+        L, _, _ = eng.ukf_loss_grad(theta, np.array([[0.2]]), np.array([[0.05]]), alpha=1.0)
+    assert abs(L + ll) < 1e-12 * abs(ll)

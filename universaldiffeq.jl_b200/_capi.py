@@ -28,7 +28,13 @@ EXPORTS = ["ude_abi_version", "ude_device_count", "ude_create", "ude_destroy", "
            "ude_set_model_weights", "ude_set_covariates", "ude_set_targets", "ude_set_skip", "ude_n_theta",
            "ude_n_models", "ude_steps_per_eval", "ude_kernel_name", "ude_launches_per_eval", "ude_loss_grad", "ude_loss_grad_device",
            "ude_forward", "ude_comm_unique_id", "ude_comm_init", "ude_adam", "ude_adam_used_graph", "ude_profile_begin", "ude_profile_read",
-           "ude_measure_fp64_peak", "ude_measure_fp32_peak", "ude_peer_export", "ude_peer_attach"]
+           "ude_measure_fp64_peak", "ude_measure_fp32_peak", "ude_peer_export", "ude_peer_attach",
+           "ude_ukf_loss_grad", "ude_ukf_filter"]
+
+
+class UkfOpts(C.Structure):
+    """ude_ukf_opts (include/ude_cuda.h)"""
+    _fields_ = [("alpha", C.c_double), ("beta", C.c_double), ("kappa", C.c_double), ("reg", C.c_double), ("Peta", C.c_double * 64)]
 
 
 class UdeDesc(C.Structure):
@@ -115,6 +121,10 @@ def load_library():
     lib.ude_profile_read.argtypes = [vp, dp, i32]
     lib.ude_measure_fp64_peak.restype = C.c_int
     lib.ude_measure_fp64_peak.argtypes = [i32, C.POINTER(C.c_double)]
+    lib.ude_ukf_loss_grad.restype = C.c_int
+    lib.ude_ukf_loss_grad.argtypes = [vp, C.POINTER(UkfOpts), dp, i64, dp, dp, dp, dp]
+    lib.ude_ukf_filter.restype = C.c_int
+    lib.ude_ukf_filter.argtypes = [vp, C.POINTER(UkfOpts), dp, i64, dp, dp, dp]
     lib.ude_peer_export.restype = C.c_int
     lib.ude_peer_export.argtypes = [vp, i32, vp, i32]
     lib.ude_peer_attach.restype = C.c_int
@@ -298,6 +308,45 @@ class Engine:
 
     def adam_used_graph(self) -> bool:
         return bool(self.lib.ude_adam_used_graph(self.handle))
+
+    def _ukf_opts(self, Peta, alpha, beta, kappa, reg):
+        o = UkfOpts()
+        o.alpha, o.beta, o.kappa, o.reg = float(alpha), float(beta), float(kappa), float(reg)
+        d = self.problem.d
+        Pe = np.asarray(Peta, dtype=np.float64).reshape(d, d)
+        for j in range(d):
+            for i in range(d):
+                o.Peta[i + d * j] = Pe[i, j]
+        return o
+
+    def ukf_loss_grad(self, theta, pnu_factor, Peta, alpha=1e-3, beta=2.0, kappa=0.0, reg=0.0, want_grad=True):
+        """Unscented-Kalman-filter marginal likelihood (src/UnscentedKalmanFilter.jl:76-87): returns
+        (loss, grad_theta, grad_pnu_factor) with P_nu = F F', F = pnu_factor (d x d)."""
+        d = self.problem.d
+        th = np.ascontiguousarray(theta, dtype=np.float64)
+        F = np.ascontiguousarray(np.asarray(pnu_factor, dtype=np.float64).reshape(d, d).T)      # column-major bytes
+        o = self._ukf_opts(Peta, alpha, beta, kappa, reg)
+        loss = C.c_double(0.0)
+        g = np.zeros_like(th) if want_grad else None
+        gF = np.zeros((d, d)) if want_grad else None
+        rc = self.lib.ude_ukf_loss_grad(self.handle, C.byref(o), th.ctypes.data, th.shape[0], F.ctypes.data, C.addressof(loss),
+                                        g.ctypes.data if want_grad else None, gF.ctypes.data if want_grad else None)
+        if rc != UDE_OK and rc != UDE_NONFINITE:
+            self._check(rc)
+        return float(loss.value), g, (gF.T.copy() if want_grad else None)
+
+    def ukf_filter(self, theta, pnu_factor, Peta, alpha=1e-3, beta=2.0, kappa=0.0):
+        """ukf_smoothing (src/UnscentedKalmanFilter.jl:59-72): filtered states (d x n_cols) and covariances (d x d x n_cols)."""
+        d = self.problem.d
+        th = np.ascontiguousarray(theta, dtype=np.float64)
+        F = np.ascontiguousarray(np.asarray(pnu_factor, dtype=np.float64).reshape(d, d).T)
+        o = self._ukf_opts(Peta, alpha, beta, kappa, 0.0)
+        xs = np.zeros((d, self.problem.n_cols), order="F")
+        Ps = np.zeros((d, d, self.problem.n_cols), order="F")
+        rc = self.lib.ude_ukf_filter(self.handle, C.byref(o), th.ctypes.data, th.shape[0], F.ctypes.data, xs.ctypes.data, Ps.ctypes.data)
+        if rc != UDE_OK and rc != UDE_NONFINITE:
+            self._check(rc)
+        return xs, Ps
 
     def peer_export(self, n_ranks: int) -> bytes:
         """Allocate this rank's exchange buffer; returns the 128-byte blob the other ranks attach with."""

@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -85,6 +86,8 @@ bool nccl_load(std::string& err) {
 
 }  // namespace
 
+namespace { struct ude_ukf_plan; }
+
 struct ude_handle {
   ude_desc desc{};
   int device = 0;
@@ -111,6 +114,8 @@ struct ude_handle {
   long long stash_rows_per_warp = 0;
   size_t smem_bytes = 0, smem_bytes_fwd = 0;
   int adam_used_graph = 0;
+  std::vector<int64_t> model_task0;     // many-model handles: tasks of model m are [model_task0[m], model_task0[m + 1])
+  ude_ukf_plan* ukf = nullptr;          // unscented-Kalman-filter loss (ude_ukf.cuh), built on first use
   // multi-GPU
   void* comm = nullptr;
   int n_ranks = 1, rank = 0;
@@ -405,9 +410,10 @@ int build_plan(ude_handle* h) {
     while (segs.size() % SPW) { Seg z = segs.back(); z.flags |= ude::SEG_NULL; z.L = 0; segs.push_back(z); }
   };
   int64_t cur_model = -1;
+  h->model_task0.assign((size_t)h->n_models + 1, 0);
   for (int64_t s = 0; s < h->n_series; ++s) {
     const int64_t m = h->model_of_series[s], c0 = h->starts[s], len = h->lengths[s];
-    if (m != cur_model) { if (!segs.empty()) pad_model(); cur_model = m; }
+    if (m != cur_model) { if (!segs.empty()) pad_model(); cur_model = m; h->model_task0[(size_t)m] = (int64_t)segs.size() / SPW; }
     auto push = [&](int64_t col, int64_t L, uint16_t flags) {
       Seg z; z.col = (int32_t)col; z.series = (int32_t)s; z.L = (int16_t)L; z.flags = flags; z.model = (int32_t)m;
       segs.push_back(z);
@@ -442,6 +448,7 @@ int build_plan(ude_handle* h) {
   if (segs.empty()) return fail(h, UDE_ERR_INVALID, "no segments (empty data)");
   pad_model();
   h->n_tasks = (int64_t)segs.size() / SPW;
+  h->model_task0[(size_t)h->n_models] = h->n_tasks;
   for (int64_t t = 0; t < h->n_tasks; ++t) {
     int64_t mx = 0;
     for (int q = 0; q < SPW; ++q) {
@@ -659,6 +666,8 @@ int finalize_eval(ude_handle* h, const double* d_theta, double* d_loss, double* 
 
 }  // namespace
 
+#include "ude_ukf.cuh"
+
 // ==================================================================================================================
 #pragma GCC visibility push(default)
 extern "C" {
@@ -709,6 +718,7 @@ int ude_create(const ude_desc* desc, ude_handle** out) {
 int ude_destroy(ude_handle* h) {
   if (!h) return UDE_OK;
   cudaSetDevice(h->device);
+  delete h->ukf;
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   for (int r = 0; r < UDE_MAX_PEERS; ++r) if (h->x_opened[r] && h->x_peer[r]) cudaIpcCloseMemHandle(h->x_peer[r]);
   if (h->x_local) cudaFree(h->x_local);
@@ -1028,6 +1038,27 @@ int ude_peer_attach(ude_handle* h, const void* blobs, int32_t n_ranks, int32_t r
   }
   h->n_ranks = n_ranks; h->rank = rank; h->x_attached = true; h->dirty = true;
   return UDE_OK;
+}
+
+int ude_ukf_loss_grad(ude_handle* h, const ude_ukf_opts* opts, const double* theta, int64_t n_theta, const double* pnu_factor,
+                      double* loss, double* grad_theta, double* grad_pnu_factor) {
+  if (!h) return UDE_ERR_INVALID;
+  if (!opts || !theta || !pnu_factor || !loss) return fail(h, UDE_ERR_INVALID, "null argument");
+  if (!h->have_data) return fail(h, UDE_ERR_STATE, "ude_set_data has not been called");
+  if (n_theta != h->n_theta) return fail(h, UDE_ERR_INVALID, "n_theta mismatch");
+  UDE_CUDA_TRY(h, cudaSetDevice(h->device));
+  return ukf_eval(h, opts, theta, pnu_factor, loss, grad_theta, grad_pnu_factor, nullptr, nullptr);
+}
+
+int ude_ukf_filter(ude_handle* h, const ude_ukf_opts* opts, const double* theta, int64_t n_theta, const double* pnu_factor,
+                   double* states, double* covariances) {
+  if (!h) return UDE_ERR_INVALID;
+  if (!opts || !theta || !pnu_factor || !states) return fail(h, UDE_ERR_INVALID, "null argument");
+  if (!h->have_data) return fail(h, UDE_ERR_STATE, "ude_set_data has not been called");
+  if (n_theta != h->n_theta) return fail(h, UDE_ERR_INVALID, "n_theta mismatch");
+  UDE_CUDA_TRY(h, cudaSetDevice(h->device));
+  double loss = 0.0;
+  return ukf_eval(h, opts, theta, pnu_factor, &loss, nullptr, nullptr, states, covariances);
 }
 
 int ude_adam(ude_handle* h, double* theta, int64_t n_theta, double step_size, int32_t n_iter, double* loss_trace) {

@@ -1,0 +1,547 @@
+// Unscented-Kalman-filter marginal likelihood on top of the segment kernels.
+//   reference: /root/reference/src/UnscentedKalmanFilter.jl:2-87 (sigma_points, ukf_update, ukf_likelihood, ukf_smoothing)
+//              /root/reference/src/LossFunctionConstructors.jl:103-127 (UDE), :427-476 (MultiUDE)
+// Included by ude_api.cu (needs ude_handle, build_plan, launch_segments).
+//
+// The filter is a recursion in time, parallel over series and over the 2d+1 sigma points of a step.  Every step k
+// (interval k -> k+1 of each series that still has one) is
+//     ukf_sigma_fwd   (thread per series)  U = chol((lambda+L) P); sigma points -> start columns of an AUXILIARY handle
+//     segment kernel  (forward)            the 2d+1 one-interval predicts of every active series: the same fused RK kernels
+//                                          as every other loss -- the auxiliary handle describes each sigma point as a
+//                                          two-column mini-series, one "model" per step so a step is a contiguous task range
+//     ukf_update_fwd  (thread per series)  mean, covariance, gain, posterior, log-likelihood term
+// and the reverse sweep runs the steps backwards:
+//     ukf_update_bwd  adjoint of the update -> lambda_j = dLoss/dy_j for every sigma point; written as the mini-series'
+//                     TARGET column  y_j - lambda_j / 2: with weight B = I the state-space loss r'Br, r = target - F, has
+//                     dLoss/dF = -2 r = lambda_j, so the ordinary loss+adjoint kernel returns J^T lambda_j in the gradient
+//                     of the start column and (dF/dp)^T lambda_j in the step's process-model gradient: an exact VJP with
+//                     an externally supplied seed, no kernel change
+//     segment kernel  (loss + adjoint)
+//     ukf_sigma_bwd   xbar = sum chibar_j, Ubar = chibar+ - chibar-, adjoint of the Cholesky factorisation -> Pbar.
+// tests/test_ukf_oracle.py holds the same reverse sweep in NumPy, checked against complex-step derivatives.
+#pragma once
+
+namespace {
+
+constexpr int UKF_MAXD = UDE_MAX_D;
+
+struct UkfConst {
+  int d, n_sig;                       // n_sig = 2d + 1
+  double c, Wm0, Wc0, Wi, ll_const;   // c = lambda + L
+  double Pnu[UKF_MAXD * UKF_MAXD];    // column-major d x d
+  double Peta[UKF_MAXD * UKF_MAXD];
+};
+
+struct UkfStep {
+  int n_act;                 // active series in this step
+  long long act0;            // offset into the active-series list / per-(step, series) storage
+  long long theta_base;      // aux theta offset of the step's model
+  long long col0;            // aux global column of the step's first mini-series
+  int k;                     // interval k -> k+1 inside each series
+};
+
+struct ude_ukf_plan {
+  ude_handle* aux = nullptr;
+  int d = 0, K = 0;
+  std::vector<UkfStep> steps;
+  DevBuf<int> d_active;
+  DevBuf<UkfStep> d_steps;
+  DevBuf<double> d_xprev, d_Pprev, d_U;               // per (step, active series)
+  DevBuf<double> d_x, d_P, d_xb, d_Pb, d_ll, d_pnub;  // per series
+  DevBuf<double> d_theta_aux, d_grad_aux, d_traj_aux;
+  DevBuf<double> d_pm, d_out, d_states, d_covs;
+  int64_t n_aux_theta = 0, n_aux_cols = 0;
+  ~ude_ukf_plan() { if (aux) ude_destroy(aux); }
+};
+
+// ---- small dense algebra, runtime d <= 8, column-major M[i + d*j] ---------------------------------------------------
+__device__ inline void ukf_chol_upper(const double* A, double* U, int d) {      // reads the upper triangle of A
+  for (int i = 0; i < d * d; ++i) U[i] = 0.0;
+  for (int i = 0; i < d; ++i) {
+    double s = A[i + d * i];
+    for (int k = 0; k < i; ++k) s -= U[k + d * i] * U[k + d * i];
+    const double p = sqrt(s);            // NaN for a non-positive pivot: the caller sees a non-finite loss
+    U[i + d * i] = p;
+    for (int j = i + 1; j < d; ++j) {
+      double t = A[i + d * j];
+      for (int k = 0; k < i; ++k) t -= U[k + d * i] * U[k + d * j];
+      U[i + d * j] = t / p;
+    }
+  }
+}
+
+// Ab (upper entries; the factorisation never reads the lower triangle) from Ub; Ub is destroyed
+__device__ inline void ukf_chol_upper_adjoint(const double* U, double* Ub, double* Ab, int d) {
+  for (int i = 0; i < d * d; ++i) Ab[i] = 0.0;
+  for (int i = d - 1; i >= 0; --i) {
+    const double p = U[i + d * i];
+    for (int j = d - 1; j > i; --j) {
+      const double sb = Ub[i + d * j] / p;
+      Ub[i + d * i] -= Ub[i + d * j] * U[i + d * j] / p;
+      Ab[i + d * j] = sb;
+      for (int k = 0; k < i; ++k) { Ub[k + d * i] -= sb * U[k + d * j]; Ub[k + d * j] -= sb * U[k + d * i]; }
+    }
+    const double sb = Ub[i + d * i] / (2.0 * p);
+    Ab[i + d * i] = sb;
+    for (int k = 0; k < i; ++k) Ub[k + d * i] -= 2.0 * sb * U[k + d * i];
+  }
+}
+
+// G = inv(S) by Gauss-Jordan with partial pivoting; returns det(S) (the reference: inv(S), log(det(S)))
+__device__ inline double ukf_inverse(const double* S, double* G, int d) {
+  double M[UKF_MAXD * UKF_MAXD];
+  for (int i = 0; i < d * d; ++i) { M[i] = S[i]; G[i] = 0.0; }
+  for (int i = 0; i < d; ++i) G[i + d * i] = 1.0;
+  double det = 1.0;
+  for (int c = 0; c < d; ++c) {
+    int piv = c; double best = fabs(M[c + d * c]);
+    for (int r = c + 1; r < d; ++r) if (fabs(M[r + d * c]) > best) { best = fabs(M[r + d * c]); piv = r; }
+    if (piv != c) {
+      for (int j = 0; j < d; ++j) {
+        double t = M[c + d * j]; M[c + d * j] = M[piv + d * j]; M[piv + d * j] = t;
+        t = G[c + d * j]; G[c + d * j] = G[piv + d * j]; G[piv + d * j] = t;
+      }
+      det = -det;
+    }
+    const double p = M[c + d * c];
+    det *= p;
+    const double ip = 1.0 / p;
+    for (int j = 0; j < d; ++j) { M[c + d * j] *= ip; G[c + d * j] *= ip; }
+    for (int r = 0; r < d; ++r) {
+      if (r == c) continue;
+      const double f = M[r + d * c];
+      if (f == 0.0) continue;
+      for (int j = 0; j < d; ++j) { M[r + d * j] -= f * M[c + d * j]; G[r + d * j] -= f * G[c + d * j]; }
+    }
+  }
+  return det;
+}
+
+// the quantities of one update, recomputed identically by the forward and the reverse kernel
+struct UkfUpdate {
+  double m[UKF_MAXD], r[UKF_MAXD];
+  double P1[UKF_MAXD * UKF_MAXD], G[UKF_MAXD * UKF_MAXD], Kg[UKF_MAXD * UKF_MAXD];
+  double det;
+};
+
+// Y: n_sig predictions, Y[j] at traj[d * (col_first + 2 j + 1) + i]
+__device__ inline void ukf_update_common(const UkfConst& C, const double* __restrict__ traj, long long col_first,
+                                         const double* __restrict__ y, UkfUpdate& W) {
+  const int d = C.d;
+  for (int i = 0; i < d; ++i) {
+    double s = C.Wm0 * traj[d * (col_first + 1) + i];
+    for (int j = 1; j < C.n_sig; ++j) s += C.Wi * traj[d * (col_first + 2 * j + 1) + i];
+    W.m[i] = s;
+  }
+  for (int a = 0; a < d; ++a)
+    for (int b = 0; b < d; ++b) {
+      double s = 0.0;
+      for (int j = 0; j < C.n_sig; ++j) {
+        const double w = j == 0 ? C.Wc0 : C.Wi;
+        const double ea = traj[d * (col_first + 2 * j + 1) + a] - W.m[a], eb = traj[d * (col_first + 2 * j + 1) + b] - W.m[b];
+        s += w * ea * eb;
+      }
+      W.P1[a + d * b] = s + C.Pnu[a + d * b];
+    }
+  double S[UKF_MAXD * UKF_MAXD];
+  for (int i = 0; i < d * d; ++i) S[i] = W.P1[i] + C.Peta[i];
+  W.det = ukf_inverse(S, W.G, d);
+  for (int a = 0; a < d; ++a)
+    for (int b = 0; b < d; ++b) {
+      double s = 0.0;
+      for (int k = 0; k < d; ++k) s += W.P1[a + d * k] * W.G[k + d * b];
+      W.Kg[a + d * b] = s;
+    }
+  for (int i = 0; i < d; ++i) W.r[i] = y[i] - W.m[i];
+}
+
+__global__ void ukf_init(int n_series, int d, const long long* __restrict__ starts, const double* __restrict__ data,
+                         UkfConst C, double* __restrict__ X, double* __restrict__ P, double* __restrict__ states,
+                         double* __restrict__ covs) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_series) return;
+  const long long c0 = starts[s];
+  for (int i = 0; i < d; ++i) { X[(long long)s * d + i] = data[d * c0 + i]; if (states) states[d * c0 + i] = data[d * c0 + i]; }
+  for (int i = 0; i < d * d; ++i) { P[(long long)s * d * d + i] = C.Peta[i]; if (covs) covs[(long long)d * d * c0 + i] = 0.0; }
+}
+
+__global__ void ukf_bcast_pm(const double* __restrict__ pm, long long n_pm, const UkfStep* __restrict__ steps, int K, int d, int n_sig,
+                             double* __restrict__ theta_aux) {
+  const int k = blockIdx.x;
+  if (k >= K) return;
+  double* dst = theta_aux + steps[k].theta_base + (long long)d * 2 * n_sig * steps[k].n_act;
+  for (long long i = threadIdx.x; i < n_pm; i += blockDim.x) dst[i] = pm[i];
+}
+
+__global__ void ukf_sigma_fwd(UkfStep st, UkfConst C, const int* __restrict__ active, const double* __restrict__ X,
+                              const double* __restrict__ P, double* __restrict__ xprev, double* __restrict__ Pprev,
+                              double* __restrict__ Usave, double* __restrict__ theta_aux) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= st.n_act) return;
+  const int d = C.d, s = active[st.act0 + a];
+  double x[UKF_MAXD], A[UKF_MAXD * UKF_MAXD], U[UKF_MAXD * UKF_MAXD];
+  for (int i = 0; i < d; ++i) { x[i] = X[(long long)s * d + i]; xprev[(st.act0 + a) * d + i] = x[i]; }
+  for (int i = 0; i < d * d; ++i) {
+    const double p = P[(long long)s * d * d + i];
+    Pprev[(st.act0 + a) * d * d + i] = p;
+    A[i] = C.c * p;
+  }
+  ukf_chol_upper(A, U, d);
+  for (int i = 0; i < d * d; ++i) Usave[(st.act0 + a) * d * d + i] = U[i];
+  double* th = theta_aux + st.theta_base + (long long)d * 2 * C.n_sig * a;     // this series' 2 n_sig columns
+  for (int i = 0; i < d; ++i) th[i] = x[i];                                    // sigma 0 -> column 0
+  for (int q = 0; q < d; ++q)
+    for (int i = 0; i < d; ++i) {
+      th[d * 2 * (1 + q) + i] = x[i] + U[q + d * i];                           // x + row q of U
+      th[d * 2 * (1 + d + q) + i] = x[i] - U[q + d * i];
+    }
+}
+
+__global__ void ukf_update_fwd(UkfStep st, UkfConst C, const int* __restrict__ active, const long long* __restrict__ starts,
+                               const double* __restrict__ data, const double* __restrict__ traj, double* __restrict__ X,
+                               double* __restrict__ P, double* __restrict__ ll, double* __restrict__ states, double* __restrict__ covs) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= st.n_act) return;
+  const int d = C.d, s = active[st.act0 + a];
+  const long long col = starts[s] + st.k + 1;
+  UkfUpdate W;
+  ukf_update_common(C, traj, st.col0 + 2LL * C.n_sig * a, data + d * col, W);
+  double q = 0.0;
+  for (int i = 0; i < d; ++i) {
+    double xi = W.m[i], gi = 0.0;
+    for (int j = 0; j < d; ++j) { xi += W.Kg[i + d * j] * W.r[j]; gi += W.G[i + d * j] * W.r[j]; }
+    X[(long long)s * d + i] = xi;
+    if (states) states[d * col + i] = xi;
+    q += W.r[i] * gi;
+  }
+  for (int i = 0; i < d; ++i)
+    for (int j = 0; j < d; ++j) {
+      double v = W.P1[i + d * j];
+      for (int k = 0; k < d; ++k) v -= W.Kg[i + d * k] * W.P1[k + d * j];
+      P[(long long)s * d * d + i + d * j] = v;
+      if (covs) covs[(long long)d * d * col + i + d * j] = v;
+    }
+  ll[s] += -0.5 * q - 0.5 * log(W.det) - C.ll_const;
+}
+
+// adjoint of the update for loss = -sum ll: in (xb, Pb) = d loss / d (posterior mean, covariance); out: target columns
+// y_j - lambda_j / 2 and this series' share of d loss / d P_nu
+__global__ void ukf_update_bwd(UkfStep st, UkfConst C, const int* __restrict__ active, const long long* __restrict__ starts,
+                               const double* __restrict__ data, const double* __restrict__ traj, const double* __restrict__ Xb,
+                               const double* __restrict__ Pb_in, double* __restrict__ pnub, double* __restrict__ theta_aux) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= st.n_act) return;
+  const int d = C.d, s = active[st.act0 + a];
+  const long long col = starts[s] + st.k + 1, cf = st.col0 + 2LL * C.n_sig * a;
+  UkfUpdate W;
+  ukf_update_common(C, traj, cf, data + d * col, W);
+  double xb[UKF_MAXD], Pb[UKF_MAXD * UKF_MAXD], Kb[UKF_MAXD * UKF_MAXD], rb[UKF_MAXD], mb[UKF_MAXD];
+  double P1b[UKF_MAXD * UKF_MAXD], Gb[UKF_MAXD * UKF_MAXD], T[UKF_MAXD * UKF_MAXD];
+  for (int i = 0; i < d; ++i) xb[i] = Xb[(long long)s * d + i];
+  for (int i = 0; i < d * d; ++i) Pb[i] = Pb_in[(long long)s * d * d + i];
+  // Kb = xb r' - Pb P1'
+  for (int i = 0; i < d; ++i)
+    for (int j = 0; j < d; ++j) {
+      double v = xb[i] * W.r[j];
+      for (int k = 0; k < d; ++k) v -= Pb[i + d * k] * W.P1[j + d * k];
+      Kb[i + d * j] = v;
+    }
+  // rb = K' xb + 0.5 (G + G') r ;  mb = xb - rb
+  for (int i = 0; i < d; ++i) {
+    double v = 0.0;
+    for (int k = 0; k < d; ++k) v += W.Kg[k + d * i] * xb[k] + 0.5 * (W.G[i + d * k] + W.G[k + d * i]) * W.r[k];
+    rb[i] = v; mb[i] = xb[i] - v;
+  }
+  // P1b = Pb - K' Pb + Kb G' ;  Gb = P1' Kb + 0.5 r r'
+  for (int i = 0; i < d; ++i)
+    for (int j = 0; j < d; ++j) {
+      double v = Pb[i + d * j], g = 0.5 * W.r[i] * W.r[j];
+      for (int k = 0; k < d; ++k) {
+        v += -W.Kg[k + d * i] * Pb[k + d * j] + Kb[i + d * k] * W.G[j + d * k];
+        g += W.P1[k + d * i] * Kb[k + d * j];
+      }
+      P1b[i + d * j] = v; Gb[i + d * j] = g;
+    }
+  // Sb = -G' Gb G' + 0.5 G' ;  P1b += Sb
+  for (int i = 0; i < d; ++i)
+    for (int j = 0; j < d; ++j) {
+      double v = 0.0;
+      for (int k = 0; k < d; ++k) v += W.G[k + d * i] * Gb[k + d * j];
+      T[i + d * j] = v;                  // G' Gb
+    }
+  for (int i = 0; i < d; ++i)
+    for (int j = 0; j < d; ++j) {
+      double v = 0.5 * W.G[j + d * i];
+      for (int k = 0; k < d; ++k) v -= T[i + d * k] * W.G[j + d * k];
+      P1b[i + d * j] += v;
+    }
+  for (int i = 0; i < d * d; ++i) pnub[(long long)s * d * d + i] += P1b[i];
+  // eb_j = w_j (P1b + P1b') e_j ; mb -= sum eb_j ; yb_j = eb_j + wm_j mb
+  double sumE[UKF_MAXD];
+  for (int i = 0; i < d; ++i) sumE[i] = 0.0;
+  double* th = theta_aux + st.theta_base + (long long)d * 2 * C.n_sig * a;
+  for (int j = 0; j < C.n_sig; ++j) {
+    const double w = j == 0 ? C.Wc0 : C.Wi;
+    for (int i = 0; i < d; ++i) {
+      double v = 0.0;
+      for (int k = 0; k < d; ++k) v += (P1b[i + d * k] + P1b[k + d * i]) * (traj[d * (cf + 2 * j + 1) + k] - W.m[k]);
+      v *= w;
+      sumE[i] += v;
+      th[d * (2 * j + 1) + i] = v;       // eb_j parked in the target column; finished below
+    }
+  }
+  for (int i = 0; i < d; ++i) mb[i] -= sumE[i];
+  for (int j = 0; j < C.n_sig; ++j) {
+    const double wm = j == 0 ? C.Wm0 : C.Wi;
+    for (int i = 0; i < d; ++i) {
+      const double lam = th[d * (2 * j + 1) + i] + wm * mb[i];
+      th[d * (2 * j + 1) + i] = traj[d * (cf + 2 * j + 1) + i] - 0.5 * lam;
+    }
+  }
+}
+
+__global__ void ukf_sigma_bwd(UkfStep st, UkfConst C, const int* __restrict__ active, const double* __restrict__ Usave,
+                              const double* __restrict__ grad_aux, double* __restrict__ Xb, double* __restrict__ Pb) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= st.n_act) return;
+  const int d = C.d, s = active[st.act0 + a];
+  const double* g = grad_aux + st.theta_base + (long long)d * 2 * C.n_sig * a;
+  double U[UKF_MAXD * UKF_MAXD], Ub[UKF_MAXD * UKF_MAXD], Ab[UKF_MAXD * UKF_MAXD];
+  for (int i = 0; i < d * d; ++i) U[i] = Usave[(st.act0 + a) * d * d + i];
+  for (int i = 0; i < d; ++i) {
+    double v = 0.0;
+    for (int j = 0; j < C.n_sig; ++j) v += g[d * 2 * j + i];
+    Xb[(long long)s * d + i] = v;
+  }
+  for (int q = 0; q < d; ++q)
+    for (int i = 0; i < d; ++i) Ub[q + d * i] = g[d * 2 * (1 + q) + i] - g[d * 2 * (1 + d + q) + i];
+  ukf_chol_upper_adjoint(U, Ub, Ab, d);
+  for (int i = 0; i < d * d; ++i) Pb[(long long)s * d * d + i] = C.c * Ab[i];
+}
+
+// out = [loss | d loss / d process_model (n_pm) | d loss / d Lf (d*d)], fixed summation order
+__global__ void ukf_finish(int n_series, int K, const UkfStep* __restrict__ steps, UkfConst C, const double* __restrict__ ll,
+                           const double* __restrict__ pnub, const double* __restrict__ grad_aux, const double* __restrict__ pm,
+                           long long n_pm, long long off_w1, long long n_w1, long long off_w2, long long n_w2, double reg,
+                           const double* __restrict__ Lf, int want_grad, double* __restrict__ out) {
+  const int d = C.d;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    double L = 0.0;
+    for (int s = 0; s < n_series; ++s) L -= ll[s];
+    double r = 0.0;
+    for (long long i = 0; i < n_w1; ++i) r = fma(pm[off_w1 + i], pm[off_w1 + i], r);
+    for (long long i = 0; i < n_w2; ++i) r = fma(pm[off_w2 + i], pm[off_w2 + i], r);
+    out[0] = L + reg * r;
+  }
+  if (!want_grad) return;
+  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n_pm + d * d; k += (long long)gridDim.x * blockDim.x) {
+    if (k < n_pm) {
+      double g = 0.0;
+      for (int q = 0; q < K; ++q) g += grad_aux[steps[q].theta_base + (long long)d * 2 * C.n_sig * steps[q].n_act + k];
+      const bool isw = (k >= off_w1 && k < off_w1 + n_w1) || (k >= off_w2 && k < off_w2 + n_w2);
+      if (isw) g = fma(2.0 * reg, pm[k], g);
+      out[1 + k] = g;
+    } else {                       // Lf_bar = (Pnu_bar + Pnu_bar') Lf
+      const int e = (int)(k - n_pm), i = e % d, j = e / d;
+      double v = 0.0;
+      for (int q = 0; q < d; ++q) {
+        double pb = 0.0;
+        for (int s = 0; s < n_series; ++s) pb += pnub[(long long)s * d * d + i + d * q] + pnub[(long long)s * d * d + q + d * i];
+        v += pb * Lf[q + d * j];
+      }
+      out[1 + k] = v;
+    }
+  }
+}
+
+int ukf_build(ude_handle* h, ude_ukf_plan*& out_plan) {
+  const ude_desc& D = h->desc;
+  if (h->n_models != 1) return fail(h, UDE_ERR_UNSUPPORTED, "UKF loss: one model per handle");
+  if (D.has_series_param) return fail(h, UDE_ERR_UNSUPPORTED, "UKF loss: per-series parameter vectors are not supported");
+  if (D.dtype != UDE_F64) return fail(h, UDE_ERR_UNSUPPORTED, "UKF loss: FP64 only");
+  if (D.n_cov > 0 && !h->have_cov) return fail(h, UDE_ERR_STATE, "ude_set_covariates has not been called");
+  const int d = D.d, n_sig = 2 * d + 1;
+  std::unique_ptr<ude_ukf_plan> pl(new ude_ukf_plan());
+  pl->d = d;
+  int64_t max_len = 0;
+  for (int64_t s = 0; s < h->n_series; ++s) max_len = std::max(max_len, h->lengths[s]);
+  const int K = (int)(max_len - 1);
+  if (K < 1) return fail(h, UDE_ERR_INVALID, "UKF loss: every series has a single point");
+  pl->K = K;
+  // host copies of what the auxiliary description is made from
+  UDE_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  std::vector<double> times((size_t)h->n_cols);
+  UDE_CUDA_TRY(h, cudaMemcpy(times.data(), h->d_times.p, times.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  std::vector<long long> koff; std::vector<double> kt, kx;
+  if (D.n_cov > 0) {
+    koff.resize((size_t)h->n_series * D.n_cov + 1);
+    UDE_CUDA_TRY(h, cudaMemcpy(koff.data(), h->d_knot_off.p, koff.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    kt.resize((size_t)std::max<long long>(koff.back(), 1)); kx.resize(kt.size());
+    if (koff.back() > 0) {
+      UDE_CUDA_TRY(h, cudaMemcpy(kt.data(), h->d_knot_t.p, (size_t)koff.back() * sizeof(double), cudaMemcpyDeviceToHost));
+      UDE_CUDA_TRY(h, cudaMemcpy(kx.data(), h->d_knot_x.p, (size_t)koff.back() * sizeof(double), cudaMemcpyDeviceToHost));
+    }
+  }
+  std::vector<int> active;
+  std::vector<int64_t> a_starts, a_lengths, a_model, a_koff(1, 0);
+  std::vector<double> a_times, a_kt, a_kx;
+  int64_t col = 0, tbase = 0;
+  for (int k = 0; k < K; ++k) {
+    UkfStep st; st.k = k; st.act0 = (long long)active.size(); st.col0 = col; st.theta_base = tbase; st.n_act = 0;
+    for (int64_t s = 0; s < h->n_series; ++s) {
+      if (h->lengths[s] <= k + 1) continue;
+      active.push_back((int)s); ++st.n_act;
+      const double ta = times[(size_t)(h->starts[s] + k)], tb = times[(size_t)(h->starts[s] + k + 1)];
+      for (int j = 0; j < n_sig; ++j) {
+        a_starts.push_back(col); a_lengths.push_back(2); a_model.push_back(k);
+        a_times.push_back(ta); a_times.push_back(tb);
+        col += 2;
+        for (int v = 0; v < D.n_cov; ++v) {       // the knots that bracket [ta, tb] (flat extrapolation keeps the end knots)
+          const long long k0 = koff[(size_t)s * D.n_cov + v], k1 = koff[(size_t)s * D.n_cov + v + 1];
+          if (k1 == k0) { a_koff.push_back((int64_t)a_kt.size()); continue; }
+          long long lo = k0, hi = k1;              // [lo, hi)
+          while (lo + 1 < k1 && kt[(size_t)lo + 1] <= ta) ++lo;
+          hi = lo + 1;
+          while (hi < k1 && kt[(size_t)hi - 1] < tb) ++hi;
+          for (long long q = lo; q < hi; ++q) { a_kt.push_back(kt[(size_t)q]); a_kx.push_back(kx[(size_t)q]); }
+          a_koff.push_back((int64_t)a_kt.size());
+        }
+      }
+    }
+    if (st.n_act == 0) return fail(h, UDE_ERR_INVALID, "UKF loss: internal step without series");
+    tbase += (int64_t)d * 2 * n_sig * st.n_act + D.n_pm;
+    pl->steps.push_back(st);
+  }
+  pl->n_aux_cols = col; pl->n_aux_theta = tbase;
+  // the auxiliary handle: state-space loss r' I r on one-interval mini-series, one model per step
+  ude_desc A = D;
+  A.loss_kind = UDE_LOSS_STATE_SPACE; A.proc_inv_dt = 0; A.preroll_eps = 0.0;
+  A.lanes_per_segment = 0; A.hidden_per_lane = 0; A.weights_in_smem = 0;
+  for (int i = 0; i < UDE_MAX_D * UDE_MAX_D; ++i) { A.A[i] = 0.0; A.B[i] = 0.0; }
+  for (int i = 0; i < d; ++i) A.B[i + d * i] = 1.0;
+  int rc = ude_create(&A, &pl->aux);
+  if (rc != UDE_OK) return fail(h, rc, std::string("UKF auxiliary handle: ") + ude_last_error(nullptr));
+  auto aux_fail = [&](int code) { return fail(h, code, std::string("UKF auxiliary handle: ") + ude_last_error(pl->aux)); };
+  std::vector<double> zeros((size_t)d * (size_t)col, 0.0);
+  rc = ude_set_data(pl->aux, (int64_t)a_starts.size(), a_starts.data(), a_lengths.data(), a_model.data(), col, a_times.data(), zeros.data());
+  if (rc != UDE_OK) return aux_fail(rc);
+  std::vector<double> ones((size_t)K, 1.0), nulls((size_t)K, 0.0);
+  rc = ude_set_model_weights(pl->aux, nulls.data(), ones.data(), nulls.data(), nulls.data());
+  if (rc != UDE_OK) return aux_fail(rc);
+  if (D.n_cov > 0) {
+    if (a_kt.empty()) { a_kt.push_back(0.0); a_kx.push_back(0.0); }
+    rc = ude_set_covariates(pl->aux, a_koff.data(), a_kt.data(), a_kx.data());
+    if (rc != UDE_OK) return aux_fail(rc);
+  }
+  if (pl->aux->n_theta != pl->n_aux_theta) return fail(h, UDE_ERR_INVALID, "UKF loss: auxiliary layout mismatch");
+  rc = build_plan(pl->aux);
+  if (rc != UDE_OK) return aux_fail(rc);
+  if ((int)pl->aux->model_task0.size() != K + 1) return fail(h, UDE_ERR_INVALID, "UKF loss: auxiliary task map missing");
+  for (int k = 0; k < K; ++k)
+    if (pl->aux->theta_base[(size_t)k] != pl->steps[(size_t)k].theta_base) return fail(h, UDE_ERR_INVALID, "UKF loss: auxiliary layout mismatch");
+  cudaStream_t s = h->stream;
+  const size_t NA = active.size(), NS = (size_t)h->n_series;
+  UDE_CUDA_TRY(h, pl->d_active.upload(active.data(), NA, s));
+  UDE_CUDA_TRY(h, pl->d_steps.upload(pl->steps.data(), (size_t)K, s));
+  UDE_CUDA_TRY(h, pl->d_xprev.reserve(NA * d)); UDE_CUDA_TRY(h, pl->d_Pprev.reserve(NA * d * d)); UDE_CUDA_TRY(h, pl->d_U.reserve(NA * d * d));
+  UDE_CUDA_TRY(h, pl->d_x.reserve(NS * d)); UDE_CUDA_TRY(h, pl->d_P.reserve(NS * d * d));
+  UDE_CUDA_TRY(h, pl->d_xb.reserve(NS * d)); UDE_CUDA_TRY(h, pl->d_Pb.reserve(NS * d * d));
+  UDE_CUDA_TRY(h, pl->d_ll.reserve(NS)); UDE_CUDA_TRY(h, pl->d_pnub.reserve(NS * d * d));
+  UDE_CUDA_TRY(h, pl->d_theta_aux.reserve((size_t)pl->n_aux_theta));
+  UDE_CUDA_TRY(h, pl->d_grad_aux.reserve((size_t)pl->n_aux_theta));
+  UDE_CUDA_TRY(h, pl->d_traj_aux.reserve((size_t)d * (size_t)col));
+  UDE_CUDA_TRY(h, pl->d_pm.reserve((size_t)D.n_pm + (size_t)d * d));
+  UDE_CUDA_TRY(h, pl->d_out.reserve(1 + (size_t)D.n_pm + (size_t)d * d));
+  UDE_CUDA_TRY(h, cudaMemsetAsync(pl->d_theta_aux.p, 0, (size_t)pl->n_aux_theta * sizeof(double), s));
+  UDE_CUDA_TRY(h, cudaStreamSynchronize(s));
+  out_plan = pl.release();
+  return UDE_OK;
+}
+
+// One evaluation.  theta: host, n_theta; Lf: host d*d column-major (P_nu = Lf Lf').  states/covs (host, may be NULL):
+// filtered means d x n_cols and covariances d x d x n_cols (ukf_smoothing).
+int ukf_eval(ude_handle* h, const ude_ukf_opts* o, const double* theta, const double* Lf, double* loss, double* grad_theta,
+             double* grad_lf, double* states, double* covs) {
+  const ude_desc& D = h->desc;
+  if (!h->ukf) { int rc = ukf_build(h, h->ukf); if (rc != UDE_OK) return rc; }
+  ude_ukf_plan* pl = h->ukf;
+  const int d = D.d, n_sig = 2 * d + 1, K = pl->K;
+  UkfConst C; memset(&C, 0, sizeof C);
+  C.d = d; C.n_sig = n_sig;
+  const double lam = o->alpha * o->alpha * (d - o->kappa) - d;
+  C.c = lam + d; C.Wm0 = lam / (lam + d); C.Wc0 = lam / (lam + d) + (1.0 - o->alpha * o->alpha + o->beta);
+  C.Wi = 1.0 / (2.0 * (d + lam)); C.ll_const = 0.5 * d * log(2.0 * 3.14159);      // sic: the reference's constant
+  for (int i = 0; i < d; ++i)
+    for (int j = 0; j < d; ++j) {
+      double v = 0.0;
+      for (int k = 0; k < d; ++k) v += Lf[i + d * k] * Lf[j + d * k];
+      C.Pnu[i + d * j] = v; C.Peta[i + d * j] = o->Peta[i + d * j];
+    }
+  const bool want_grad = grad_theta != nullptr || grad_lf != nullptr;
+  const bool want_states = states != nullptr;
+  cudaStream_t s = h->stream;
+  ude_handle* ax = pl->aux;
+  const size_t NS = (size_t)h->n_series;
+  const long long n_u = (long long)d * h->n_cols;
+  UDE_CUDA_TRY(h, cudaMemcpyAsync(pl->d_pm.p, theta + n_u, (size_t)D.n_pm * sizeof(double), cudaMemcpyHostToDevice, s));
+  UDE_CUDA_TRY(h, cudaMemcpyAsync(pl->d_pm.p + D.n_pm, Lf, (size_t)d * d * sizeof(double), cudaMemcpyHostToDevice, s));
+  UDE_CUDA_TRY(h, cudaMemsetAsync(pl->d_ll.p, 0, NS * sizeof(double), s));
+  if (want_states) {
+    UDE_CUDA_TRY(h, pl->d_states.reserve((size_t)d * h->n_cols));
+    if (covs) UDE_CUDA_TRY(h, pl->d_covs.reserve((size_t)d * d * h->n_cols));
+  }
+  double* d_states = want_states ? pl->d_states.p : nullptr;
+  double* d_covs = (want_states && covs) ? pl->d_covs.p : nullptr;
+  const int TB = 64;
+  ukf_init<<<(int)((NS + TB - 1) / TB), TB, 0, s>>>((int)NS, d, h->d_starts.p, h->d_data.p, C, pl->d_x.p, pl->d_P.p, d_states, d_covs);
+  ukf_bcast_pm<<<K, 128, 0, s>>>(pl->d_pm.p, D.n_pm, pl->d_steps.p, K, d, n_sig, pl->d_theta_aux.p);
+  UDE_CUDA_TRY(h, cudaGetLastError());
+  for (int k = 0; k < K; ++k) {
+    const UkfStep& st = pl->steps[(size_t)k];
+    const int nb = (st.n_act + TB - 1) / TB;
+    ukf_sigma_fwd<<<nb, TB, 0, s>>>(st, C, pl->d_active.p, pl->d_x.p, pl->d_P.p, pl->d_xprev.p, pl->d_Pprev.p, pl->d_U.p, pl->d_theta_aux.p);
+    int rc = launch_segments(ax, pl->d_theta_aux.p, nullptr, pl->d_traj_aux.p, ax->model_task0[(size_t)k], ax->model_task0[(size_t)k + 1], 0, s);
+    if (rc != UDE_OK) return fail(h, rc, std::string("UKF predict: ") + ude_last_error(ax));
+    ukf_update_fwd<<<nb, TB, 0, s>>>(st, C, pl->d_active.p, h->d_starts.p, h->d_data.p, pl->d_traj_aux.p, pl->d_x.p, pl->d_P.p, pl->d_ll.p,
+                                     d_states, d_covs);
+  }
+  UDE_CUDA_TRY(h, cudaGetLastError());
+  if (want_grad) {
+    UDE_CUDA_TRY(h, cudaMemsetAsync(pl->d_grad_aux.p, 0, (size_t)pl->n_aux_theta * sizeof(double), s));
+    UDE_CUDA_TRY(h, cudaMemsetAsync(pl->d_xb.p, 0, NS * d * sizeof(double), s));
+    UDE_CUDA_TRY(h, cudaMemsetAsync(pl->d_Pb.p, 0, NS * d * d * sizeof(double), s));
+    UDE_CUDA_TRY(h, cudaMemsetAsync(pl->d_pnub.p, 0, NS * d * d * sizeof(double), s));
+    UDE_CUDA_TRY(h, cudaMemsetAsync(ax->d_model_loss.p, 0, (size_t)K * sizeof(double), s));
+    for (int k = K - 1; k >= 0; --k) {
+      const UkfStep& st = pl->steps[(size_t)k];
+      const int nb = (st.n_act + TB - 1) / TB;
+      ukf_update_bwd<<<nb, TB, 0, s>>>(st, C, pl->d_active.p, h->d_starts.p, h->d_data.p, pl->d_traj_aux.p, pl->d_xb.p, pl->d_Pb.p,
+                                       pl->d_pnub.p, pl->d_theta_aux.p);
+      int rc = launch_segments(ax, pl->d_theta_aux.p, pl->d_grad_aux.p, nullptr, ax->model_task0[(size_t)k], ax->model_task0[(size_t)k + 1], 0, s);
+      if (rc != UDE_OK) return fail(h, rc, std::string("UKF adjoint: ") + ude_last_error(ax));
+      ukf_sigma_bwd<<<nb, TB, 0, s>>>(st, C, pl->d_active.p, pl->d_U.p, pl->d_grad_aux.p, pl->d_xb.p, pl->d_Pb.p);
+    }
+    UDE_CUDA_TRY(h, cudaGetLastError());
+  }
+  const long long n_w1 = (long long)D.nn_hidden * D.nn_in, n_w2 = (long long)D.nn_out * D.nn_hidden;
+  ukf_finish<<<8, 128, 0, s>>>((int)NS, K, pl->d_steps.p, C, pl->d_ll.p, pl->d_pnub.p, pl->d_grad_aux.p, pl->d_pm.p, D.n_pm, D.off_w1, n_w1,
+                               D.off_w2, n_w2, o->reg, pl->d_pm.p + D.n_pm, want_grad ? 1 : 0, pl->d_out.p);
+  UDE_CUDA_TRY(h, cudaGetLastError());
+  std::vector<double> outv(1 + (size_t)D.n_pm + (size_t)d * d, 0.0);
+  UDE_CUDA_TRY(h, cudaMemcpyAsync(outv.data(), pl->d_out.p, (want_grad ? outv.size() : 1) * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (want_states) {
+    UDE_CUDA_TRY(h, cudaMemcpyAsync(states, d_states, (size_t)d * h->n_cols * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (covs) UDE_CUDA_TRY(h, cudaMemcpyAsync(covs, d_covs, (size_t)d * d * h->n_cols * sizeof(double), cudaMemcpyDeviceToHost, s));
+  }
+  UDE_CUDA_TRY(h, cudaStreamSynchronize(s));
+  if (loss) *loss = outv[0];
+  if (grad_theta) {
+    memset(grad_theta, 0, (size_t)h->n_theta * sizeof(double));      // uhat does not enter this loss
+    memcpy(grad_theta + n_u, outv.data() + 1, (size_t)D.n_pm * sizeof(double));
+  }
+  if (grad_lf) memcpy(grad_lf, outv.data() + 1 + D.n_pm, (size_t)d * d * sizeof(double));
+  if (!std::isfinite(outv[0])) return fail(h, UDE_NONFINITE, "UKF loss is not finite (covariance lost positive definiteness?)");
+  return UDE_OK;
+}
+
+}  // namespace
