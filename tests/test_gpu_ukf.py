@@ -84,3 +84,39 @@ def test_ukf_linear_dynamics_known_answer(ude):
     with ude.Engine(prob) as eng:
         L, _, _ = eng.ukf_loss_grad(theta, np.array([[0.2]]), np.array([[0.05]]), alpha=1.0)
     assert abs(L + ll) < 1e-12 * abs(ll)
+
+
+def test_train_marginal_likelihood(ude):
+    """train!(model, loss_function = "marginal likelihood") (test/UDETests.jl:45 only checks it runs): the loss must go down,
+    uhat must hold the filtered states and the returned P_nu must be the fitted factor's square."""
+    df = ude.LotkaVolterra(plot=False, datasize=20)
+    m = ude.NODE(df, hidden_units=6, seed=2)
+    out = ude.train_(m, "marginal likelihood", verbose=False, regularization_weight=1e-4,
+                     loss_options=dict(observation_error=0.05, alpha=1.0), optim_options=dict(maxiter=25, step_size=0.02))
+    Pnu, Px = out
+    tr = m.extra["loss_trace"]
+    assert tr[-1] < tr[0] and np.all(np.isfinite(tr))
+    assert Pnu.shape == (2, 2) and np.all(np.linalg.eigvalsh(Pnu) > 0) and Px.shape == (2, 2, 20)
+    assert np.allclose(m.uhat[:, 0], m.data[:, 0]) and np.all(np.isfinite(m.uhat))
+    # multi-series model: regulariser counted n_series + 1 times
+    Y, ts = ude.synthetic.lotka_volterra_data(np.random.default_rng(0), 3, 9, random_u0=True)
+    import pandas as pd
+    dfm = pd.concat([pd.DataFrame({"time": ts, "series": s, "x1": Y[s, 0], "x2": Y[s, 1]}) for s in range(3)], ignore_index=True)
+    mm = ude.MultiNODE(dfm, hidden_units=5, seed=1)
+    ude.train_(mm, "marginal likelihood", verbose=False, loss_options=dict(alpha=1.0), optim_options=dict(maxiter=5))
+    assert mm.extra["loss_trace"][-1] < mm.extra["loss_trace"][0]
+
+
+def test_ukf_graph_replay_equals_plain_launches(ude, monkeypatch):
+    prob, theta, F, Peta = _setup("node_d2", 5, (9, 4, 6), 0)
+    res = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("UDE_UKF_GRAPH", flag)
+        with ude.Engine(prob) as eng:
+            a = eng.ukf_loss_grad(theta, F, Peta, alpha=1.0)
+            b = eng.ukf_loss_grad(theta, 1.1 * F, Peta, alpha=1.0)       # a second call replays the captured graph with new constants
+            res.append((a, b))
+    for i in range(2):
+        assert res[0][i][0] == res[1][i][0]
+        assert np.array_equal(res[0][i][1], res[1][i][1]) and np.array_equal(res[0][i][2], res[1][i][2])
+    assert res[0][0][0] != res[0][1][0]

@@ -28,6 +28,7 @@ constexpr int UKF_MAXD = UDE_MAX_D;
 struct UkfConst {
   int d, n_sig;                       // n_sig = 2d + 1
   double c, Wm0, Wc0, Wi, ll_const;   // c = lambda + L
+  double reg;                         // weight of |W1|^2 + |W2|^2
   double Pnu[UKF_MAXD * UKF_MAXD];    // column-major d x d
   double Peta[UKF_MAXD * UKF_MAXD];
 };
@@ -50,20 +51,32 @@ struct ude_ukf_plan {
   DevBuf<double> d_x, d_P, d_xb, d_Pb, d_ll, d_pnub;  // per series
   DevBuf<double> d_theta_aux, d_grad_aux, d_traj_aux;
   DevBuf<double> d_pm, d_out, d_states, d_covs;
+  DevBuf<UkfConst> d_const;
+  cudaGraphExec_t exec[4] = {nullptr, nullptr, nullptr, nullptr};   // loss / loss+grad / filter / filter+covariances
+  int used_graph = 0;
   int64_t n_aux_theta = 0, n_aux_cols = 0;
-  ~ude_ukf_plan() { if (aux) ude_destroy(aux); }
+  ~ude_ukf_plan() {
+    for (cudaGraphExec_t e : exec) if (e) cudaGraphExecDestroy(e);
+    if (aux) ude_destroy(aux);
+  }
 };
 
-// ---- small dense algebra, runtime d <= 8, column-major M[i + d*j] ---------------------------------------------------
-__device__ inline void ukf_chol_upper(const double* A, double* U, int d) {      // reads the upper triangle of A
+// ---- small dense algebra, compile-time D <= 8 (everything stays in registers), column-major M[i + D*j] ---------------------------------------------------
+template <int d>
+__device__ __forceinline__ void ukf_chol_upper(const double* A, double* U) {      // reads the upper triangle of A
+  #pragma unroll
   for (int i = 0; i < d * d; ++i) U[i] = 0.0;
+  #pragma unroll
   for (int i = 0; i < d; ++i) {
     double s = A[i + d * i];
+    #pragma unroll
     for (int k = 0; k < i; ++k) s -= U[k + d * i] * U[k + d * i];
     const double p = sqrt(s);            // NaN for a non-positive pivot: the caller sees a non-finite loss
     U[i + d * i] = p;
+    #pragma unroll
     for (int j = i + 1; j < d; ++j) {
       double t = A[i + d * j];
+      #pragma unroll
       for (int k = 0; k < i; ++k) t -= U[k + d * i] * U[k + d * j];
       U[i + d * j] = t / p;
     }
@@ -71,46 +84,51 @@ __device__ inline void ukf_chol_upper(const double* A, double* U, int d) {      
 }
 
 // Ab (upper entries; the factorisation never reads the lower triangle) from Ub; Ub is destroyed
-__device__ inline void ukf_chol_upper_adjoint(const double* U, double* Ub, double* Ab, int d) {
+template <int d>
+__device__ __forceinline__ void ukf_chol_upper_adjoint(const double* U, double* Ub, double* Ab) {
+  #pragma unroll
   for (int i = 0; i < d * d; ++i) Ab[i] = 0.0;
+  #pragma unroll
   for (int i = d - 1; i >= 0; --i) {
     const double p = U[i + d * i];
+    #pragma unroll
     for (int j = d - 1; j > i; --j) {
       const double sb = Ub[i + d * j] / p;
       Ub[i + d * i] -= Ub[i + d * j] * U[i + d * j] / p;
       Ab[i + d * j] = sb;
+      #pragma unroll
       for (int k = 0; k < i; ++k) { Ub[k + d * i] -= sb * U[k + d * j]; Ub[k + d * j] -= sb * U[k + d * i]; }
     }
     const double sb = Ub[i + d * i] / (2.0 * p);
     Ab[i + d * i] = sb;
+    #pragma unroll
     for (int k = 0; k < i; ++k) Ub[k + d * i] -= 2.0 * sb * U[k + d * i];
   }
 }
 
-// G = inv(S) by Gauss-Jordan with partial pivoting; returns det(S) (the reference: inv(S), log(det(S)))
-__device__ inline double ukf_inverse(const double* S, double* G, int d) {
-  double M[UKF_MAXD * UKF_MAXD];
+// G = inv(S) by Gauss-Jordan WITHOUT pivoting (S = P1 + P_eta is symmetric positive definite while the filter is healthy;
+// a lost definiteness shows up as a non-finite loss); returns det(S) (the reference: inv(S), log(det(S))).  No pivot
+// search means no data-dependent indexing, so the matrices stay in registers.
+template <int d>
+__device__ __forceinline__ double ukf_inverse(const double* S, double* G) {
+  double M[d * d];
+  #pragma unroll
   for (int i = 0; i < d * d; ++i) { M[i] = S[i]; G[i] = 0.0; }
+  #pragma unroll
   for (int i = 0; i < d; ++i) G[i + d * i] = 1.0;
   double det = 1.0;
+  #pragma unroll
   for (int c = 0; c < d; ++c) {
-    int piv = c; double best = fabs(M[c + d * c]);
-    for (int r = c + 1; r < d; ++r) if (fabs(M[r + d * c]) > best) { best = fabs(M[r + d * c]); piv = r; }
-    if (piv != c) {
-      for (int j = 0; j < d; ++j) {
-        double t = M[c + d * j]; M[c + d * j] = M[piv + d * j]; M[piv + d * j] = t;
-        t = G[c + d * j]; G[c + d * j] = G[piv + d * j]; G[piv + d * j] = t;
-      }
-      det = -det;
-    }
     const double p = M[c + d * c];
     det *= p;
     const double ip = 1.0 / p;
+    #pragma unroll
     for (int j = 0; j < d; ++j) { M[c + d * j] *= ip; G[c + d * j] *= ip; }
+    #pragma unroll
     for (int r = 0; r < d; ++r) {
       if (r == c) continue;
       const double f = M[r + d * c];
-      if (f == 0.0) continue;
+      #pragma unroll
       for (int j = 0; j < d; ++j) { M[r + d * j] -= f * M[c + d * j]; G[r + d * j] -= f * G[c + d * j]; }
     }
   }
@@ -118,46 +136,58 @@ __device__ inline double ukf_inverse(const double* S, double* G, int d) {
 }
 
 // the quantities of one update, recomputed identically by the forward and the reverse kernel
+template <int d>
 struct UkfUpdate {
-  double m[UKF_MAXD], r[UKF_MAXD];
-  double P1[UKF_MAXD * UKF_MAXD], G[UKF_MAXD * UKF_MAXD], Kg[UKF_MAXD * UKF_MAXD];
+  double m[d], r[d];
+  double P1[d * d], G[d * d], Kg[d * d];
   double det;
 };
 
 // Y: n_sig predictions, Y[j] at traj[d * (col_first + 2 j + 1) + i]
-__device__ inline void ukf_update_common(const UkfConst& C, const double* __restrict__ traj, long long col_first,
-                                         const double* __restrict__ y, UkfUpdate& W) {
-  const int d = C.d;
+template <int d>
+__device__ __forceinline__ void ukf_update_common(const UkfConst& C, const double* __restrict__ traj, long long col_first,
+                                                  const double* __restrict__ y, UkfUpdate<d>& W) {
+  #pragma unroll
   for (int i = 0; i < d; ++i) {
     double s = C.Wm0 * traj[d * (col_first + 1) + i];
-    for (int j = 1; j < C.n_sig; ++j) s += C.Wi * traj[d * (col_first + 2 * j + 1) + i];
+    #pragma unroll
+    for (int j = 1; j < (2 * d + 1); ++j) s += C.Wi * traj[d * (col_first + 2 * j + 1) + i];
     W.m[i] = s;
   }
+  #pragma unroll
   for (int a = 0; a < d; ++a)
+    #pragma unroll
     for (int b = 0; b < d; ++b) {
       double s = 0.0;
-      for (int j = 0; j < C.n_sig; ++j) {
+      #pragma unroll
+      for (int j = 0; j < (2 * d + 1); ++j) {
         const double w = j == 0 ? C.Wc0 : C.Wi;
         const double ea = traj[d * (col_first + 2 * j + 1) + a] - W.m[a], eb = traj[d * (col_first + 2 * j + 1) + b] - W.m[b];
         s += w * ea * eb;
       }
       W.P1[a + d * b] = s + C.Pnu[a + d * b];
     }
-  double S[UKF_MAXD * UKF_MAXD];
+  double S[d * d];
+  #pragma unroll
   for (int i = 0; i < d * d; ++i) S[i] = W.P1[i] + C.Peta[i];
-  W.det = ukf_inverse(S, W.G, d);
+  W.det = ukf_inverse<d>(S, W.G);
+  #pragma unroll
   for (int a = 0; a < d; ++a)
+    #pragma unroll
     for (int b = 0; b < d; ++b) {
       double s = 0.0;
+      #pragma unroll
       for (int k = 0; k < d; ++k) s += W.P1[a + d * k] * W.G[k + d * b];
       W.Kg[a + d * b] = s;
     }
+  #pragma unroll
   for (int i = 0; i < d; ++i) W.r[i] = y[i] - W.m[i];
 }
 
 __global__ void ukf_init(int n_series, int d, const long long* __restrict__ starts, const double* __restrict__ data,
-                         UkfConst C, double* __restrict__ X, double* __restrict__ P, double* __restrict__ states,
+                         const UkfConst* __restrict__ Cp, double* __restrict__ X, double* __restrict__ P, double* __restrict__ states,
                          double* __restrict__ covs) {
+  const UkfConst& C = *Cp;
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n_series) return;
   const long long c0 = starts[s];
@@ -173,50 +203,65 @@ __global__ void ukf_bcast_pm(const double* __restrict__ pm, long long n_pm, cons
   for (long long i = threadIdx.x; i < n_pm; i += blockDim.x) dst[i] = pm[i];
 }
 
-__global__ void ukf_sigma_fwd(UkfStep st, UkfConst C, const int* __restrict__ active, const double* __restrict__ X,
+template <int d>
+__global__ void ukf_sigma_fwd(UkfStep st, const UkfConst* __restrict__ Cp, const int* __restrict__ active, const double* __restrict__ X,
                               const double* __restrict__ P, double* __restrict__ xprev, double* __restrict__ Pprev,
                               double* __restrict__ Usave, double* __restrict__ theta_aux) {
+  const UkfConst& C = *Cp;
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= st.n_act) return;
-  const int d = C.d, s = active[st.act0 + a];
-  double x[UKF_MAXD], A[UKF_MAXD * UKF_MAXD], U[UKF_MAXD * UKF_MAXD];
+  const int s = active[st.act0 + a];
+  double x[d], A[d * d], U[d * d];
+  #pragma unroll
   for (int i = 0; i < d; ++i) { x[i] = X[(long long)s * d + i]; xprev[(st.act0 + a) * d + i] = x[i]; }
+  #pragma unroll
   for (int i = 0; i < d * d; ++i) {
     const double p = P[(long long)s * d * d + i];
     Pprev[(st.act0 + a) * d * d + i] = p;
     A[i] = C.c * p;
   }
-  ukf_chol_upper(A, U, d);
+  ukf_chol_upper<d>(A, U);
+  #pragma unroll
   for (int i = 0; i < d * d; ++i) Usave[(st.act0 + a) * d * d + i] = U[i];
-  double* th = theta_aux + st.theta_base + (long long)d * 2 * C.n_sig * a;     // this series' 2 n_sig columns
+  double* th = theta_aux + st.theta_base + (long long)d * 2 * (2 * d + 1) * a;     // this series' 2 n_sig columns
+  #pragma unroll
   for (int i = 0; i < d; ++i) th[i] = x[i];                                    // sigma 0 -> column 0
+  #pragma unroll
   for (int q = 0; q < d; ++q)
+    #pragma unroll
     for (int i = 0; i < d; ++i) {
       th[d * 2 * (1 + q) + i] = x[i] + U[q + d * i];                           // x + row q of U
       th[d * 2 * (1 + d + q) + i] = x[i] - U[q + d * i];
     }
 }
 
-__global__ void ukf_update_fwd(UkfStep st, UkfConst C, const int* __restrict__ active, const long long* __restrict__ starts,
+template <int d>
+__global__ void ukf_update_fwd(UkfStep st, const UkfConst* __restrict__ Cp, const int* __restrict__ active, const long long* __restrict__ starts,
                                const double* __restrict__ data, const double* __restrict__ traj, double* __restrict__ X,
                                double* __restrict__ P, double* __restrict__ ll, double* __restrict__ states, double* __restrict__ covs) {
+  const UkfConst& C = *Cp;
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= st.n_act) return;
-  const int d = C.d, s = active[st.act0 + a];
+  const int s = active[st.act0 + a];
   const long long col = starts[s] + st.k + 1;
-  UkfUpdate W;
-  ukf_update_common(C, traj, st.col0 + 2LL * C.n_sig * a, data + d * col, W);
+  UkfUpdate<d> W;
+  ukf_update_common(C, traj, st.col0 + 2LL * (2 * d + 1) * a, data + d * col, W);
   double q = 0.0;
+  #pragma unroll
   for (int i = 0; i < d; ++i) {
     double xi = W.m[i], gi = 0.0;
+    #pragma unroll
     for (int j = 0; j < d; ++j) { xi += W.Kg[i + d * j] * W.r[j]; gi += W.G[i + d * j] * W.r[j]; }
     X[(long long)s * d + i] = xi;
     if (states) states[d * col + i] = xi;
     q += W.r[i] * gi;
   }
+  #pragma unroll
   for (int i = 0; i < d; ++i)
+    #pragma unroll
     for (int j = 0; j < d; ++j) {
       double v = W.P1[i + d * j];
+      #pragma unroll
       for (int k = 0; k < d; ++k) v -= W.Kg[i + d * k] * W.P1[k + d * j];
       P[(long long)s * d * d + i + d * j] = v;
       if (covs) covs[(long long)d * d * col + i + d * j] = v;
@@ -226,36 +271,48 @@ __global__ void ukf_update_fwd(UkfStep st, UkfConst C, const int* __restrict__ a
 
 // adjoint of the update for loss = -sum ll: in (xb, Pb) = d loss / d (posterior mean, covariance); out: target columns
 // y_j - lambda_j / 2 and this series' share of d loss / d P_nu
-__global__ void ukf_update_bwd(UkfStep st, UkfConst C, const int* __restrict__ active, const long long* __restrict__ starts,
+template <int d>
+__global__ void ukf_update_bwd(UkfStep st, const UkfConst* __restrict__ Cp, const int* __restrict__ active, const long long* __restrict__ starts,
                                const double* __restrict__ data, const double* __restrict__ traj, const double* __restrict__ Xb,
                                const double* __restrict__ Pb_in, double* __restrict__ pnub, double* __restrict__ theta_aux) {
+  const UkfConst& C = *Cp;
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= st.n_act) return;
-  const int d = C.d, s = active[st.act0 + a];
-  const long long col = starts[s] + st.k + 1, cf = st.col0 + 2LL * C.n_sig * a;
-  UkfUpdate W;
+  const int s = active[st.act0 + a];
+  const long long col = starts[s] + st.k + 1, cf = st.col0 + 2LL * (2 * d + 1) * a;
+  UkfUpdate<d> W;
   ukf_update_common(C, traj, cf, data + d * col, W);
-  double xb[UKF_MAXD], Pb[UKF_MAXD * UKF_MAXD], Kb[UKF_MAXD * UKF_MAXD], rb[UKF_MAXD], mb[UKF_MAXD];
-  double P1b[UKF_MAXD * UKF_MAXD], Gb[UKF_MAXD * UKF_MAXD], T[UKF_MAXD * UKF_MAXD];
+  double xb[d], Pb[d * d], Kb[d * d], rb[d], mb[d];
+  double P1b[d * d], Gb[d * d], T[d * d];
+  #pragma unroll
   for (int i = 0; i < d; ++i) xb[i] = Xb[(long long)s * d + i];
+  #pragma unroll
   for (int i = 0; i < d * d; ++i) Pb[i] = Pb_in[(long long)s * d * d + i];
   // Kb = xb r' - Pb P1'
+  #pragma unroll
   for (int i = 0; i < d; ++i)
+    #pragma unroll
     for (int j = 0; j < d; ++j) {
       double v = xb[i] * W.r[j];
+      #pragma unroll
       for (int k = 0; k < d; ++k) v -= Pb[i + d * k] * W.P1[j + d * k];
       Kb[i + d * j] = v;
     }
   // rb = K' xb + 0.5 (G + G') r ;  mb = xb - rb
+  #pragma unroll
   for (int i = 0; i < d; ++i) {
     double v = 0.0;
+    #pragma unroll
     for (int k = 0; k < d; ++k) v += W.Kg[k + d * i] * xb[k] + 0.5 * (W.G[i + d * k] + W.G[k + d * i]) * W.r[k];
     rb[i] = v; mb[i] = xb[i] - v;
   }
   // P1b = Pb - K' Pb + Kb G' ;  Gb = P1' Kb + 0.5 r r'
+  #pragma unroll
   for (int i = 0; i < d; ++i)
+    #pragma unroll
     for (int j = 0; j < d; ++j) {
       double v = Pb[i + d * j], g = 0.5 * W.r[i] * W.r[j];
+      #pragma unroll
       for (int k = 0; k < d; ++k) {
         v += -W.Kg[k + d * i] * Pb[k + d * j] + Kb[i + d * k] * W.G[j + d * k];
         g += W.P1[k + d * i] * Kb[k + d * j];
@@ -263,36 +320,50 @@ __global__ void ukf_update_bwd(UkfStep st, UkfConst C, const int* __restrict__ a
       P1b[i + d * j] = v; Gb[i + d * j] = g;
     }
   // Sb = -G' Gb G' + 0.5 G' ;  P1b += Sb
+  #pragma unroll
   for (int i = 0; i < d; ++i)
+    #pragma unroll
     for (int j = 0; j < d; ++j) {
       double v = 0.0;
+      #pragma unroll
       for (int k = 0; k < d; ++k) v += W.G[k + d * i] * Gb[k + d * j];
       T[i + d * j] = v;                  // G' Gb
     }
+  #pragma unroll
   for (int i = 0; i < d; ++i)
+    #pragma unroll
     for (int j = 0; j < d; ++j) {
       double v = 0.5 * W.G[j + d * i];
+      #pragma unroll
       for (int k = 0; k < d; ++k) v -= T[i + d * k] * W.G[j + d * k];
       P1b[i + d * j] += v;
     }
+  #pragma unroll
   for (int i = 0; i < d * d; ++i) pnub[(long long)s * d * d + i] += P1b[i];
   // eb_j = w_j (P1b + P1b') e_j ; mb -= sum eb_j ; yb_j = eb_j + wm_j mb
-  double sumE[UKF_MAXD];
+  double sumE[d];
+  #pragma unroll
   for (int i = 0; i < d; ++i) sumE[i] = 0.0;
-  double* th = theta_aux + st.theta_base + (long long)d * 2 * C.n_sig * a;
-  for (int j = 0; j < C.n_sig; ++j) {
+  double* th = theta_aux + st.theta_base + (long long)d * 2 * (2 * d + 1) * a;
+  #pragma unroll
+  for (int j = 0; j < (2 * d + 1); ++j) {
     const double w = j == 0 ? C.Wc0 : C.Wi;
+    #pragma unroll
     for (int i = 0; i < d; ++i) {
       double v = 0.0;
+      #pragma unroll
       for (int k = 0; k < d; ++k) v += (P1b[i + d * k] + P1b[k + d * i]) * (traj[d * (cf + 2 * j + 1) + k] - W.m[k]);
       v *= w;
       sumE[i] += v;
       th[d * (2 * j + 1) + i] = v;       // eb_j parked in the target column; finished below
     }
   }
+  #pragma unroll
   for (int i = 0; i < d; ++i) mb[i] -= sumE[i];
-  for (int j = 0; j < C.n_sig; ++j) {
+  #pragma unroll
+  for (int j = 0; j < (2 * d + 1); ++j) {
     const double wm = j == 0 ? C.Wm0 : C.Wi;
+    #pragma unroll
     for (int i = 0; i < d; ++i) {
       const double lam = th[d * (2 * j + 1) + i] + wm * mb[i];
       th[d * (2 * j + 1) + i] = traj[d * (cf + 2 * j + 1) + i] - 0.5 * lam;
@@ -300,31 +371,41 @@ __global__ void ukf_update_bwd(UkfStep st, UkfConst C, const int* __restrict__ a
   }
 }
 
-__global__ void ukf_sigma_bwd(UkfStep st, UkfConst C, const int* __restrict__ active, const double* __restrict__ Usave,
+template <int d>
+__global__ void ukf_sigma_bwd(UkfStep st, const UkfConst* __restrict__ Cp, const int* __restrict__ active, const double* __restrict__ Usave,
                               const double* __restrict__ grad_aux, double* __restrict__ Xb, double* __restrict__ Pb) {
+  const UkfConst& C = *Cp;
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= st.n_act) return;
-  const int d = C.d, s = active[st.act0 + a];
-  const double* g = grad_aux + st.theta_base + (long long)d * 2 * C.n_sig * a;
-  double U[UKF_MAXD * UKF_MAXD], Ub[UKF_MAXD * UKF_MAXD], Ab[UKF_MAXD * UKF_MAXD];
+  const int s = active[st.act0 + a];
+  const double* g = grad_aux + st.theta_base + (long long)d * 2 * (2 * d + 1) * a;
+  double U[d * d], Ub[d * d], Ab[d * d];
+  #pragma unroll
   for (int i = 0; i < d * d; ++i) U[i] = Usave[(st.act0 + a) * d * d + i];
+  #pragma unroll
   for (int i = 0; i < d; ++i) {
     double v = 0.0;
-    for (int j = 0; j < C.n_sig; ++j) v += g[d * 2 * j + i];
+    #pragma unroll
+    for (int j = 0; j < (2 * d + 1); ++j) v += g[d * 2 * j + i];
     Xb[(long long)s * d + i] = v;
   }
+  #pragma unroll
   for (int q = 0; q < d; ++q)
+    #pragma unroll
     for (int i = 0; i < d; ++i) Ub[q + d * i] = g[d * 2 * (1 + q) + i] - g[d * 2 * (1 + d + q) + i];
-  ukf_chol_upper_adjoint(U, Ub, Ab, d);
+  ukf_chol_upper_adjoint<d>(U, Ub, Ab);
+  #pragma unroll
   for (int i = 0; i < d * d; ++i) Pb[(long long)s * d * d + i] = C.c * Ab[i];
 }
 
 // out = [loss | d loss / d process_model (n_pm) | d loss / d Lf (d*d)], fixed summation order
-__global__ void ukf_finish(int n_series, int K, const UkfStep* __restrict__ steps, UkfConst C, const double* __restrict__ ll,
+__global__ void ukf_finish(int n_series, int K, const UkfStep* __restrict__ steps, const UkfConst* __restrict__ Cp, const double* __restrict__ ll,
                            const double* __restrict__ pnub, const double* __restrict__ grad_aux, const double* __restrict__ pm,
-                           long long n_pm, long long off_w1, long long n_w1, long long off_w2, long long n_w2, double reg,
+                           long long n_pm, long long off_w1, long long n_w1, long long off_w2, long long n_w2,
                            const double* __restrict__ Lf, int want_grad, double* __restrict__ out) {
+  const UkfConst& C = *Cp;
   const int d = C.d;
+  const double reg = C.reg;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     double L = 0.0;
     for (int s = 0; s < n_series; ++s) L -= ll[s];
@@ -337,7 +418,7 @@ __global__ void ukf_finish(int n_series, int K, const UkfStep* __restrict__ step
   for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n_pm + d * d; k += (long long)gridDim.x * blockDim.x) {
     if (k < n_pm) {
       double g = 0.0;
-      for (int q = 0; q < K; ++q) g += grad_aux[steps[q].theta_base + (long long)d * 2 * C.n_sig * steps[q].n_act + k];
+      for (int q = 0; q < K; ++q) g += grad_aux[steps[q].theta_base + (long long)d * 2 * (2 * d + 1) * steps[q].n_act + k];
       const bool isw = (k >= off_w1 && k < off_w1 + n_w1) || (k >= off_w2 && k < off_w2 + n_w2);
       if (isw) g = fma(2.0 * reg, pm[k], g);
       out[1 + k] = g;
@@ -353,6 +434,14 @@ __global__ void ukf_finish(int n_series, int K, const UkfStep* __restrict__ step
     }
   }
 }
+
+#define UKF_DISPATCH(dd, KERNEL, ...)                                                        \
+  switch (dd) {                                                                              \
+    case 1: KERNEL<1> __VA_ARGS__; break; case 2: KERNEL<2> __VA_ARGS__; break;              \
+    case 3: KERNEL<3> __VA_ARGS__; break; case 4: KERNEL<4> __VA_ARGS__; break;              \
+    case 5: KERNEL<5> __VA_ARGS__; break; case 6: KERNEL<6> __VA_ARGS__; break;              \
+    case 7: KERNEL<7> __VA_ARGS__; break; default: KERNEL<8> __VA_ARGS__; break;             \
+  }
 
 int ukf_build(ude_handle* h, ude_ukf_plan*& out_plan) {
   const ude_desc& D = h->desc;
@@ -458,16 +547,63 @@ int ukf_build(ude_handle* h, ude_ukf_plan*& out_plan) {
   return UDE_OK;
 }
 
+// every launch of one evaluation, in order, on `s` (capturable: no host-dependent arguments)
+int ukf_enqueue(ude_handle* h, ude_ukf_plan* pl, bool want_grad, double* d_states, double* d_covs, cudaStream_t s) {
+  const ude_desc& D = h->desc;
+  const int d = D.d, n_sig = 2 * d + 1, K = pl->K;
+  ude_handle* ax = pl->aux;
+  const size_t NS = (size_t)h->n_series;
+  const UkfConst* C = pl->d_const.p;
+  const int TB = 64;
+  UDE_CUDA_TRY(h, cudaMemsetAsync(pl->d_ll.p, 0, NS * sizeof(double), s));
+  ukf_init<<<(int)((NS + TB - 1) / TB), TB, 0, s>>>((int)NS, d, h->d_starts.p, h->d_data.p, C, pl->d_x.p, pl->d_P.p, d_states, d_covs);
+  ukf_bcast_pm<<<K, 128, 0, s>>>(pl->d_pm.p, D.n_pm, pl->d_steps.p, K, d, n_sig, pl->d_theta_aux.p);
+  UDE_CUDA_TRY(h, cudaGetLastError());
+  for (int k = 0; k < K; ++k) {
+    const UkfStep& st = pl->steps[(size_t)k];
+    const int nb = (st.n_act + TB - 1) / TB;
+    UKF_DISPATCH(d, ukf_sigma_fwd, <<<nb, TB, 0, s>>>(st, C, pl->d_active.p, pl->d_x.p, pl->d_P.p, pl->d_xprev.p, pl->d_Pprev.p, pl->d_U.p, pl->d_theta_aux.p))
+    int rc = launch_segments(ax, pl->d_theta_aux.p, nullptr, pl->d_traj_aux.p, ax->model_task0[(size_t)k], ax->model_task0[(size_t)k + 1], 0, s);
+    if (rc != UDE_OK) return fail(h, rc, std::string("UKF predict: ") + ude_last_error(ax));
+    UKF_DISPATCH(d, ukf_update_fwd, <<<nb, TB, 0, s>>>(st, C, pl->d_active.p, h->d_starts.p, h->d_data.p, pl->d_traj_aux.p, pl->d_x.p,
+                                                      pl->d_P.p, pl->d_ll.p, d_states, d_covs))
+  }
+  UDE_CUDA_TRY(h, cudaGetLastError());
+  if (want_grad) {
+    UDE_CUDA_TRY(h, cudaMemsetAsync(pl->d_grad_aux.p, 0, (size_t)pl->n_aux_theta * sizeof(double), s));
+    UDE_CUDA_TRY(h, cudaMemsetAsync(pl->d_xb.p, 0, NS * d * sizeof(double), s));
+    UDE_CUDA_TRY(h, cudaMemsetAsync(pl->d_Pb.p, 0, NS * d * d * sizeof(double), s));
+    UDE_CUDA_TRY(h, cudaMemsetAsync(pl->d_pnub.p, 0, NS * d * d * sizeof(double), s));
+    UDE_CUDA_TRY(h, cudaMemsetAsync(ax->d_model_loss.p, 0, (size_t)K * sizeof(double), s));
+    for (int k = K - 1; k >= 0; --k) {
+      const UkfStep& st = pl->steps[(size_t)k];
+      const int nb = (st.n_act + TB - 1) / TB;
+      UKF_DISPATCH(d, ukf_update_bwd, <<<nb, TB, 0, s>>>(st, C, pl->d_active.p, h->d_starts.p, h->d_data.p, pl->d_traj_aux.p, pl->d_xb.p,
+                                                        pl->d_Pb.p, pl->d_pnub.p, pl->d_theta_aux.p))
+      int rc = launch_segments(ax, pl->d_theta_aux.p, pl->d_grad_aux.p, nullptr, ax->model_task0[(size_t)k], ax->model_task0[(size_t)k + 1], 0, s);
+      if (rc != UDE_OK) return fail(h, rc, std::string("UKF adjoint: ") + ude_last_error(ax));
+      UKF_DISPATCH(d, ukf_sigma_bwd, <<<nb, TB, 0, s>>>(st, C, pl->d_active.p, pl->d_U.p, pl->d_grad_aux.p, pl->d_xb.p, pl->d_Pb.p))
+    }
+    UDE_CUDA_TRY(h, cudaGetLastError());
+  }
+  const long long n_w1 = (long long)D.nn_hidden * D.nn_in, n_w2 = (long long)D.nn_out * D.nn_hidden;
+  ukf_finish<<<8, 128, 0, s>>>((int)NS, K, pl->d_steps.p, C, pl->d_ll.p, pl->d_pnub.p, pl->d_grad_aux.p, pl->d_pm.p, D.n_pm, D.off_w1, n_w1,
+                               D.off_w2, n_w2, pl->d_pm.p + D.n_pm, want_grad ? 1 : 0, pl->d_out.p);
+  UDE_CUDA_TRY(h, cudaGetLastError());
+  return UDE_OK;
+}
+
 // One evaluation.  theta: host, n_theta; Lf: host d*d column-major (P_nu = Lf Lf').  states/covs (host, may be NULL):
-// filtered means d x n_cols and covariances d x d x n_cols (ukf_smoothing).
+// filtered means d x n_cols and covariances d x d x n_cols (ukf_smoothing).  The launch sequence (6 kernels per filter
+// step) is captured once per variant and replayed as a CUDA graph: a single series of 60 points is launch-bound otherwise.
 int ukf_eval(ude_handle* h, const ude_ukf_opts* o, const double* theta, const double* Lf, double* loss, double* grad_theta,
              double* grad_lf, double* states, double* covs) {
   const ude_desc& D = h->desc;
   if (!h->ukf) { int rc = ukf_build(h, h->ukf); if (rc != UDE_OK) return rc; }
   ude_ukf_plan* pl = h->ukf;
-  const int d = D.d, n_sig = 2 * d + 1, K = pl->K;
+  const int d = D.d, n_sig = 2 * d + 1;
   UkfConst C; memset(&C, 0, sizeof C);
-  C.d = d; C.n_sig = n_sig;
+  C.d = d; C.n_sig = n_sig; C.reg = o->reg;
   const double lam = o->alpha * o->alpha * (d - o->kappa) - d;
   C.c = lam + d; C.Wm0 = lam / (lam + d); C.Wc0 = lam / (lam + d) + (1.0 - o->alpha * o->alpha + o->beta);
   C.Wi = 1.0 / (2.0 * (d + lam)); C.ll_const = 0.5 * d * log(2.0 * 3.14159);      // sic: the reference's constant
@@ -480,53 +616,37 @@ int ukf_eval(ude_handle* h, const ude_ukf_opts* o, const double* theta, const do
   const bool want_grad = grad_theta != nullptr || grad_lf != nullptr;
   const bool want_states = states != nullptr;
   cudaStream_t s = h->stream;
-  ude_handle* ax = pl->aux;
-  const size_t NS = (size_t)h->n_series;
   const long long n_u = (long long)d * h->n_cols;
-  UDE_CUDA_TRY(h, cudaMemcpyAsync(pl->d_pm.p, theta + n_u, (size_t)D.n_pm * sizeof(double), cudaMemcpyHostToDevice, s));
-  UDE_CUDA_TRY(h, cudaMemcpyAsync(pl->d_pm.p + D.n_pm, Lf, (size_t)d * d * sizeof(double), cudaMemcpyHostToDevice, s));
-  UDE_CUDA_TRY(h, cudaMemsetAsync(pl->d_ll.p, 0, NS * sizeof(double), s));
+  UDE_CUDA_TRY(h, pl->d_const.reserve(1));
   if (want_states) {
     UDE_CUDA_TRY(h, pl->d_states.reserve((size_t)d * h->n_cols));
     if (covs) UDE_CUDA_TRY(h, pl->d_covs.reserve((size_t)d * d * h->n_cols));
   }
   double* d_states = want_states ? pl->d_states.p : nullptr;
   double* d_covs = (want_states && covs) ? pl->d_covs.p : nullptr;
-  const int TB = 64;
-  ukf_init<<<(int)((NS + TB - 1) / TB), TB, 0, s>>>((int)NS, d, h->d_starts.p, h->d_data.p, C, pl->d_x.p, pl->d_P.p, d_states, d_covs);
-  ukf_bcast_pm<<<K, 128, 0, s>>>(pl->d_pm.p, D.n_pm, pl->d_steps.p, K, d, n_sig, pl->d_theta_aux.p);
-  UDE_CUDA_TRY(h, cudaGetLastError());
-  for (int k = 0; k < K; ++k) {
-    const UkfStep& st = pl->steps[(size_t)k];
-    const int nb = (st.n_act + TB - 1) / TB;
-    ukf_sigma_fwd<<<nb, TB, 0, s>>>(st, C, pl->d_active.p, pl->d_x.p, pl->d_P.p, pl->d_xprev.p, pl->d_Pprev.p, pl->d_U.p, pl->d_theta_aux.p);
-    int rc = launch_segments(ax, pl->d_theta_aux.p, nullptr, pl->d_traj_aux.p, ax->model_task0[(size_t)k], ax->model_task0[(size_t)k + 1], 0, s);
-    if (rc != UDE_OK) return fail(h, rc, std::string("UKF predict: ") + ude_last_error(ax));
-    ukf_update_fwd<<<nb, TB, 0, s>>>(st, C, pl->d_active.p, h->d_starts.p, h->d_data.p, pl->d_traj_aux.p, pl->d_x.p, pl->d_P.p, pl->d_ll.p,
-                                     d_states, d_covs);
-  }
-  UDE_CUDA_TRY(h, cudaGetLastError());
-  if (want_grad) {
-    UDE_CUDA_TRY(h, cudaMemsetAsync(pl->d_grad_aux.p, 0, (size_t)pl->n_aux_theta * sizeof(double), s));
-    UDE_CUDA_TRY(h, cudaMemsetAsync(pl->d_xb.p, 0, NS * d * sizeof(double), s));
-    UDE_CUDA_TRY(h, cudaMemsetAsync(pl->d_Pb.p, 0, NS * d * d * sizeof(double), s));
-    UDE_CUDA_TRY(h, cudaMemsetAsync(pl->d_pnub.p, 0, NS * d * d * sizeof(double), s));
-    UDE_CUDA_TRY(h, cudaMemsetAsync(ax->d_model_loss.p, 0, (size_t)K * sizeof(double), s));
-    for (int k = K - 1; k >= 0; --k) {
-      const UkfStep& st = pl->steps[(size_t)k];
-      const int nb = (st.n_act + TB - 1) / TB;
-      ukf_update_bwd<<<nb, TB, 0, s>>>(st, C, pl->d_active.p, h->d_starts.p, h->d_data.p, pl->d_traj_aux.p, pl->d_xb.p, pl->d_Pb.p,
-                                       pl->d_pnub.p, pl->d_theta_aux.p);
-      int rc = launch_segments(ax, pl->d_theta_aux.p, pl->d_grad_aux.p, nullptr, ax->model_task0[(size_t)k], ax->model_task0[(size_t)k + 1], 0, s);
-      if (rc != UDE_OK) return fail(h, rc, std::string("UKF adjoint: ") + ude_last_error(ax));
-      ukf_sigma_bwd<<<nb, TB, 0, s>>>(st, C, pl->d_active.p, pl->d_U.p, pl->d_grad_aux.p, pl->d_xb.p, pl->d_Pb.p);
+  // C lives on the stack: a synchronous copy (pageable source) before anything is enqueued
+  UDE_CUDA_TRY(h, cudaMemcpy(pl->d_const.p, &C, sizeof C, cudaMemcpyHostToDevice));
+  UDE_CUDA_TRY(h, cudaMemcpyAsync(pl->d_pm.p, theta + n_u, (size_t)D.n_pm * sizeof(double), cudaMemcpyHostToDevice, s));
+  UDE_CUDA_TRY(h, cudaMemcpyAsync(pl->d_pm.p + D.n_pm, Lf, (size_t)d * d * sizeof(double), cudaMemcpyHostToDevice, s));
+  const int variant = want_grad ? 1 : (want_states ? (covs ? 3 : 2) : 0);
+  const char* genv = getenv("UDE_UKF_GRAPH");
+  pl->used_graph = 0;
+  if (!(genv && atoi(genv) == 0)) {
+    if (!pl->exec[variant]) {
+      cudaGraph_t g = nullptr;
+      if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+        const int rc = ukf_enqueue(h, pl, want_grad, d_states, d_covs, s);
+        const cudaError_t e = cudaStreamEndCapture(s, &g);
+        if (rc == UDE_OK && e == cudaSuccess && g) {
+          if (cudaGraphInstantiate(&pl->exec[variant], g, 0) != cudaSuccess) pl->exec[variant] = nullptr;
+        }
+        if (g) cudaGraphDestroy(g);
+      }
+      cudaGetLastError();
     }
-    UDE_CUDA_TRY(h, cudaGetLastError());
+    if (pl->exec[variant]) { UDE_CUDA_TRY(h, cudaGraphLaunch(pl->exec[variant], s)); pl->used_graph = 1; }
   }
-  const long long n_w1 = (long long)D.nn_hidden * D.nn_in, n_w2 = (long long)D.nn_out * D.nn_hidden;
-  ukf_finish<<<8, 128, 0, s>>>((int)NS, K, pl->d_steps.p, C, pl->d_ll.p, pl->d_pnub.p, pl->d_grad_aux.p, pl->d_pm.p, D.n_pm, D.off_w1, n_w1,
-                               D.off_w2, n_w2, o->reg, pl->d_pm.p + D.n_pm, want_grad ? 1 : 0, pl->d_out.p);
-  UDE_CUDA_TRY(h, cudaGetLastError());
+  if (!pl->used_graph) { int rc = ukf_enqueue(h, pl, want_grad, d_states, d_covs, s); if (rc != UDE_OK) return rc; }
   std::vector<double> outv(1 + (size_t)D.n_pm + (size_t)d * d, 0.0);
   UDE_CUDA_TRY(h, cudaMemcpyAsync(outv.data(), pl->d_out.p, (want_grad ? outv.size() : 1) * sizeof(double), cudaMemcpyDeviceToHost, s));
   if (want_states) {

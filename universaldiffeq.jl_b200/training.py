@@ -161,7 +161,7 @@ def build_problem(model: UDE, loss_function, regularization_weight=0.0, loss_opt
     if loss_function == "default":
         return default_loss(model, t_skip)
     raise ValueError("Select a valid loss function. The CUDA hot path implements 'conditional likelihood', 'derivative matching', "
-                     "'shooting', 'multiple shooting' (and 'default' = model.loss_function); 'marginal likelihood', 'neural "
+                     "'shooting', 'multiple shooting', 'marginal likelihood' (and 'default' = model.loss_function); 'neural "
                      "gradient matching' and 'spline gradient matching' are outside its scope (SURVEY.md 8f).")
 
 
@@ -183,6 +183,46 @@ def adam_host(engine: Engine, theta, step_size, maxiter, verbose=False, callback
     return th, np.array(trace)
 
 
+def marginal_likelihood_(model: UDE, regularization_weight=0.0, loss_options=None, optim_options=None, verbose=False, device=0):
+    """train!(model; loss_function = "marginal likelihood") (src/Optimizers.jl:391-423, :500-560; MultiUDE :604-640): Adam over
+    (process_model, P_nu factor) on the unscented-Kalman-filter likelihood, then uhat <- filtered states.  Returns
+    (P_nu, Px) like the reference's `out`.  Options: process_error / observation_error (default 0.1), alpha, beta, kappa
+    (defaults 1e-3, 2, 0)."""
+    o = dict(loss_options or {})
+    d = model.d
+    Pnu0 = errors_to_matrix(o.get("process_error", 0.1), d)
+    Peta = errors_to_matrix(o.get("observation_error", 0.1), d)
+    alpha, beta, kappa = o.get("alpha", 1e-3), o.get("beta", 2.0), o.get("kappa", 0.0)
+    opts = dict(default_options("marginal likelihood")); opts.update(optim_options or {})
+    prob = default_loss(model)
+    # the regulariser enters once (UDE, LFC.jl:119) or once per series plus once (MultiUDE, LFC.jl:441 and :457)
+    reg = regularization_weight * model.weights["regularization"] * (_n_series(model) + 1 if model.multi else 1)
+    F = np.linalg.cholesky(Pnu0)                       # Matrix(cholesky(P_nu).L)
+    n_u, n_pm = d * model.data.shape[1], prob.n_pm
+    x = np.concatenate([model.parameters[n_u:n_u + n_pm], F.reshape(-1, order="F")])
+    m = np.zeros_like(x); v = np.zeros_like(x)
+    theta = np.array(model.parameters, dtype=np.float64, copy=True)
+    trace = []
+    with Engine(prob, device=device) as eng:
+        for it in range(1, int(opts["maxiter"]) + 1):
+            theta[n_u:n_u + n_pm] = x[:n_pm]
+            L, g, gF = eng.ukf_loss_grad(theta, x[n_pm:].reshape(d, d, order="F"), Peta, alpha, beta, kappa, reg)
+            trace.append(L)
+            if verbose:
+                print(round(L, 3), end=" ", flush=True)
+            gx = np.concatenate([g[n_u:n_u + n_pm], gF.reshape(-1, order="F")])
+            m = 0.9 * m + 0.1 * gx
+            v = 0.999 * v + 0.001 * gx * gx
+            x = x - opts["step_size"] * (m / (1 - 0.9 ** it)) / (np.sqrt(v / (1 - 0.999 ** it)) + 1e-8)
+        theta[n_u:n_u + n_pm] = x[:n_pm]
+        F = x[n_pm:].reshape(d, d, order="F")
+        xs, Ps = eng.ukf_filter(theta, F, Peta, alpha, beta, kappa)
+    theta[:n_u] = xs.reshape(-1, order="F")
+    model.parameters = theta
+    model.extra["loss_trace"] = np.array(trace)
+    return F @ F.T, Ps
+
+
 def train_(model: UDE, loss_function="derivative matching", optimizer="ADAM", regularization_weight=0.0, verbose=True,
            loss_options=None, optim_options=None, t_skip=None, device=0, on_device: Optional[bool] = None):
     """train!(model; ...) (src/Optimizers.jl:352-570, :578-742) on the CUDA hot path.  Mutates model.parameters.
@@ -190,6 +230,8 @@ def train_(model: UDE, loss_function="derivative matching", optimizer="ADAM", re
     the default does so whenever no per-iteration printing is requested."""
     if optimizer != "ADAM":
         raise ValueError("only optimizer='ADAM' is routed to the CUDA path (BFGS would consume the same loss/grad entry point)")
+    if loss_function == "marginal likelihood":
+        return marginal_likelihood_(model, regularization_weight, loss_options, optim_options, verbose, device)
     prob = build_problem(model, loss_function, regularization_weight, loss_options, t_skip)
     opts = dict(default_options(loss_function)); opts.update(optim_options or {})
     on_device = (not verbose) if on_device is None else on_device
