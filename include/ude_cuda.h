@@ -136,6 +136,13 @@ int ude_loss_grad_device(ude_handle* h, const double* d_theta, double* d_loss, d
  * LFC.jl:237-258, :310-341, :604-631, :711-756; src/ModelTesting.jl:181-195): out is d x n_cols. */
 int ude_forward(ude_handle* h, const double* theta, int64_t n_theta, double* out);
 
+/* forecast (src/ModelTesting.jl:541-571): the handle's series are one-interval mini-series [t_{j-1}, t_j] of ONE trajectory;
+ * interval j starts from the damped end of interval j-1 (extrapolation damping of init_forecast, src/ProcessModels.jl:2-25:
+ * outside [umin, umax] the increment is blended with a pull towards umean, width l, rate rho).  limits = [umax | umin |
+ * umean] (3 d); out is d x n_series.  The whole chain stays on the device. */
+int ude_forecast_chain(ude_handle* h, const double* theta, int64_t n_theta, const double* u0, const double* limits, double l,
+                       double rho, double* out);
+
 /* Multi-GPU (one handle per GPU, one rank per process or per host thread): after ude_comm_init every
  * ude_loss_grad* call sum-allreduces [grad of process_model (minus the per-series vector) | loss] across
  * ranks with one NCCL call on the handle's stream. id_bytes is an ncclUniqueId (128 B). */

@@ -120,3 +120,19 @@ def test_ukf_graph_replay_equals_plain_launches(ude, monkeypatch):
         assert res[0][i][0] == res[1][i][0]
         assert np.array_equal(res[0][i][1], res[1][i][1]) and np.array_equal(res[0][i][2], res[1][i][2])
     assert res[0][0][0] != res[0][1][0]
+
+
+def test_kalman_filter_multi(ude):
+    """kalman_filter!(MultiUDE, sigma2) (src/UnscentedKalmanFilter.jl:181-235): diagonal process noise p.^2, first loss equals
+    the oracle's with F = diag(p) and the regulariser counted once per series."""
+    import pandas as pd
+    Y, ts = ude.synthetic.lotka_volterra_data(np.random.default_rng(0), 3, 8, random_u0=True)
+    dfm = pd.concat([pd.DataFrame({"time": ts, "series": s, "x1": Y[s, 0], "x2": Y[s, 1]}) for s in range(3)], ignore_index=True)
+    mm = ude.MultiNODE(dfm, hidden_units=4, seed=1, reg_weight=1e-3)
+    theta0 = mm.parameters.copy()
+    prob = ude.default_loss(mm)
+    ref = ukf.loss(prob, theta0, np.diag([0.1, 0.1]), 0.1 * np.eye(2), alpha=1.0, reg_weight=float(prob.reg_weight[0]), reg_mult=3.0)
+    Pn, Px = ude.kalman_filter_(mm, 0.1, alpha=1.0, maxiter=6, step_size=0.02)
+    tr = mm.extra["loss_trace"]
+    assert abs(tr[0] - ref) < 1e-10 * abs(ref)
+    assert tr[-1] < tr[0] and Pn.shape == (2, 2) and Px.shape == (2, 2, 24) and np.all(np.isfinite(mm.uhat))

@@ -133,3 +133,18 @@ def test_simulated_data_sets(ude):
     assert np.all(np.isfinite(data.to_numpy())) and np.all(np.isfinite(X.to_numpy()))
     data, X = ude.simulate_coral_data()
     assert list(data.columns) == ["time", "A", "C"] and len(data) == 125 and data["time"].iloc[-1] == 249
+
+
+def test_save_and_load_model_parameters(ude, tmp_path):
+    """save_model_parameters / load_model_parameters! (src/LoadSaveModels.jl:1-11)."""
+    df = ude.LotkaVolterra(plot=False, datasize=12)
+    a = ude.NODE(df, hidden_units=5, seed=1)
+    b = ude.NODE(df, hidden_units=5, seed=2)
+    assert not np.array_equal(a.process_model, b.process_model)
+    f = tmp_path / "pm.json"
+    ude.save_model_parameters(a, f)
+    ude.load_model_parameters_(b, f)
+    assert np.array_equal(a.process_model, b.process_model)
+    c = ude.NODE(df, hidden_units=6, seed=2)
+    with pytest.raises(ValueError):
+        ude.load_model_parameters_(c, f)

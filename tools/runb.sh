@@ -1,2 +1,1 @@
-timeout 600 python tools/ukf_bench.py > gpurun_out/ukf_r01.json 2> gpurun_out/ukf.err; tail -3 gpurun_out/ukf.err
-python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+timeout 900 python -m pytest tests/test_gpu_host_api.py tests/test_gpu_ukf.py -m gpu -x -q 2>&1 | tail -8

@@ -29,7 +29,7 @@ EXPORTS = ["ude_abi_version", "ude_device_count", "ude_create", "ude_destroy", "
            "ude_n_models", "ude_steps_per_eval", "ude_kernel_name", "ude_launches_per_eval", "ude_loss_grad", "ude_loss_grad_device",
            "ude_forward", "ude_comm_unique_id", "ude_comm_init", "ude_adam", "ude_adam_used_graph", "ude_profile_begin", "ude_profile_read",
            "ude_measure_fp64_peak", "ude_measure_fp32_peak", "ude_peer_export", "ude_peer_attach",
-           "ude_ukf_loss_grad", "ude_ukf_filter"]
+           "ude_ukf_loss_grad", "ude_ukf_filter", "ude_forecast_chain"]
 
 
 class UkfOpts(C.Structure):
@@ -121,6 +121,8 @@ def load_library():
     lib.ude_profile_read.argtypes = [vp, dp, i32]
     lib.ude_measure_fp64_peak.restype = C.c_int
     lib.ude_measure_fp64_peak.argtypes = [i32, C.POINTER(C.c_double)]
+    lib.ude_forecast_chain.restype = C.c_int
+    lib.ude_forecast_chain.argtypes = [vp, dp, i64, dp, dp, C.c_double, C.c_double, dp]
     lib.ude_ukf_loss_grad.restype = C.c_int
     lib.ude_ukf_loss_grad.argtypes = [vp, C.POINTER(UkfOpts), dp, i64, dp, dp, dp, dp]
     lib.ude_ukf_filter.restype = C.c_int
@@ -308,6 +310,16 @@ class Engine:
 
     def adam_used_graph(self) -> bool:
         return bool(self.lib.ude_adam_used_graph(self.handle))
+
+    def forecast_chain(self, theta, u0, umax, umin, umean, l, rho):
+        """ude_forecast_chain: the handle's one-interval series chained on the device; returns d x n_series."""
+        th = np.ascontiguousarray(theta, dtype=np.float64)
+        x0 = np.ascontiguousarray(u0, dtype=np.float64)
+        lim = np.ascontiguousarray(np.concatenate([umax, umin, umean]), dtype=np.float64)
+        out = np.zeros((self.problem.d, self.problem.n_series), order="F")
+        self._check(self.lib.ude_forecast_chain(self.handle, th.ctypes.data, th.shape[0], x0.ctypes.data, lim.ctypes.data,
+                                                float(l), float(rho), out.ctypes.data))
+        return out
 
     def _ukf_opts(self, Peta, alpha, beta, kappa, reg):
         o = UkfOpts()

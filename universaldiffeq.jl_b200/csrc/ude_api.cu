@@ -317,6 +317,24 @@ __global__ void ude_finalize_exchange(const double* __restrict__ block_part, int
   if (x == 0 && y == 0) T.epoch[blockIdx.x] = epoch;
 }
 
+
+// ---- forecast chain (src/ModelTesting.jl:541-571 with the extrapolation damping of src/ProcessModels.jl:2-25) ----------
+// lim = [umax | umin | umean] (3 d doubles); x is the running state
+__global__ void ude_chain_set(const double* __restrict__ x, double* __restrict__ start_col, int d) {
+  if (threadIdx.x < d) start_col[threadIdx.x] = x[threadIdx.x];
+}
+__global__ void ude_chain_damp(double* __restrict__ x, const double* __restrict__ pred, const double* __restrict__ lim, int d,
+                               double l, double rho, double* __restrict__ out) {
+  const int i = threadIdx.x;
+  if (i >= d) return;
+  const double xi = x[i], umax = lim[i], umin = lim[d + i], umean = lim[2 * d + i], span = umax - umin;
+  double du = pred[i] - xi;
+  if (xi > umax) { const double z = (xi - umax) / span, w = exp(-0.5 / (l * l) * z * z); du = w * du - rho * (1.0 - w) * (xi - umean); }
+  if (xi < umin) { const double z = (xi - umin) / span, w = exp(-0.5 / (l * l) * z * z); du = w * du - (1.0 - w) * rho * (xi - umean); }
+  const double xn = xi + du;
+  x[i] = xn; out[i] = xn;
+}
+
 // Optimisers.jl Adam: m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2; theta -= eta * (m/(1-b1^t)) / (sqrt(v/(1-b2^t)) + eps)
 __global__ void ude_adam_update(double* __restrict__ theta, double* __restrict__ m, double* __restrict__ v,
                                 const double* __restrict__ g, long long n, double eta, double c1, double c2) {
@@ -948,6 +966,39 @@ int ude_forward(ude_handle* h, const double* theta, int64_t n_theta, double* out
   int rc = enqueue_eval(h, h->d_theta.p, h->d_loss.p, nullptr, h->d_traj.p, s);
   if (rc != UDE_OK) return rc;
   UDE_CUDA_TRY(h, cudaMemcpyAsync(out, h->d_traj.p, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+  UDE_CUDA_TRY(h, cudaStreamSynchronize(s));
+  return UDE_OK;
+}
+
+int ude_forecast_chain(ude_handle* h, const double* theta, int64_t n_theta, const double* u0, const double* limits, double l,
+                       double rho, double* out) {
+  if (!h) return UDE_ERR_INVALID;
+  if (!theta || !u0 || !limits || !out) return fail(h, UDE_ERR_INVALID, "null argument");
+  if (!h->have_data) return fail(h, UDE_ERR_STATE, "ude_set_data has not been called");
+  if (n_theta != h->n_theta) return fail(h, UDE_ERR_INVALID, "n_theta mismatch");
+  if (h->n_models != 1 || h->desc.loss_kind != UDE_LOSS_STATE_SPACE) return fail(h, UDE_ERR_INVALID, "forecast chain: one model, state-space layout");
+  for (int64_t s = 0; s < h->n_series; ++s)
+    if (h->lengths[s] != 2) return fail(h, UDE_ERR_INVALID, "forecast chain: every series must be one interval (two columns)");
+  UDE_CUDA_TRY(h, cudaSetDevice(h->device));
+  if (h->dirty) { int rc = build_plan(h); if (rc != UDE_OK) return rc; }
+  cudaStream_t s = h->stream;
+  const int d = h->desc.d, SPW = h->k_fwd->spw;
+  const size_t n = (size_t)d * h->n_cols;
+  DevBuf<double> d_x, d_lim, d_out;
+  UDE_CUDA_TRY(h, h->d_traj.reserve(n));
+  UDE_CUDA_TRY(h, d_x.upload(u0, (size_t)d, s));
+  UDE_CUDA_TRY(h, d_lim.upload(limits, (size_t)3 * d, s));
+  UDE_CUDA_TRY(h, d_out.reserve((size_t)d * h->n_series));
+  UDE_CUDA_TRY(h, cudaMemcpyAsync(h->d_theta.p, theta, (size_t)n_theta * sizeof(double), cudaMemcpyHostToDevice, s));
+  for (int64_t j = 0; j < h->n_series; ++j) {
+    ude_chain_set<<<1, 32, 0, s>>>(d_x.p, h->d_theta.p + (size_t)d * 2 * j, d);
+    // the task that holds interval j (its other intervals are recomputed when their turn comes)
+    int rc = launch_segments(h, h->d_theta.p, nullptr, h->d_traj.p, j / SPW, j / SPW + 1, 0, s);
+    if (rc != UDE_OK) return rc;
+    ude_chain_damp<<<1, 32, 0, s>>>(d_x.p, h->d_traj.p + (size_t)d * (2 * j + 1), d_lim.p, d, l, rho, d_out.p + (size_t)d * j);
+  }
+  UDE_CUDA_TRY(h, cudaGetLastError());
+  UDE_CUDA_TRY(h, cudaMemcpyAsync(out, d_out.p, (size_t)d * h->n_series * sizeof(double), cudaMemcpyDeviceToHost, s));
   UDE_CUDA_TRY(h, cudaStreamSynchronize(s));
   return UDE_OK;
 }

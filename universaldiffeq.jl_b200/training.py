@@ -223,6 +223,58 @@ def marginal_likelihood_(model: UDE, regularization_weight=0.0, loss_options=Non
     return F @ F.T, Ps
 
 
+def kalman_filter_(model: UDE, sigma2, Pnu=None, Peta=None, alpha=1e-3, beta=2.0, kappa=0.0, verbose=False, maxiter=500, step_size=0.05,
+                   device=0):
+    """kalman_filter!(UDE::MultiUDE, sigma2; ...) (src/UnscentedKalmanFilter.jl:181-235): Adam over (process_model, p) with
+    P_nu = diag(p.^2) (:117), the model's own regulariser once per series (:122), then uhat <- filtered states.  Quirk kept:
+    the final smoothing pass and the returned matrix use diag(p), not diag(p.^2) (:156, :231).  Returns (P_nu, Px)."""
+    d = model.d
+    pv = np.full(d, float(sigma2)) if Pnu is None else np.asarray(Pnu, dtype=np.float64).copy()
+    Pe = float(sigma2) * np.eye(d) if Peta is None else errors_to_matrix(Peta, d)
+    prob = default_loss(model)
+    reg = float(np.asarray(prob.reg_weight).reshape(-1)[0]) * _n_series(model)
+    n_u, n_pm = d * model.data.shape[1], prob.n_pm
+    x = np.concatenate([model.parameters[n_u:n_u + n_pm], pv])
+    m = np.zeros_like(x); v = np.zeros_like(x)
+    theta = np.array(model.parameters, dtype=np.float64, copy=True)
+    trace = []
+    with Engine(prob, device=device) as eng:
+        for it in range(1, int(maxiter) + 1):
+            theta[n_u:n_u + n_pm] = x[:n_pm]
+            L, g, gF = eng.ukf_loss_grad(theta, np.diag(x[n_pm:]), Pe, alpha, beta, kappa, reg)
+            trace.append(L)
+            if verbose:
+                print(round(L, 3), end=" ", flush=True)
+            gx = np.concatenate([g[n_u:n_u + n_pm], np.diag(gF)])
+            m = 0.9 * m + 0.1 * gx
+            v = 0.999 * v + 0.001 * gx * gx
+            x = x - step_size * (m / (1 - 0.9 ** it)) / (np.sqrt(v / (1 - 0.999 ** it)) + 1e-8)
+        theta[n_u:n_u + n_pm] = x[:n_pm]
+        Pn = np.diag(x[n_pm:])
+        xs, Ps = eng.ukf_filter(theta, np.diag(np.sqrt(np.abs(x[n_pm:]))), Pe, alpha, beta, kappa)      # P_nu = diag(p) in the smoother
+    theta[:n_u] = xs.reshape(-1, order="F")
+    model.parameters = theta
+    model.extra["loss_trace"] = np.array(trace)
+    return Pn, Ps
+
+
+def save_model_parameters(model: UDE, file):
+    """src/LoadSaveModels.jl:1-5: the process-model parameters as a JSON array (flat ComponentVector order)."""
+    import json
+    with open(file, "w") as f:
+        json.dump([float(x) for x in model.process_model], f)
+
+
+def load_model_parameters_(model: UDE, file):
+    """load_model_parameters! (src/LoadSaveModels.jl:7-11)."""
+    import json
+    with open(file) as f:
+        vals = np.asarray(json.load(f), dtype=np.float64)
+    if vals.shape != model.process_model.shape:
+        raise ValueError("parameter file does not match the model's process_model")
+    model.process_model[:] = vals
+
+
 def train_(model: UDE, loss_function="derivative matching", optimizer="ADAM", regularization_weight=0.0, verbose=True,
            loss_options=None, optim_options=None, t_skip=None, device=0, on_device: Optional[bool] = None):
     """train!(model; ...) (src/Optimizers.jl:352-570, :578-742) on the CUDA hot path.  Mutates model.parameters.
@@ -284,7 +336,7 @@ def predictions(model: UDE, test_data=None, device=0):
 
 def forecast(model: UDE, u0, t0, times, series=0, device=0):
     """forecast(UDE, u0, t0, times) (src/ModelTesting.jl:541-571) with the extrapolation damping of init_forecast
-    (src/ProcessModels.jl:2-25; l, extrap_rho from the constructor defaults).  Each interval is one segment on the GPU."""
+    (src/ProcessModels.jl:2-25; l, extrap_rho from the constructor defaults): ude_forecast_chain, device-resident."""
     times = np.asarray(times, dtype=np.float64)
     assert np.all(times > t0), "t0 is greater than the first time point in times"
     d, n = model.d, times.shape[0]
@@ -315,18 +367,7 @@ def forecast(model: UDE, u0, t0, times, series=0, device=0):
     pr.finalize()
     theta = np.concatenate([np.zeros(d * 2 * n), model.process_model])
     out = np.zeros((n, d + 1))
-    x = np.asarray(u0, dtype=np.float64).copy()
-    with Engine(pr, device=device) as eng:
-        for j in range(n):
-            theta[d * 2 * j: d * 2 * j + d] = x
-            pred = eng.forward(theta)[:, 2 * j + 1]
-            du = pred - x
-            hi, lo = x > umax, x < umin
-            span = umax - umin
-            w = np.exp(-0.5 / l ** 2 * ((x - umax) / span) ** 2)
-            du = np.where(hi, w * du - rho * (1 - w) * (x - umean), du)
-            w = np.exp(-0.5 / l ** 2 * ((x - umin) / span) ** 2)
-            du = np.where(lo, w * du - (1 - w) * rho * (x - umean), du)
-            x = x + du
-            out[j, 0], out[j, 1:] = times[j], x
+    with Engine(pr, device=device) as eng:     # the chain (predict, damp, next start) never leaves the device
+        out[:, 1:] = eng.forecast_chain(theta, np.asarray(u0, dtype=np.float64), umax, umin, umean, l, rho).T
+    out[:, 0] = times
     return out
