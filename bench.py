@@ -360,11 +360,14 @@ def main():
     others = None
     if rank == 0 and world == 1 and args.config == "c3" and not args.no_other_configs:
         others = {}
-        for cfg, n in (("c2", 10_000), ("c4", 1000), ("c5", 1_000_000)):
+        for key, cfg, n, solver2, dt2k in (("c2", "c2", 10_000, args.solver, 0), ("c4", "c4", 1000, args.solver, 0),
+                                           ("c5", "c5", 1_000_000, args.solver, 0), ("c3_tsit5", "c3", 100_000, "tsit5", 0),
+                                           ("c3_f32_mode", "c3", 100_000, args.solver, 1)):
             try:
-                a2 = argparse.Namespace(**vars(args)); a2.config = cfg; a2.series = n
+                a2 = argparse.Namespace(**vars(args)); a2.config = cfg; a2.series = n; a2.solver = solver2
                 p2, th2, nm2 = build_problem(ude, a2, 0)
-                with ude.Engine(p2, device=local) as e2:
+                cfg = key
+                with ude.Engine(p2, device=local, dtype=dt2k) as e2:
                     dt2 = torch.from_numpy(th2).to(dev); dg2 = torch.empty_like(dt2)
                     dl2 = torch.empty(p2.n_models, dtype=torch.float64, device=dev)
                     for _ in range(3):
@@ -378,10 +381,24 @@ def main():
                     ms2 = a.elapsed_time(b) / 10
                     st2 = e2.steps_per_eval()
                     others[cfg] = {"workload": nm2, "steps_per_s": st2 / (ms2 * 1e-3), "ms_per_step": ms2, "kernel": e2.kernel_name(),
-                                   "fp64_frac": st2 * p2.flops_per_step() / (ms2 * 1e-3) * 1e-12 / fp64_peak}
+                                   "fp64_frac": (st2 * p2.flops_per_step() / (ms2 * 1e-3) * 1e-12 / fp64_peak) if dt2k == 0 else None}
                 del dt2, dg2, dl2
             except Exception as ex:        # a side measurement must never take the headline down
                 others[cfg] = {"error": str(ex)[:200]}
+
+        try:       # UKF marginal likelihood on the C1 tutorial model (host buffers in and out, loss + gradient)
+            p3, th3 = ude.synthetic.config_c1()
+            with ude.Engine(p3, device=local) as e3:
+                F3, Pe3 = 0.3 * np.eye(p3.d), 0.1 * np.eye(p3.d)
+                for _ in range(3):
+                    e3.ukf_loss_grad(th3, F3, Pe3)
+                t0 = time.perf_counter()
+                for _ in range(20):
+                    e3.ukf_loss_grad(th3, F3, Pe3)
+                others["ukf_c1"] = {"workload": "C1 LV tutorial UDE, UKF marginal likelihood (ude_ukf_loss_grad), 59 filter steps x 5 sigma points",
+                                    "ms_per_eval": (time.perf_counter() - t0) / 20 * 1e3}
+        except Exception as ex:
+            others["ukf_c1"] = {"error": str(ex)[:200]}
 
     if rank == 0:
         kms = float(np.mean(kern_ms)) if len(kern_ms) else None

@@ -1,1 +1,4 @@
-timeout 900 python -m pytest tests/test_gpu_host_api.py tests/test_gpu_ukf.py -m gpu -x -q 2>&1 | tail -8
+SECONDS=0
+python bench.py 2> gpurun_out/b.err > gpurun_out/bench_default.json; echo "bench wall seconds: $SECONDS"; tail -3 gpurun_out/b.err
+python -c "
+import json; d=json.load(open('gpurun_out/bench_default.json')); print('%.3e' % d['value'], 'e2e %.3e' % d['e2e']['value'], d['roofline']['frac'], d['clocks']); print(json.dumps(d['other_configs'], indent=0)[:2500])"
