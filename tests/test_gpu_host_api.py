@@ -154,3 +154,13 @@ def test_leave_future_out_predict_matches_oracle_steps(ude):
                 assert len(row) == 1
                 assert abs(row["predicted"].iloc[0] - (p1[v] - Y[v, j])) < 1e-10
                 assert abs(row["observed"].iloc[0] - (Y[v, j + 1] - Y[v, j])) < 1e-14
+
+
+def test_train_bfgs_reaches_lower_loss_than_start(ude):
+    """train!(...; optimizer = "BFGS") (src/Optimizers.jl:506-521; docs/src/examples.md:180): same loss/gradient entry point."""
+    m = ude.NODE(_lv_frame(ude, n=14), hidden_units=5, seed=4)
+    ude.train_(m, "conditional likelihood", optimizer="BFGS", verbose=False, optim_options=dict(maxiter=15))
+    tr = m.extra["loss_trace"].ravel()
+    assert tr.min() < 0.5 * tr[0] and np.all(np.isfinite(m.parameters))
+    with pytest.raises(ValueError):
+        ude.train_(m, "conditional likelihood", optimizer="SGD")

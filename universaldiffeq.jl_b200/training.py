@@ -280,15 +280,30 @@ def train_(model: UDE, loss_function="derivative matching", optimizer="ADAM", re
     """train!(model; ...) (src/Optimizers.jl:352-570, :578-742) on the CUDA hot path.  Mutates model.parameters.
     on_device=True keeps theta, Adam moments and the gradient on the GPU for all iterations (SURVEY.md 8f row 1);
     the default does so whenever no per-iteration printing is requested."""
-    if optimizer != "ADAM":
-        raise ValueError("only optimizer='ADAM' is routed to the CUDA path (BFGS would consume the same loss/grad entry point)")
+    if optimizer not in ("ADAM", "BFGS"):
+        raise ValueError("Select a valid optimization algorithm. Choose from 'ADAM' or 'BFGS'.")      # src/Optimizers.jl:524
     if loss_function == "marginal likelihood":
+        if optimizer != "ADAM":
+            raise ValueError("marginal likelihood: only optimizer='ADAM' is implemented on the CUDA path")
         return marginal_likelihood_(model, regularization_weight, loss_options, optim_options, verbose, device)
     prob = build_problem(model, loss_function, regularization_weight, loss_options, t_skip)
     opts = dict(default_options(loss_function)); opts.update(optim_options or {})
     on_device = (not verbose) if on_device is None else on_device
     with Engine(prob, device=device) as eng:
-        if on_device:
+        if optimizer == "BFGS":
+            # src/Optimizers.jl:506-510: Optim.BFGS on the same loss; here SciPy's BFGS driven by ude_loss_grad
+            from scipy.optimize import minimize
+            trace = []
+
+            def fg(x):
+                L, g = eng.loss_grad(x)
+                trace.append(L.copy())
+                return float(L.sum()), g
+
+            res = minimize(fg, np.array(model.parameters, dtype=np.float64), jac=True, method="BFGS",
+                           options=dict(maxiter=int((optim_options or {}).get("maxiter", 200))))
+            theta, trace = res.x, np.array(trace)
+        elif on_device:
             theta, trace = eng.adam(model.parameters, opts["step_size"], opts["maxiter"])
         else:
             theta, trace = adam_host(eng, model.parameters, opts["step_size"], opts["maxiter"], verbose=verbose)
