@@ -419,7 +419,11 @@ def main():
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         hbm_bytes = prob.hbm_bytes_per_eval()
-        roofline = {"bound": "fp64" if args.dtype == "f64" else "fp32", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+        is_mma = "mma" in eng.kernel_name()
+        roofline = {"bound": ("tensor" if is_mma else "fp64") if args.dtype == "f64" else "fp32",
+                    "pipe": ("FP64 tensor-core DMMA m8n8k4 + DFMA: ONE shared FP64 datapath (profiles/microbench_r01b.json), so the FP64 "
+                             "FMA peak is the denominator, not the bf16 tensor peak") if is_mma else "FP64 FMA" if args.dtype == "f64" else "FP32 FMA",
+                    "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                     "frac": (achieved / fp64_peak) if achieved else None, "traffic": traffic,
                     "peak_source": ("measured live: ude_measure_fp64_peak (DFMA chain, 8-way ILP, 64 warps/SM); vendor 37.2" if args.dtype == "f64"
                                     else "measured live: ude_measure_fp32_peak (FFMA chain, 8-way ILP, 64 warps/SM)"),

@@ -1,4 +1,3 @@
-SECONDS=0
-python bench.py 2> gpurun_out/b.err > gpurun_out/bench_default.json; echo "bench wall seconds: $SECONDS"; tail -3 gpurun_out/b.err
-python -c "
-import json; d=json.load(open('gpurun_out/bench_default.json')); print('%.3e' % d['value'], 'e2e %.3e' % d['e2e']['value'], d['roofline']['frac'], d['clocks']); print(json.dumps(d['other_configs'], indent=0)[:2500])"
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python bench.py --steps 10 --warmup 3 --no-other-configs --no-cpu-baseline 2>/dev/null | python -c "
+import sys,json; d=json.loads(sys.stdin.read()); print(d['roofline']['bound'], d['roofline']['frac'], d['value'])"
