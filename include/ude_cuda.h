@@ -43,7 +43,9 @@ typedef enum ude_status {
 
 /* solver: fixed-step explicit RK replacing OrdinaryDiffEq.solve(..., Tsit5(), abstol=1e-6, reltol=1e-6)
  * (src/ProcessModels.jl:82-83); `substeps` steps per observation interval. */
-enum { UDE_RK4 = 0, UDE_TSIT5 = 1 };
+enum { UDE_RK4 = 0, UDE_TSIT5 = 1,
+       UDE_EULER = 2 /* one RHS evaluation per step: the spline-gradient-matching loss (LFC.jl:888-931) is a state-space
+                        loss on the knot grid with this solver; FP64 lane-per-hidden-unit kernels, state-space loss only */ };
 enum { UDE_F64 = 0, UDE_F32 = 1 };
 /* loss kinds */
 enum {

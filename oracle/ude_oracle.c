@@ -39,7 +39,11 @@ static const tableau TAB_TSIT5 = {
    {5.86145544294642, -12.92096931784711, 8.159367898576159, -0.071584973281401, -0.028269050394068383}},
   {0.09646076681806523, 0.01, 0.4798896504144996, 1.379008574103742, -3.290069515436081, 2.324710524099774}};
 
-static const tableau* get_tab(int solver) { return solver == ORC_TSIT5 ? &TAB_TSIT5 : &TAB_RK4; }
+/* explicit Euler: the spline-gradient-matching loss compares finite differences of the knot values with ONE right-hand-side
+ * evaluation at the left knot (/root/reference/src/LossFunctionConstructors.jl:918-921) = one Euler step per interval */
+static const tableau TAB_EULER = {1, {0.0}, {{0}}, {1.0}};
+
+static const tableau* get_tab(int solver) { return solver == ORC_TSIT5 ? &TAB_TSIT5 : (solver == ORC_EULER ? &TAB_EULER : &TAB_RK4); }
 
 /* ---- per-thread workspace ---------------------------------------------------------------- */
 typedef struct {

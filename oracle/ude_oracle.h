@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-enum { ORC_RK4 = 0, ORC_TSIT5 = 1 };
+enum { ORC_RK4 = 0, ORC_TSIT5 = 1, ORC_EULER = 2 };
 enum { ORC_LOSS_STATE_SPACE = 0, ORC_LOSS_MULTI_SHOOT = 1, ORC_LOSS_SHOOT = 2, ORC_LOSS_DERIV_MATCH = 3 };
 enum { ORC_RHS_NODE = 0, ORC_RHS_NODE_TIME = 1, ORC_RHS_LV_UDE = 2, ORC_RHS_LV_UDE_ABS = 3,
        ORC_RHS_FISHERY = 4, ORC_RHS_NN_DECAY = 5, ORC_RHS_SERIES_GROWTH = 6 };

@@ -16,6 +16,7 @@ RK4_TAB = dict(
     a=[[], [0.5], [0.0, 0.5], [0.0, 0.0, 1.0]],
     b=[1 / 6, 1 / 3, 1 / 3, 1 / 6],
 )
+EULER_TAB = dict(c=[0.0], a=[[]], b=[1.0])
 TSIT5_TAB = dict(
     c=[0.0, 0.161, 0.327, 0.9, 0.9800255409045097, 1.0],
     a=[[],
@@ -91,7 +92,7 @@ def rhs(p, pm, series_local, series_global, u, t):
 
 
 def rk_step(p, pm, sl, sg, u, t, h):
-    tab = TSIT5_TAB if p.solver == 1 else RK4_TAB
+    tab = TSIT5_TAB if p.solver == 1 else (EULER_TAB if p.solver == 2 else RK4_TAB)
     ks = []
     for i in range(len(tab["c"])):
         U = u

@@ -164,3 +164,39 @@ def test_train_bfgs_reaches_lower_loss_than_start(ude):
     assert tr.min() < 0.5 * tr[0] and np.all(np.isfinite(m.parameters))
     with pytest.raises(ValueError):
         ude.train_(m, "conditional likelihood", optimizer="SGD")
+
+
+def test_spline_gradient_matching_default_loss(ude):
+    """train!(model) with its default loss, spline gradient matching (src/Optimizers.jl:354, LFC.jl:888-931; reference test:
+    test/UDETests.jl:41 only checks it runs).  One evaluation against the formula written out with the NumPy RHS, the
+    gradient against the oracle-driven twin, then a short training run."""
+    from oracle import ude_oracle_np as onp
+    df = ude.LotkaVolterra(plot=False, datasize=15)
+    m = ude.NODE(df, hidden_units=4, seed=2)
+    sg = ude.SplineGradientMatching(m, T=12, regularization_weight=1e-3)
+    x = sg.initial_parameters()
+    x[: sg.n_alpha] = 0.5 + 0.3 * np.random.default_rng(0).normal(size=sg.n_alpha)
+
+    class OracleEngine:
+        def loss_grad(self, th):
+            return oracle.loss_grad(sg.problem, th)
+
+    with ude.Engine(sg.problem) as eng:
+        L, g = sg.loss_grad(eng, x)
+    Lo, go = sg.loss_grad(OracleEngine(), x)
+    d, N, T = 2, 15, 12
+    alpha = x[: sg.n_alpha].reshape(sg.n_knots, d, order="F"); pm = x[sg.n_alpha + d * N:]
+    t = m.times; dt = (t[-1] - t[0]) / T; Dt = dt / ((t[-1] - t[0]) / N)
+    uh = (alpha[sg.i1] * sg.w1[:, None] + alpha[sg.i2] * sg.w2[:, None]).T
+    ref = np.sum(((m.data - uh) / 0.05 ** 2) ** 2)
+    That = sg.n_knots - 1
+    for k in range(That - 1):
+        r = (alpha[k + 1] - alpha[k]) / (sg.ts[k + 1] - sg.ts[k]) - onp.rhs(sg.problem, pm, 0, 0, alpha[k], sg.ts[k])
+        ref += N / That * np.sum((r / (np.sqrt(Dt) * 0.025 ** 2)) ** 2)
+    pr = sg.problem
+    ref += 1e-3 * (np.sum(pm[pr.off_w1:pr.off_w1 + 8] ** 2) + np.sum(pm[pr.off_w2:pr.off_w2 + 8] ** 2))
+    assert abs(L - ref) < 1e-12 * abs(ref) and abs(L - Lo) < 1e-12 * abs(Lo)
+    assert np.max(np.abs(g - go)) < 1e-10 * np.max(np.abs(go))
+    ude.train_(m, "spline gradient matching", verbose=False, loss_options=dict(T=12), optim_options=dict(maxiter=30))
+    tr = m.extra["loss_trace"]
+    assert tr[-1] < tr[0] and m.extra["spline_alpha"].shape == (17, 2) and np.all(np.isfinite(m.uhat))

@@ -271,3 +271,13 @@ def test_full_size_configs_sampled_and_additive(ude, name):
     for sh, _, gr in parts:
         glo, ghi, llo = sh.uhat_slices[0]
         assert cases.relerr(gr[llo:llo + (ghi - glo)], g[glo:ghi]) < 1e-12
+
+
+@pytest.mark.parametrize("loss", ["cond_lik", "mse"])
+@pytest.mark.parametrize("rhs", list(cases.RHS_SPECS))
+def test_parity_euler_state_space(ude, rhs, loss):
+    """UDE_EULER (one RHS evaluation per interval): the solver behind the spline-gradient-matching loss (LFC.jl:888-931)."""
+    prob, theta = cases.make_case(rhs, loss, 2, substeps=1, skip=(loss == "cond_lik"))
+    _check(prob, theta, ude)
+    prob, theta = cases.make_case(rhs, loss, 2, substeps=3, hidden=32 if rhs == "node_d4x1" else 10)
+    _check(prob, theta, ude)

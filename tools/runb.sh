@@ -1,3 +1,1 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python bench.py --steps 10 --warmup 3 --no-other-configs --no-cpu-baseline 2>/dev/null | python -c "
-import sys,json; d=json.loads(sys.stdin.read()); print(d['roofline']['bound'], d['roofline']['frac'], d['value'])"
+python -m pytest tests -m gpu -x -q 2>&1 | tail -6

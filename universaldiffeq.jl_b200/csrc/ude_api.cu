@@ -513,7 +513,7 @@ int build_plan(ude_handle* h) {
   UDE_CUDA_TRY(h, h->d_segs.upload(segs.data(), segs.size(), h->stream));
 
   // launch geometry: persistent grid, a multiple of the SM count
-  const int stages = D.solver == UDE_TSIT5 ? 6 : 4;
+  const int stages = D.solver == UDE_TSIT5 ? 6 : (D.solver == UDE_EULER ? 1 : 4);
   // dynamic smem: block partial row (single model) padded to 16 B + per-warp two-step TMA staging ring of the stash
   const size_t red_doubles = (size_t)(((h->n_models == 1 ? D.n_pm + 1 : 0) + 1) / 2 * 2);
   auto smem_for = [&](const KernelEntry* k) {
@@ -709,7 +709,7 @@ int ude_create(const ude_desc* desc, ude_handle** out) {
       desc->substeps < 1 || desc->n_scalars < 0 || desc->n_scalars > UDE_MAX_SCALARS || desc->n_cov < 0)
     return fail(nullptr, UDE_ERR_INVALID, "bad model dimensions");
   if (desc->dtype != UDE_F64 && desc->dtype != UDE_F32) return fail(nullptr, UDE_ERR_INVALID, "bad dtype");
-  if (desc->solver != UDE_RK4 && desc->solver != UDE_TSIT5) return fail(nullptr, UDE_ERR_INVALID, "bad solver");
+  if (desc->solver != UDE_RK4 && desc->solver != UDE_TSIT5 && desc->solver != UDE_EULER) return fail(nullptr, UDE_ERR_INVALID, "bad solver");
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
   if (e != cudaSuccess || n == 0) {

@@ -85,6 +85,13 @@ template <> struct Tab<1> {   // Tsit5 stages 1..6 (OrdinaryDiffEq Tsit5Constant
   }
 };
 
+template <> struct Tab<2> {   // explicit Euler (spline gradient matching: one RHS evaluation at the left knot)
+  static constexpr int S = 1;
+  __host__ __device__ static constexpr double c(int) { return 0.0; }
+  __host__ __device__ static constexpr double b(int) { return 1.0; }
+  __host__ __device__ static constexpr double a(int, int) { return 0.0; }
+};
+
 // ------------------------------------------------------------------------------------------------
 // All-reduce of N doubles over the G lanes of a sub-warp group (G a power of two, groups aligned).
 // Reduce-scatter (halving the payload each butterfly step) followed by an all-gather: for N = 4, G = 16

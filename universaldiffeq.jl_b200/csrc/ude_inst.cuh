@@ -43,6 +43,7 @@ void register_combo_t(const char* name, int priority) {
   register_one<NS, R, G, HPL, MINB, 1, LK_STATE, WS>(name, priority);
   register_one<NS, R, G, HPL, MINB, 1, LK_TRAJ, WS>(name, priority);
   register_one<NS, R, G, HPL, MINB, 1, LK_DM, WS>(name, priority);
+  if constexpr (NS::DTYPE == UDE_F64 && !WS) register_one<NS, R, G, HPL, MINB, 2, LK_STATE, WS>(name, priority);   // Euler
 }
 // FP64 (R is an f64:: trait, found through `using namespace f64`)
 template <class R, int G, int HPL, int MINB, bool WS = false>

@@ -17,8 +17,8 @@ from typing import List, Optional, Sequence
 import numpy as np
 
 # solver
-RK4, TSIT5 = 0, 1
-SOLVER_STAGES = {RK4: 4, TSIT5: 6}
+RK4, TSIT5, EULER = 0, 1, 2      # EULER: one RHS evaluation per interval (spline gradient matching)
+SOLVER_STAGES = {RK4: 4, TSIT5: 6, EULER: 1}
 # loss kinds
 LOSS_STATE_SPACE, LOSS_MULTI_SHOOT, LOSS_SHOOT, LOSS_DERIV_MATCH = 0, 1, 2, 3
 # right-hand-side catalog
@@ -221,7 +221,7 @@ class Problem:
         tanh counted as one flop, F_mv = 2H(din+dout), comb = 28d (RK4) / 84d (Tsit5)."""
         s = SOLVER_STAGES[self.solver]
         fmv = 2 * self.nn_hidden * (self.nn_in + self.nn_out)
-        comb = (28 if self.solver == RK4 else 84) * self.d
+        comb = {RK4: 28, TSIT5: 84, EULER: 4}[self.solver] * self.d
         return s * (3 * fmv + 5 * self.nn_hidden + 2 * self.nn_out) + comb
 
     def hbm_bytes_per_eval(self) -> float:

@@ -161,8 +161,8 @@ def build_problem(model: UDE, loss_function, regularization_weight=0.0, loss_opt
     if loss_function == "default":
         return default_loss(model, t_skip)
     raise ValueError("Select a valid loss function. The CUDA hot path implements 'conditional likelihood', 'derivative matching', "
-                     "'shooting', 'multiple shooting', 'marginal likelihood' (and 'default' = model.loss_function); 'neural "
-                     "gradient matching' and 'spline gradient matching' are outside its scope (SURVEY.md 8f).")
+                     "'shooting', 'multiple shooting', 'marginal likelihood', 'spline gradient matching' (and 'default' = "
+                     "model.loss_function); 'neural gradient matching' is outside its scope (SURVEY.md 8f).")
 
 
 def adam_host(engine: Engine, theta, step_size, maxiter, verbose=False, callback=None):
@@ -181,6 +181,99 @@ def adam_host(engine: Engine, theta, step_size, maxiter, verbose=False, callback
         v = 0.999 * v + 0.001 * g * g
         th -= step_size * (m / (1 - 0.9 ** it)) / (np.sqrt(v / (1 - 0.999 ** it)) + 1e-8)
     return th, np.array(trace)
+
+
+class SplineGradientMatching:
+    """spline_gradient_matching_loss(UDE, sigma, tau, regularization_weight, T) (src/LossFunctionConstructors.jl:888-931), the
+    DEFAULT loss of train!(::UDE) (src/Optimizers.jl:354).  Parameters: knot values alpha (n_knots x d) and the UDE's theta.
+        loss = sum(((u - uhat(alpha)) / sigma)^2) + w_reg * (|W1|^2 + |W2|^2)
+             + N / That * sum_k |(alpha[k+1] - alpha[k]) / dt - rhs(alpha[k], pm, ts[k])|^2 / (Dt * tau^2),   k = 1 .. That - 1
+    The last sum is a batched RHS + VJP: with explicit Euler as the "solver" it is exactly the state-space process term
+    |alpha[k+1] - (alpha[k] + dt * rhs)|^2 / dt^2 on the knot grid, so it runs on the same fused kernels (UDE_EULER).  The
+    observation term is a sparse linear map of alpha and stays on the host.  Quirks kept: knots run from t1 - 2dt to
+    tN + 2dt; the interpolation weight (t - ts1)/(ts2 - ts1) multiplies the LEFT knot (:876-880); a data time that coincides
+    with a knot is interpolated between its two neighbours (strict < and > in :865-866)."""
+
+    def __init__(self, model: UDE, sigma=0.05 ** 2, tau=0.025 ** 2, regularization_weight=0.0, T=100):
+        if model.multi:
+            raise NotImplementedError("spline gradient matching is defined for single-series models in the reference")
+        self.model, self.sigma = model, float(sigma)
+        t = np.asarray(model.times, dtype=np.float64)
+        N, d = t.shape[0], model.d
+        T = int(T)
+        dt = (t[-1] - t[0]) / T
+        self.ts = (t[0] - 2 * dt) + dt * np.arange(T + 5)
+        self.i1 = np.array([np.nonzero(self.ts < u)[0][-1] for u in t])
+        self.i2 = np.array([np.nonzero(self.ts > u)[0][0] for u in t])
+        self.w1 = (t - self.ts[self.i1]) / (self.ts[self.i2] - self.ts[self.i1])
+        self.w2 = 1.0 - self.w1
+        self.n_knots, self.That = T + 5, T + 4
+        Dt = dt / ((t[-1] - t[0]) / N)
+        m2 = copy.copy(model)
+        m2.times = self.ts[: self.That].copy()
+        m2.data = np.zeros((d, self.That), order="F")
+        pr = m2.base_problem()
+        pr.loss_kind, pr.solver, pr.substeps = P.LOSS_STATE_SPACE, P.EULER, 1
+        pr.A, pr.B = np.zeros((d, d)), np.eye(d)
+        pr.obs_scale, pr.proc_inv_dt = 0.0, False
+        pr.proc_scale = (N / self.That) / (Dt * float(tau) ** 2) / dt ** 2
+        pr.reg_weight = float(regularization_weight)
+        self.problem = pr.finalize()
+        self.n_alpha = self.n_knots * d
+
+    def initial_parameters(self):
+        """ComponentArray((alpha = zeros, UDE = UDE.parameters)) (:903-904): alpha is n_knots x d, column-major like Julia."""
+        return np.concatenate([np.zeros(self.n_alpha), self.model.parameters])
+
+    def states(self, alpha):
+        """interp_states_spline (:876-882): d x N."""
+        A = np.asarray(alpha).reshape(self.n_knots, self.model.d, order="F")
+        return (A[self.i1] * self.w1[:, None] + A[self.i2] * self.w2[:, None]).T
+
+    def loss_grad(self, eng: Engine, x):
+        d, n_u = self.model.d, self.model.d * self.model.data.shape[1]
+        alpha = x[: self.n_alpha].reshape(self.n_knots, d, order="F")
+        theta = x[self.n_alpha:]
+        # observation term on the host: O(N d)
+        res = (np.asarray(self.model.data) - self.states(x[: self.n_alpha])) / self.sigma          # d x N
+        L_obs = float(np.sum(res * res))
+        g_alpha = np.zeros_like(alpha)
+        gu = (-2.0 / self.sigma) * res.T                                                            # N x d: d L_obs / d uhat
+        np.add.at(g_alpha, self.i1, gu * self.w1[:, None])
+        np.add.at(g_alpha, self.i2, gu * self.w2[:, None])
+        # dynamics term + regulariser on the GPU: theta_gpu = [alpha[1:That]' (d x That) | process_model]
+        th = np.concatenate([alpha[: self.That].T.reshape(-1, order="F"), theta[n_u:]])
+        L, g = eng.loss_grad(th)
+        g_alpha[: self.That] += g[: d * self.That].reshape(d, self.That, order="F").T
+        g_theta = np.zeros_like(theta)
+        g_theta[n_u:] = g[d * self.That:]
+        return L_obs + float(L[0]), np.concatenate([g_alpha.reshape(-1, order="F"), g_theta])
+
+
+def spline_gradient_matching_(model: UDE, regularization_weight=0.0, loss_options=None, optim_options=None, verbose=False, device=0):
+    """train!(model)'s default for single-series models (src/Optimizers.jl:354, :461-466, :565-566): Adam over (alpha, theta),
+    then uhat <- interpolated states."""
+    o = dict(loss_options or {})
+    opts = dict(default_options("spline gradient matching")); opts.update(optim_options or {})
+    sg = SplineGradientMatching(model, o.get("sigma", 0.05 ** 2), o.get("tau", 0.025 ** 2), regularization_weight, o.get("T", 100))
+    x = sg.initial_parameters()
+    m = np.zeros_like(x); v = np.zeros_like(x)
+    trace = []
+    with Engine(sg.problem, device=device) as eng:
+        for it in range(1, int(opts["maxiter"]) + 1):
+            L, g = sg.loss_grad(eng, x)
+            trace.append(L)
+            if verbose:
+                print(round(L, 3), end=" ", flush=True)
+            m = 0.9 * m + 0.1 * g
+            v = 0.999 * v + 0.001 * g * g
+            x = x - opts["step_size"] * (m / (1 - 0.9 ** it)) / (np.sqrt(v / (1 - 0.999 ** it)) + 1e-8)
+    theta = x[sg.n_alpha:].copy()
+    theta[: model.d * model.data.shape[1]] = sg.states(x[: sg.n_alpha]).reshape(-1, order="F")
+    model.parameters = theta
+    model.extra["loss_trace"] = np.array(trace)
+    model.extra["spline_alpha"] = x[: sg.n_alpha].reshape(sg.n_knots, model.d, order="F").copy()
+    return None
 
 
 def marginal_likelihood_(model: UDE, regularization_weight=0.0, loss_options=None, optim_options=None, verbose=False, device=0):
@@ -282,6 +375,10 @@ def train_(model: UDE, loss_function="derivative matching", optimizer="ADAM", re
     the default does so whenever no per-iteration printing is requested."""
     if optimizer not in ("ADAM", "BFGS"):
         raise ValueError("Select a valid optimization algorithm. Choose from 'ADAM' or 'BFGS'.")      # src/Optimizers.jl:524
+    if loss_function == "spline gradient matching":
+        if optimizer != "ADAM":
+            raise ValueError("spline gradient matching: only optimizer='ADAM' is implemented on the CUDA path")
+        return spline_gradient_matching_(model, regularization_weight, loss_options, optim_options, verbose, device)
     if loss_function == "marginal likelihood":
         if optimizer != "ADAM":
             raise ValueError("marginal likelihood: only optimizer='ADAM' is implemented on the CUDA path")
