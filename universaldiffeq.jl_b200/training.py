@@ -368,11 +368,13 @@ def load_model_parameters_(model: UDE, file):
     model.process_model[:] = vals
 
 
-def train_(model: UDE, loss_function="derivative matching", optimizer="ADAM", regularization_weight=0.0, verbose=True,
+def train_(model: UDE, loss_function=None, optimizer="ADAM", regularization_weight=0.0, verbose=True,
            loss_options=None, optim_options=None, t_skip=None, device=0, on_device: Optional[bool] = None):
     """train!(model; ...) (src/Optimizers.jl:352-570, :578-742) on the CUDA hot path.  Mutates model.parameters.
     on_device=True keeps theta, Adam moments and the gradient on the GPU for all iterations (SURVEY.md 8f row 1);
     the default does so whenever no per-iteration printing is requested."""
+    if loss_function is None:      # the reference's defaults: src/Optimizers.jl:354 (UDE), :579 (MultiUDE)
+        loss_function = "derivative matching" if model.multi else "spline gradient matching"
     if optimizer not in ("ADAM", "BFGS"):
         raise ValueError("Select a valid optimization algorithm. Choose from 'ADAM' or 'BFGS'.")      # src/Optimizers.jl:524
     if loss_function == "spline gradient matching":
