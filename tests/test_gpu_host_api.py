@@ -200,3 +200,38 @@ def test_spline_gradient_matching_default_loss(ude):
     ude.train_(m, "spline gradient matching", verbose=False, loss_options=dict(T=12), optim_options=dict(maxiter=30))
     tr = m.extra["loss_trace"]
     assert tr[-1] < tr[0] and m.extra["spline_alpha"].shape == (17, 2) and np.all(np.isfinite(m.uhat))
+
+
+def test_neural_gradient_matching(ude):
+    """train!(model; loss_function = "neural gradient matching") (LFC.jl:764-846; reference test: test/UDETests.jl:43 runs it).
+    One evaluation against the formula written out with the NumPy RHS and against the oracle-driven twin, then training."""
+    from oracle import ude_oracle_np as onp
+    df = ude.LotkaVolterra(plot=False, datasize=10)
+    X = pd.DataFrame({"time": np.linspace(-0.5, 4.5, 11), "X": np.sin(np.linspace(0, 3, 11))})
+    m = ude.NODE(df, X, hidden_units=4, seed=2)
+    ng = ude.NeuralGradientMatching(m, regularization_weight=1e-3, prefit=False)
+    x = ng.initial_parameters()
+    x = x + 0.01 * np.random.default_rng(0).normal(size=x.shape)
+
+    class OracleEngine:
+        def loss_grad(self, th):
+            return oracle.loss_grad(ng.problem, th)
+
+    with ude.Engine(ng.problem) as eng:
+        L, g = ng.loss_grad(eng, x)
+    Lo, go = ng.loss_grad(OracleEngine(), x)
+    d, N = 2, 10
+    n_theta = m.parameters.shape[0]
+    pm = x[d * N:n_theta]
+    U, dU, _ = ng.interp(ng.unpack(x[n_theta:]))
+    ref = np.sum((m.data - U) ** 2) / 0.1 ** 2
+    for j in range(N):
+        r = dU[:, j] - onp.rhs(ng.problem, pm, j, j, U[:, j], m.times[j])
+        ref += np.sum(r * r) / 0.5 ** 2
+    pr = ng.problem
+    ref += 1e-3 * (np.sum(pm[pr.off_w1:pr.off_w1 + pr.nn_hidden * pr.nn_in] ** 2) + np.sum(pm[pr.off_w2:pr.off_w2 + pr.nn_out * pr.nn_hidden] ** 2))
+    assert abs(L - ref) < 1e-12 * abs(ref) and abs(L - Lo) < 1e-12 * abs(Lo)
+    assert np.max(np.abs(g - go)) < 1e-10 * np.max(np.abs(go))
+    ude.train_(m, "neural gradient matching", verbose=False, optim_options=dict(maxiter=20))
+    tr = m.extra["loss_trace"]
+    assert tr[-1] < tr[0] and np.all(np.isfinite(m.uhat)) and np.max(np.abs(m.uhat - m.data)) < 0.5

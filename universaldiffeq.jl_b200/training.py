@@ -161,8 +161,8 @@ def build_problem(model: UDE, loss_function, regularization_weight=0.0, loss_opt
     if loss_function == "default":
         return default_loss(model, t_skip)
     raise ValueError("Select a valid loss function. The CUDA hot path implements 'conditional likelihood', 'derivative matching', "
-                     "'shooting', 'multiple shooting', 'marginal likelihood', 'spline gradient matching' (and 'default' = "
-                     "model.loss_function); 'neural gradient matching' is outside its scope (SURVEY.md 8f).")
+                     "'shooting', 'multiple shooting', 'marginal likelihood', 'neural gradient matching', 'spline gradient matching' "
+                     "(and 'default' = model.loss_function).")
 
 
 def adam_host(engine: Engine, theta, step_size, maxiter, verbose=False, callback=None):
@@ -181,6 +181,141 @@ def adam_host(engine: Engine, theta, step_size, maxiter, verbose=False, callback
         v = 0.999 * v + 0.001 * g * g
         th -= step_size * (m / (1 - 0.9 ** it)) / (np.sqrt(v / (1 - 0.999 ** it)) + 1e-8)
     return th, np.array(trace)
+
+
+def _interval_problem(model: UDE, t_from, t_to, series=0) -> P.Problem:
+    """A state-space Problem (not finalized) whose series are independent one-interval mini-series [t_from[j], t_to[j]] of
+    `model` (two columns each; the covariate knots of `series` repeated for every mini-series)."""
+    d, n = model.d, len(t_from)
+    m2 = copy.copy(model)
+    m2.times = np.stack([np.asarray(t_from, dtype=np.float64), np.asarray(t_to, dtype=np.float64)], axis=1).reshape(-1)
+    m2.data = np.zeros((d, 2 * n), order="F")
+    m2.multi = True
+    m2.starts = np.arange(n, dtype=np.int64) * 2
+    m2.lengths = np.full(n, 2, dtype=np.int64)
+    if model.cov:
+        nc, off, kt, kx = model.cov
+        blk = slice(series * nc, series * nc + nc + 1) if model.multi else slice(0, nc + 1)
+        o = off[blk]
+        seg_t, seg_x = kt[o[0]:o[-1]], kx[o[0]:o[-1]]
+        m2.cov = (nc, np.concatenate([[0], np.tile(np.diff(o), n).cumsum()]).astype(np.int64), np.tile(seg_t, n), np.tile(seg_x, n))
+    pr = m2.base_problem()
+    pr.loss_kind = P.LOSS_STATE_SPACE
+    if pr.has_series_param:
+        raise NotImplementedError("per-series parameters are not supported on mini-series problems")
+    return pr
+
+
+class NeuralGradientMatching:
+    """neural_gradient_matching_loss(UDE, sigma, tau, regularization_weight, init_weights_layer_1)
+    (src/LossFunctionConstructors.jl:764-846): an interpolating network uhat(t) = W2 tanh(W1 t + b1) + b2 (one hidden unit
+    per observation, pre-fitted to the data with two Adam runs, :788-793) and
+        loss = sum((u - uhat)^2) / sigma^2 + sum_t |duhat/dt(t) - rhs(uhat(t), pm, t)|^2 / tau^2 + w_reg (|W1|^2 + |W2|^2).
+    The RHS term with its gradients w.r.t. uhat, duhat/dt and the process model is one batched evaluation on the GPU: every
+    observation time is a two-column mini-series [uhat, uhat + h duhat/dt] under explicit Euler (h = 1), whose state-space
+    residual is h (duhat/dt - rhs).  The interpolating network (N hidden units of one input) is host-side NumPy."""
+    H_STEP = 1.0
+
+    def __init__(self, model: UDE, sigma=0.1, tau=0.5, regularization_weight=0.0, init_weights_layer_1=5.0, seed=0, prefit=True):
+        if model.multi:
+            raise NotImplementedError("neural gradient matching is defined for single-series models in the reference")
+        self.model, self.sigma, self.tau = model, float(sigma), float(tau)
+        t = np.asarray(model.times, dtype=np.float64)
+        self.t, self.N, d = t, t.shape[0], model.d
+        rng = np.random.default_rng(seed)
+        lim = np.sqrt(6.0 / (self.N + d))
+        self.ip = dict(W1=np.full(self.N, float(init_weights_layer_1)), b1=-t * float(init_weights_layer_1),
+                       W2=rng.uniform(-lim, lim, size=(d, self.N)).astype(np.float32).astype(np.float64), b2=np.zeros(d))
+        if prefit:      # Adam(0.05) x 250, then Adam(0.025) x 500 on sum((u - uhat)^2)
+            x = self.pack(self.ip)
+            for step, iters in ((0.05, 250), (0.025, 500)):
+                m = np.zeros_like(x); v = np.zeros_like(x)
+                for it in range(1, iters + 1):
+                    ip = self.unpack(x)
+                    U, dU, H = self.interp(ip)
+                    g = self.pack(self.interp_vjp(ip, H, -2.0 * (np.asarray(model.data) - U), np.zeros_like(U)))
+                    m = 0.9 * m + 0.1 * g; v = 0.999 * v + 0.001 * g * g
+                    x = x - step * (m / (1 - 0.9 ** it)) / (np.sqrt(v / (1 - 0.999 ** it)) + 1e-8)
+            self.ip = self.unpack(x)
+        pr = _interval_problem(model, t, t + self.H_STEP)
+        pr.solver, pr.substeps = P.EULER, 1
+        pr.A, pr.B = np.zeros((d, d)), np.eye(d)
+        pr.obs_scale, pr.proc_inv_dt = 0.0, False
+        pr.proc_scale = 1.0 / (self.tau ** 2 * self.H_STEP ** 2)
+        pr.reg_weight = float(regularization_weight)
+        self.problem = pr.finalize()
+        self.n_interp = self.pack(self.ip).shape[0]
+
+    def pack(self, ip):
+        return np.concatenate([ip["W1"], ip["b1"], ip["W2"].reshape(-1, order="F"), ip["b2"]])
+
+    def unpack(self, x):
+        N, d = self.N, self.model.d
+        return dict(W1=x[:N], b1=x[N:2 * N], W2=x[2 * N:2 * N + d * N].reshape(d, N, order="F"), b2=x[2 * N + d * N:2 * N + d * N + d])
+
+    def interp(self, ip):
+        """uhat (d x N), duhat/dt (d x N) (dNNdt, :797-806) and the hidden activations."""
+        H = np.tanh(ip["W1"][:, None] * self.t[None, :] + ip["b1"][:, None])
+        return ip["W2"] @ H + ip["b2"][:, None], ip["W2"] @ (ip["W1"][:, None] * (1.0 - H * H)), H
+
+    def interp_vjp(self, ip, H, GU, GD):
+        S = 1.0 - H * H
+        D = ip["W1"][:, None] * S
+        W2b = GU @ H.T + GD @ D.T
+        Hb = ip["W2"].T @ GU
+        Db = ip["W2"].T @ GD
+        W1b = np.sum(Db * S, axis=1)
+        Hb = Hb + Db * ip["W1"][:, None] * (-2.0 * H)
+        Zb = Hb * S
+        return dict(W1=W1b + Zb @ self.t, b1=np.sum(Zb, axis=1), W2=W2b, b2=np.sum(GU, axis=1))
+
+    def initial_parameters(self):
+        """ComponentArray((UDE = UDE.parameters, interp = interp_params)) (:812)."""
+        return np.concatenate([self.model.parameters, self.pack(self.ip)])
+
+    def loss_grad(self, eng: Engine, x):
+        d, N, h = self.model.d, self.N, self.H_STEP
+        n_theta = self.model.parameters.shape[0]
+        n_u = d * N
+        theta, ip = x[:n_theta], self.unpack(x[n_theta:])
+        U, dU, H = self.interp(ip)
+        res = np.asarray(self.model.data) - U
+        L_obs = float(np.sum(res * res)) / self.sigma ** 2
+        cols = np.empty((d, 2 * N), order="F")
+        cols[:, 0::2] = U; cols[:, 1::2] = U + h * dU
+        L, g = eng.loss_grad(np.concatenate([cols.reshape(-1, order="F"), theta[n_u:]]))
+        gc = g[: d * 2 * N].reshape(d, 2 * N, order="F")
+        GU = gc[:, 0::2] + gc[:, 1::2] - (2.0 / self.sigma ** 2) * res
+        GD = h * gc[:, 1::2]
+        g_theta = np.zeros(n_theta)
+        g_theta[n_u:] = g[d * 2 * N:]
+        return L_obs + float(L[0]), np.concatenate([g_theta, self.pack(self.interp_vjp(ip, H, GU, GD))])
+
+
+def neural_gradient_matching_(model: UDE, regularization_weight=0.0, loss_options=None, optim_options=None, verbose=False, device=0):
+    """train!(model; loss_function = "neural gradient matching") (src/Optimizers.jl:453-459, :505, :562-563)."""
+    o = dict(loss_options or {})
+    opts = dict(default_options("neural gradient matching")); opts.update(optim_options or {})
+    ng = NeuralGradientMatching(model, o.get("sigma", 0.1), o.get("tau", 0.5), regularization_weight, o.get("init_weights_layer_1", 5.0),
+                                seed=o.get("seed", 0))
+    x = ng.initial_parameters()
+    m = np.zeros_like(x); v = np.zeros_like(x)
+    trace = []
+    with Engine(ng.problem, device=device) as eng:
+        for it in range(1, int(opts["maxiter"]) + 1):
+            L, g = ng.loss_grad(eng, x)
+            trace.append(L)
+            if verbose:
+                print(round(L, 3), end=" ", flush=True)
+            m = 0.9 * m + 0.1 * g
+            v = 0.999 * v + 0.001 * g * g
+            x = x - opts["step_size"] * (m / (1 - 0.9 ** it)) / (np.sqrt(v / (1 - 0.999 ** it)) + 1e-8)
+    n_theta = model.parameters.shape[0]
+    theta = x[:n_theta].copy()
+    theta[: model.d * ng.N] = ng.interp(ng.unpack(x[n_theta:]))[0].reshape(-1, order="F")
+    model.parameters = theta
+    model.extra["loss_trace"] = np.array(trace)
+    return None
 
 
 class SplineGradientMatching:
@@ -377,6 +512,10 @@ def train_(model: UDE, loss_function=None, optimizer="ADAM", regularization_weig
         loss_function = "derivative matching" if model.multi else "spline gradient matching"
     if optimizer not in ("ADAM", "BFGS"):
         raise ValueError("Select a valid optimization algorithm. Choose from 'ADAM' or 'BFGS'.")      # src/Optimizers.jl:524
+    if loss_function == "neural gradient matching":
+        if optimizer != "ADAM":
+            raise ValueError("neural gradient matching: only optimizer='ADAM' is implemented on the CUDA path")
+        return neural_gradient_matching_(model, regularization_weight, loss_options, optim_options, verbose, device)
     if loss_function == "spline gradient matching":
         if optimizer != "ADAM":
             raise ValueError("spline gradient matching: only optimizer='ADAM' is implemented on the CUDA path")
@@ -461,23 +600,8 @@ def forecast(model: UDE, u0, t0, times, series=0, device=0):
         uh = uh[:, s0:s0 + ln]
     umax, umin, umean = uh.max(axis=1), uh.min(axis=1), uh.mean(axis=1)
     # one two-column series per forecast interval; column 0 of series j is filled with the running state
-    m2 = copy.copy(model)
     tt = np.concatenate([[t0], times])
-    m2.times = np.stack([tt[:-1], tt[1:]], axis=1).reshape(-1)
-    m2.data = np.zeros((d, 2 * n), order="F")
-    m2.multi = True
-    m2.starts = np.arange(n, dtype=np.int64) * 2
-    m2.lengths = np.full(n, 2, dtype=np.int64)
-    if model.cov:
-        nc, off, kt, kx = model.cov
-        blk = slice(series * nc, series * nc + nc + 1) if model.multi else slice(0, nc + 1)
-        o = off[blk]
-        seg_t, seg_x = kt[o[0]:o[-1]], kx[o[0]:o[-1]]
-        m2.cov = (nc, np.concatenate([[0], np.tile(np.diff(o), n).cumsum()]).astype(np.int64), np.tile(seg_t, n), np.tile(seg_x, n))
-    pr = m2.base_problem()
-    pr.loss_kind = P.LOSS_STATE_SPACE
-    if pr.has_series_param:
-        raise NotImplementedError("forecast with per-series parameters")
+    pr = _interval_problem(model, tt[:-1], tt[1:], series)
     pr.finalize()
     theta = np.concatenate([np.zeros(d * 2 * n), model.process_model])
     out = np.zeros((n, d + 1))
