@@ -235,3 +235,28 @@ def test_neural_gradient_matching(ude):
     ude.train_(m, "neural gradient matching", verbose=False, optim_options=dict(maxiter=20))
     tr = m.extra["loss_trace"]
     assert tr[-1] < tr[0] and np.all(np.isfinite(m.uhat)) and np.max(np.abs(m.uhat - m.data)) < 0.5
+
+
+def test_leave_site_out_and_predict(ude):
+    """leave_site_out (src/CrossValidation.jl:463-474) and predict(::MultiUDE, test_data) (src/MultiModelTests.jl:124-150):
+    predictions equal the oracle's one-interval flow from the observed start with the covariates of the labelled series."""
+    from oracle import ude_oracle_np as onp
+    Y, ts = ude.synthetic.lotka_volterra_data(np.random.default_rng(0), 3, 7, random_u0=True)
+    dfm = pd.concat([pd.DataFrame({"time": ts, "series": s + 1, "x1": Y[s, 0], "x2": Y[s, 1]}) for s in range(3)], ignore_index=True)
+    Xc = pd.concat([pd.DataFrame({"time": np.linspace(-0.5, 4.0, 6), "series": s + 1, "X": np.cos(s + np.linspace(0, 2, 6))}) for s in range(3)],
+                   ignore_index=True)
+    mm = ude.MultiNODE(dfm, Xc, hidden_units=4, seed=1)
+    test = dfm[dfm["series"] == 2].copy(); test["series"] = 3
+    out = ude.predict(mm, test)
+    assert list(out.columns) == ["series", "time", "x1", "x2"] and len(out) == 6
+    prob = ude.default_loss(mm)
+    yy = test.sort_values("time")[["x1", "x2"]].to_numpy().T
+    for k in range(6):
+        ref = np.real(onp.flow(prob, mm.process_model, 2, 2, yy[:, k], ts[k], ts[k + 1]))      # covariates of series index 2 (label 3)
+        assert np.max(np.abs(out[["x1", "x2"]].to_numpy()[k] - ref)) < 1e-10
+    score = ude.leave_site_out(mm, lambda m: ude.train_(m, "conditional likelihood", verbose=False, optim_options=dict(maxiter=2)))
+    assert np.isfinite(score) and score > 0
+    # identical predictions from every site => the energy score is the mean absolute error
+    p1 = out.copy()
+    assert abs(ude.energy_score(test[test["time"] > ts[0]], [p1, p1.copy()], mm)
+               - np.mean(np.abs(p1[["x1", "x2"]].to_numpy() - yy[:, 1:].T).sum(axis=1))) < 1e-12

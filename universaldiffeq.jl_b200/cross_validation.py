@@ -181,6 +181,69 @@ def leave_future_out_predict(model: UDE, training: Callable[[UDE], None], n_per_
     return summary, raw
 
 
+def predict(model: UDE, test_data: pd.DataFrame, device=0) -> pd.DataFrame:
+    """predict(UDE, test_data) (src/MultiModelTests.jl:124-150; single series: src/ModelTesting.jl:245-260): one-step-ahead
+    predictions between consecutive rows of `test_data`, started from the observed values; for multi-series models each
+    series of the test frame is predicted with the covariates of the TRAINED series that carries the same label.  All
+    intervals of a series are one batch of segments on the GPU.  Returns [series,] time, variables at the interval ends."""
+    from .training import _interval_problem
+    tcol, scol = model.time_column_name, model.series_column_name
+    frames = []
+    groups = [(None, test_data)] if not model.multi else [(lab, test_data[test_data[scol] == lab]) for lab in sorted(pd.unique(test_data[scol]))]
+    for lab, df in groups:
+        df = df.sort_values(tcol)
+        j = 0 if lab is None else list(model.labels).index(lab)
+        tt = df[tcol].to_numpy(dtype=np.float64)
+        Y = df[list(model.varnames)].to_numpy(dtype=np.float64).T
+        if tt.shape[0] < 2:
+            continue
+        pr = _interval_problem(model, tt[:-1], tt[1:], j).finalize()
+        cols = np.zeros((model.d, 2 * (tt.shape[0] - 1)), order="F")
+        cols[:, 0::2] = Y[:, :-1]
+        with Engine(pr, device=device) as eng:
+            pred = eng.forward(np.concatenate([cols.reshape(-1, order="F"), model.process_model]))[:, 1::2]
+        out = pd.DataFrame(pred.T, columns=list(model.varnames))
+        out.insert(0, tcol, tt[1:])
+        if lab is not None:
+            out.insert(0, scol, lab)
+        frames.append(out)
+    return pd.concat(frames, ignore_index=True)
+
+
+def energy_score(testing: pd.DataFrame, preds: List[pd.DataFrame], model: UDE) -> float:
+    """src/CrossValidation.jl:422-447: mean over test rows of sum_i [ |pred_i - y|_1 / M - sum_j |pred_i - pred_j|_1 / (2 M^2) ]."""
+    Y = testing[list(model.varnames)].to_numpy(dtype=np.float64)
+    Pm = np.stack([p[list(model.varnames)].to_numpy(dtype=np.float64) for p in preds])          # M x T x d
+    M = Pm.shape[0]
+    a = np.abs(Pm - Y[None]).sum(axis=2).sum(axis=0) / M
+    b = np.abs(Pm[:, None] - Pm[None, :]).sum(axis=3).sum(axis=(0, 1)) / (2.0 * M * M)
+    return float(np.mean(a - b))
+
+
+def leave_site_out(model: UDE, training: Callable[[UDE], None], sites: Optional[int] = None, seed: int = 0, device=0) -> float:
+    """leave_site_out(model, training!; sites) (src/CrossValidation.jl:463-474): for each left-out site, refit on the others and
+    score the one-step-ahead predictions of the left-out series made with every remaining site's covariates (energy score)."""
+    if not model.multi:
+        raise ValueError("leave_site_out needs a multi-series model")
+    scol, tcol = model.series_column_name, model.time_column_name
+    labels = list(pd.unique(model.data_frame[scol]))
+    n = len(labels) if sites is None else int(sites)
+    chosen = list(np.random.default_rng(seed).choice(np.array(labels, dtype=object), size=n, replace=False))
+    scores = []
+    for lab in chosen:
+        train_i = model.data_frame[model.data_frame[scol] != lab]
+        test_i = model.data_frame[model.data_frame[scol] == lab].copy()
+        m = model.constructor(train_i)
+        training(m)
+        preds = []
+        for j in m.labels:
+            test_i[scol] = j
+            preds.append(predict(m, test_i, device=device))
+        tmin = test_i[tcol].min()
+        scores.append(energy_score(test_i[test_i[tcol] > tmin].sort_values(tcol), preds, m))
+    return float(np.mean(scores))
+
+
 def kfold_cv(model: UDE, training: Callable[[UDE, float], None], k: int = 10):
     """kfold_cv (src/CrossValidation.jl:167-195): k single-interval hold-outs via the t_skip loss variant; `training(model, t_skip)`
     must fit with that interval left out.  Returns the one-step prediction errors at the skipped intervals."""
