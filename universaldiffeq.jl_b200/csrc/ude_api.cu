@@ -492,10 +492,26 @@ int build_plan(ude_handle* h) {
       if ((int64_t)K > NT) K = (int)NT;
     }
     auto series_end_col = [&](int64_t s) { return h->starts[s] + h->lengths[s]; };
+    const char* renv = getenv("UDE_HOST_CHUNK_RAMP");
+    const bool ramp = K >= 4 && renv && atoi(renv) == 1;      // tuning aid, off: measured slower on C3 (9.20 ms vs 8.99 ms per step)
+    // uniform chunks by default; UDE_HOST_CHUNK_RAMP=1 makes them triangular (1, 2, 3, ..., 3, 2, 1) so that the first upload
+    // and the last download -- the only transfers nothing overlaps -- are small: the under-filled edge launches cost more
+    // than that saves.  Boundaries are strictly increasing (K <= NT).
+    std::vector<int64_t> bounds((size_t)K + 1, 0);
+    {
+      long long wtot = 0, w = 0;
+      for (int i = 0; i < K; ++i) wtot += ramp ? std::min(i + 1, K - i) : 1;
+      for (int k = 1; k <= K; ++k) {
+        w += ramp ? std::min(k, K - k + 1) : 1;
+        bounds[(size_t)k] = std::max<int64_t>(NT * w / wtot, bounds[(size_t)k - 1] + 1);
+      }
+      bounds[(size_t)K] = NT;
+      for (int k = K - 1; k >= 1; --k) bounds[(size_t)k] = std::min(bounds[(size_t)k], bounds[(size_t)k + 1] - 1);
+    }
     int64_t prev_up = 0, prev_dn = 0;
     for (int k = 0; k < K; ++k) {
       ude_handle::Chunk c;
-      c.task_begin = NT * k / K; c.task_end = NT * (k + 1) / K;
+      c.task_begin = bounds[(size_t)k]; c.task_end = bounds[(size_t)k + 1];
       const int64_t s_last = segs[(size_t)c.task_end * SPW - 1].series;          // last series this chunk touches
       c.up_lo = prev_up; c.up_hi = (k == K - 1) ? h->n_cols : series_end_col(s_last);
       // a series touched by the next chunk as well (its first task may start inside s_last) is finalised there
