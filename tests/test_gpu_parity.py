@@ -156,9 +156,24 @@ def test_pipelined_host_path(ude, loss, chunks, monkeypatch):
     """ude_loss_grad overlaps H2D(uhat chunk k+1) / kernel(chunk k) / D2H(grad chunk k-1); chunk borders fall inside
     series here, so columns shared by two chunks exercise the upload/download bookkeeping."""
     monkeypatch.setenv("UDE_HOST_CHUNKS", str(chunks))
+    monkeypatch.setenv("UDE_HOST_CHUNK_ROUNDS", "0")      # tiny problem: keep the requested number of chunks (no rounding to whole grid rounds)
     for rhs, kw in (("node_d4x1", dict(hidden=32)), ("lv_ude", {})):
         prob, theta = cases.make_case(rhs, loss, 0, lengths=(13, 2, 30, 7, 1, 22, 9, 16, 5, 11, 3, 8), skip=(loss == "cond_lik"), **kw)
         _check(prob, theta, ude)
+
+
+def test_pipelined_host_path_whole_rounds(ude, monkeypatch):
+    """default chunk plan (whole rounds of the persistent grid per chunk) on a problem big enough to be split: same result as
+    the resident path and as one chunk."""
+    prob, theta = ude.synthetic.config_c3(n_series=20_000)
+    theta = theta + 0.01 * np.random.default_rng(3).normal(size=theta.shape)
+    res = []
+    for k in ("12", "1"):
+        monkeypatch.setenv("UDE_HOST_CHUNKS", k)
+        with ude.Engine(prob) as eng:
+            res.append(eng.loss_grad(theta))
+    assert abs(res[0][0][0] - res[1][0][0]) < 1e-12 * abs(res[1][0][0])
+    assert cases.relerr(res[0][1], res[1][1]) < 1e-12
 
 
 @pytest.mark.parametrize("rhs,hidden", [("node_d1", 32), ("node_d2", 29), ("node_d3", 32), ("node_d1x1", 20), ("node_d2x1", 32),

@@ -478,54 +478,6 @@ int build_plan(ude_handle* h) {
   }
   h->steps_per_eval = steps;
   h->max_steps_per_task = max_steps;
-  // ---- chunk plan for the host-buffer path (single model, big problems): K contiguous task ranges; chunk k needs the
-  // uhat columns of every series it touches on the device before it starts (up_*), and after it finishes the gradient
-  // of every column no later chunk touches is final (dn_*).
-  h->chunks.clear();
-  {
-    const int64_t NT = h->n_tasks;
-    int K = 1;
-    if (h->n_models == 1 && D.loss_kind != UDE_LOSS_DERIV_MATCH) {
-      const char* env = getenv("UDE_HOST_CHUNKS");
-      K = env ? atoi(env) : (int)std::min<int64_t>(12, NT / 6000);   // measured on C3: 12 chunks = 95% of the resident rate
-      if (K < 1) K = 1;
-      if ((int64_t)K > NT) K = (int)NT;
-    }
-    auto series_end_col = [&](int64_t s) { return h->starts[s] + h->lengths[s]; };
-    const char* renv = getenv("UDE_HOST_CHUNK_RAMP");
-    const bool ramp = K >= 4 && renv && atoi(renv) == 1;      // tuning aid, off: measured slower on C3 (9.20 ms vs 8.99 ms per step)
-    // uniform chunks by default; UDE_HOST_CHUNK_RAMP=1 makes them triangular (1, 2, 3, ..., 3, 2, 1) so that the first upload
-    // and the last download -- the only transfers nothing overlaps -- are small: the under-filled edge launches cost more
-    // than that saves.  Boundaries are strictly increasing (K <= NT).
-    std::vector<int64_t> bounds((size_t)K + 1, 0);
-    {
-      long long wtot = 0, w = 0;
-      for (int i = 0; i < K; ++i) wtot += ramp ? std::min(i + 1, K - i) : 1;
-      for (int k = 1; k <= K; ++k) {
-        w += ramp ? std::min(k, K - k + 1) : 1;
-        bounds[(size_t)k] = std::max<int64_t>(NT * w / wtot, bounds[(size_t)k - 1] + 1);
-      }
-      bounds[(size_t)K] = NT;
-      for (int k = K - 1; k >= 1; --k) bounds[(size_t)k] = std::min(bounds[(size_t)k], bounds[(size_t)k + 1] - 1);
-    }
-    int64_t prev_up = 0, prev_dn = 0;
-    for (int k = 0; k < K; ++k) {
-      ude_handle::Chunk c;
-      c.task_begin = bounds[(size_t)k]; c.task_end = bounds[(size_t)k + 1];
-      const int64_t s_last = segs[(size_t)c.task_end * SPW - 1].series;          // last series this chunk touches
-      c.up_lo = prev_up; c.up_hi = (k == K - 1) ? h->n_cols : series_end_col(s_last);
-      // a series touched by the next chunk as well (its first task may start inside s_last) is finalised there
-      int64_t dn_hi = h->n_cols;
-      if (k < K - 1) {
-        const int64_t s_next_first = segs[(size_t)c.task_end * SPW].series;
-        dn_hi = h->starts[std::min<int64_t>(s_next_first, s_last)];
-        if (s_next_first > s_last) dn_hi = series_end_col(s_last);
-      }
-      c.dn_lo = prev_dn; c.dn_hi = std::max(dn_hi, prev_dn);
-      prev_up = c.up_hi; prev_dn = c.dn_hi;
-      h->chunks.push_back(c);
-    }
-  }
   UDE_CUDA_TRY(h, h->d_segs.upload(segs.data(), segs.size(), h->stream));
 
   // launch geometry: persistent grid, a multiple of the SM count
@@ -562,6 +514,66 @@ int build_plan(ude_handle* h) {
   const size_t stash_bytes = (size_t)h->grid_grad * wpb * (size_t)h->stash_rows_per_warp * 32 * (size_t)h->k_grad->elem_bytes;
   if ((double)stash_bytes > 0.8 * (double)free_b) return fail(h, UDE_ERR_CUDA, "reverse-sweep stash does not fit in device memory");
   UDE_CUDA_TRY(h, h->d_stash.reserve((stash_bytes + 7) / 8));
+  // ---- chunk plan for the host-buffer path (single model, big problems): K contiguous task ranges; chunk k needs the
+  // uhat columns of every series it touches on the device before it starts (up_*), and after it finishes the gradient
+  // of every column no later chunk touches is final (dn_*).
+  h->chunks.clear();
+  {
+    const int64_t NT = h->n_tasks;
+    int K = 1;
+    if (h->n_models == 1 && D.loss_kind != UDE_LOSS_DERIV_MATCH) {
+      const char* env = getenv("UDE_HOST_CHUNKS");
+      K = env ? atoi(env) : (int)std::min<int64_t>(12, NT / 6000);   // measured on C3: ~12 chunks = 95% of the resident rate
+      if (K < 1) K = 1;
+      if ((int64_t)K > NT) K = (int)NT;
+    }
+    // Every chunk is one launch of the persistent grid, whose warps stride over the chunk's tasks: a chunk that is not a
+    // whole number of rounds of the grid leaves part of the GPU idle in its last round (3.5 rounds per chunk = 12 % lost).
+    // So chunks are whole rounds; the remainder goes to the last one.
+    const char* wenv = getenv("UDE_HOST_CHUNK_ROUNDS");
+    int64_t per_chunk = 0;
+    if (K > 1 && !(wenv && atoi(wenv) == 0)) {
+      const int64_t Wg = (int64_t)h->grid_grad * (wpb / best_g->warps_per_task);
+      const int64_t rounds = std::max<int64_t>(1, (NT + (int64_t)K * Wg / 2) / ((int64_t)K * Wg));
+      per_chunk = rounds * Wg;
+      K = (int)((NT + per_chunk - 1) / per_chunk);
+      if (K < 1) K = 1;
+    }
+    auto series_end_col = [&](int64_t s) { return h->starts[s] + h->lengths[s]; };
+    const char* renv = getenv("UDE_HOST_CHUNK_RAMP");
+    const bool ramp = K >= 4 && renv && atoi(renv) == 1;      // tuning aid, off: measured slower on C3 (9.20 ms vs 8.99 ms per step)
+    // uniform chunks by default; UDE_HOST_CHUNK_RAMP=1 makes them triangular (1, 2, 3, ..., 3, 2, 1) so that the first upload
+    // and the last download -- the only transfers nothing overlaps -- are small: the under-filled edge launches cost more
+    // than that saves.  Boundaries are strictly increasing (K <= NT).
+    std::vector<int64_t> bounds((size_t)K + 1, 0);
+    {
+      long long wtot = 0, w = 0;
+      for (int i = 0; i < K; ++i) wtot += ramp ? std::min(i + 1, K - i) : 1;
+      for (int k = 1; k <= K; ++k) {
+        w += ramp ? std::min(k, K - k + 1) : 1;
+        bounds[(size_t)k] = std::max<int64_t>(per_chunk > 0 ? std::min<int64_t>(per_chunk * k, NT) : NT * w / wtot, bounds[(size_t)k - 1] + 1);
+      }
+      bounds[(size_t)K] = NT;
+      for (int k = K - 1; k >= 1; --k) bounds[(size_t)k] = std::min(bounds[(size_t)k], bounds[(size_t)k + 1] - 1);
+    }
+    int64_t prev_up = 0, prev_dn = 0;
+    for (int k = 0; k < K; ++k) {
+      ude_handle::Chunk c;
+      c.task_begin = bounds[(size_t)k]; c.task_end = bounds[(size_t)k + 1];
+      const int64_t s_last = segs[(size_t)c.task_end * SPW - 1].series;          // last series this chunk touches
+      c.up_lo = prev_up; c.up_hi = (k == K - 1) ? h->n_cols : series_end_col(s_last);
+      // a series touched by the next chunk as well (its first task may start inside s_last) is finalised there
+      int64_t dn_hi = h->n_cols;
+      if (k < K - 1) {
+        const int64_t s_next_first = segs[(size_t)c.task_end * SPW].series;
+        dn_hi = h->starts[std::min<int64_t>(s_next_first, s_last)];
+        if (s_next_first > s_last) dn_hi = series_end_col(s_last);
+      }
+      c.dn_lo = prev_dn; c.dn_hi = std::max(dn_hi, prev_dn);
+      prev_up = c.up_hi; prev_dn = c.dn_hi;
+      h->chunks.push_back(c);
+    }
+  }
   UDE_CUDA_TRY(h, h->d_block_part.reserve((size_t)std::max(h->grid_grad, h->grid_fwd) * (size_t)(D.n_pm + 1) * std::max<size_t>(1, h->chunks.size())));
   if (h->chunks.size() > 1 && !h->s_h2d) {
     UDE_CUDA_TRY(h, cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
