@@ -532,11 +532,22 @@ int build_plan(ude_handle* h) {
     // So chunks are whole rounds; the remainder goes to the last one.
     const char* wenv = getenv("UDE_HOST_CHUNK_ROUNDS");
     int64_t per_chunk = 0;
+    std::vector<int64_t> edge_sizes;
     if (K > 1 && !(wenv && atoi(wenv) == 0)) {
       const int64_t Wg = (int64_t)h->grid_grad * (wpb / best_g->warps_per_task);
       const int64_t rounds = std::max<int64_t>(1, (NT + (int64_t)K * Wg / 2) / ((int64_t)K * Wg));
       per_chunk = rounds * Wg;
-      K = (int)((NT + per_chunk - 1) / per_chunk);
+      // the first upload and the last download are the only transfers nothing overlaps: one-round chunks at both ends
+      const char* eenv = getenv("UDE_HOST_CHUNK_EDGE");
+      if (!(eenv && atoi(eenv) == 0) && rounds > 1 && NT > 2 * per_chunk + 2 * Wg) {
+        edge_sizes.push_back(Wg);
+        int64_t rem = NT - 2 * Wg;
+        while (rem > 0) { const int64_t t = std::min(per_chunk, rem); edge_sizes.push_back(t); rem -= t; }
+        edge_sizes.push_back(Wg);
+        K = (int)edge_sizes.size();
+      } else {
+        K = (int)((NT + per_chunk - 1) / per_chunk);
+      }
       if (K < 1) K = 1;
     }
     auto series_end_col = [&](int64_t s) { return h->starts[s] + h->lengths[s]; };
@@ -551,7 +562,10 @@ int build_plan(ude_handle* h) {
       for (int i = 0; i < K; ++i) wtot += ramp ? std::min(i + 1, K - i) : 1;
       for (int k = 1; k <= K; ++k) {
         w += ramp ? std::min(k, K - k + 1) : 1;
-        bounds[(size_t)k] = std::max<int64_t>(per_chunk > 0 ? std::min<int64_t>(per_chunk * k, NT) : NT * w / wtot, bounds[(size_t)k - 1] + 1);
+        int64_t want = NT * w / wtot;
+        if (!edge_sizes.empty()) want = bounds[(size_t)k - 1] + edge_sizes[(size_t)k - 1];
+        else if (per_chunk > 0) want = std::min<int64_t>(per_chunk * k, NT);
+        bounds[(size_t)k] = std::max<int64_t>(want, bounds[(size_t)k - 1] + 1);
       }
       bounds[(size_t)K] = NT;
       for (int k = K - 1; k >= 1; --k) bounds[(size_t)k] = std::min(bounds[(size_t)k], bounds[(size_t)k + 1] - 1);
