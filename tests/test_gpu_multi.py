@@ -23,3 +23,50 @@ def test_two_or_more_gpus_peer_exchange_and_nccl():
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "MULTI_GPU_OK" in out.stdout
+
+
+@pytest.mark.gpu
+def test_peer_exchange_between_threads_of_one_process():
+    """ude_peer_attach with ranks that are host threads of ONE process driving one GPU each (one handle per device
+    from Julia tasks): buffers attach by pointer after cudaDeviceEnablePeerAccess instead of through CUDA IPC."""
+    import threading
+    import numpy as np
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import cases
+    import ude_b200 as ude
+    from oracle import oracle
+    prob, theta = cases.make_case("node_d4x1", "multi_shoot", 0, lengths=(9, 4, 7, 1, 12, 6, 3, 8, 5, 11), hidden=32, reg=1e-3)
+    L_ref, g_ref = oracle.loss_grad(prob, theta)
+    world = 2
+    shards = [ude.sharding.shard_problem(prob, theta, r, world) for r in range(world)]
+    engines = [ude.Engine(shards[r].problem, device=r) for r in range(world)]
+    blobs = [engines[r].peer_export(world) for r in range(world)]
+    for r in range(world):
+        engines[r].peer_attach(blobs, world, r)
+    out, errs = [None] * world, []
+
+    def work(r):
+        try:
+            for _ in range(3):
+                out[r] = engines[r].loss_grad(shards[r].theta)
+        except Exception as ex:      # noqa: BLE001
+            errs.append(ex)
+
+    ts = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(timeout=120)
+    for e in engines:
+        e.close()
+    assert not errs, errs
+    n_u0 = shards[0].uhat_slices[0][1] - shards[0].uhat_slices[0][0]
+    n_u1 = shards[1].uhat_slices[0][1] - shards[1].uhat_slices[0][0]
+    pm0, pm1 = out[0][1][n_u0:n_u0 + shards[0].pm_shared], out[1][1][n_u1:n_u1 + shards[1].pm_shared]
+    assert np.array_equal(pm0, pm1) and out[0][0][0] == out[1][0][0]
+    assert abs(out[0][0][0] - L_ref[0]) < 1e-10 * abs(L_ref[0])
+    base = prob.d * prob.n_cols
+    assert cases.relerr(pm0, g_ref[base:base + shards[0].pm_shared]) < 1e-10

@@ -296,3 +296,31 @@ def test_parity_euler_state_space(ude, rhs, loss):
     _check(prob, theta, ude)
     prob, theta = cases.make_case(rhs, loss, 2, substeps=3, hidden=32 if rhs == "node_d4x1" else 10)
     _check(prob, theta, ude)
+
+
+def test_independent_handles_on_host_threads(ude):
+    """SURVEY 8b threading contract: independent handles are usable concurrently from different host threads (the reference
+    calls training! from Threads.@threads fold tasks, src/CrossValidation.jl:30)."""
+    import threading
+    specs = [("node_d2", "multi_shoot", 10), ("node_d4x1", "cond_lik", 32), ("lv_ude_abs", "mse", 10), ("node_time_d3", "shoot_theta", 10)]
+    probs = [cases.make_case(r, l, 0, hidden=h, lengths=(9, 4, 12, 7, 3, 10), seed=i) for i, (r, l, h) in enumerate(specs)]
+    refs = [oracle.loss_grad(p, th) for p, th in probs]
+    out, errs = [None] * len(probs), []
+
+    def work(i):
+        try:
+            p, th = probs[i]
+            with ude.Engine(p) as eng:
+                for _ in range(20):
+                    out[i] = eng.loss_grad(th)
+        except Exception as ex:      # noqa: BLE001
+            errs.append(ex)
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(len(probs))]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errs, errs
+    for (L, g), (Lr, gr) in zip(out, refs):
+        assert abs(L[0] - Lr[0]) < TOL * abs(Lr[0]) and cases.relerr(g, gr) < TOL
