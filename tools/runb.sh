@@ -1,8 +1,5 @@
-for k in node_time_d3_g2h5_ws_b3 node_time_d3_g2h5_ws_b4 node_time_d3_g2h5_b3; do
-UDE_KERNEL=$k python bench.py --config c4 --steps 20 --warmup 3 --no-other-configs --no-cpu-baseline --no-e2e 2>/dev/null | python -c "
-import sys,json; d=json.loads(sys.stdin.read()); print('c4 $k value %.4e ms %.3f' % (d['value'], d['ms_per_step']), d['roofline']['kernel'][40:75])"
-done
-for k in node_d2_g2h5_ws_b3 node_d2_g2h5_ws_b4 node_d2_g2h5_b3; do
-UDE_KERNEL=$k python bench.py --config c2 --steps 20 --warmup 3 --no-other-configs --no-cpu-baseline --no-e2e 2>/dev/null | python -c "
-import sys,json; d=json.loads(sys.stdin.read()); print('c2 $k value %.4e ms %.3f' % (d['value'], d['ms_per_step']), d['roofline']['kernel'][40:75])"
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+for c in c4 c2; do
+python bench.py --config $c --steps 20 --warmup 3 --no-other-configs --no-cpu-baseline --no-e2e 2>/dev/null | python -c "
+import sys,json; d=json.loads(sys.stdin.read()); print('$c value %.4e ms %.3f' % (d['value'], d['ms_per_step']), d['roofline']['kernel'][40:70])"
 done

@@ -438,7 +438,7 @@ int build_plan(ude_handle* h) {
     };
     switch (D.loss_kind) {
       case UDE_LOSS_STATE_SPACE:
-        if (len == 1) push(c0, 0, ude::SEG_SKIP_PROC);
+        if (len == 1) push(c0, 0, ude::SEG_SKIP_PROC | ude::SEG_NO_PREV);
         for (int64_t t = 1; t < len; ++t) {
           uint16_t f = (t == 1) ? ude::SEG_OBS_FIRST : 0;
           if (!h->skip.empty() && h->skip[c0 + t]) f |= ude::SEG_SKIP_PROC; else steps += S;

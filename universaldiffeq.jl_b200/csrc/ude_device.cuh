@@ -15,7 +15,8 @@ namespace ude {
 constexpr int kMaxD = 8;
 constexpr int kBlockThreads = 128;
 
-enum : uint16_t { SEG_NULL = 1, SEG_OBS_FIRST = 2, SEG_SKIP_PROC = 4 };
+enum : uint16_t { SEG_NULL = 1, SEG_OBS_FIRST = 2, SEG_SKIP_PROC = 4,
+                  SEG_NO_PREV = 8 };   // state-space segment of a one-point series: no interval ends at its column
 
 struct Seg {
   int32_t col;      // STATE_SPACE: END column of the interval; otherwise first column of the block

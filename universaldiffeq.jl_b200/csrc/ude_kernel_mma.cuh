@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) ude_mma_kernel(const DevP
       double wpt = 0.0, eps = 0.0;
       if (LK == LK_STATE) {
         const long long col = sg.col;
-        has_prev = !is_null && (col - 1 >= P.starts[series]);
+        has_prev = !is_null && !(sg.flags & SEG_NO_PREV);
         c0 = has_prev ? col - 1 : col;
         L = (skip || !has_prev) ? 0 : 1; maxL = 1; pre = 0; first_scored = 0; from_theta = true;
       } else {
