@@ -246,6 +246,7 @@ def main():
         raise SystemExit("bench.py needs a B200: the CUDA library is the only implementation (no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = _bind_to_gpu_numa_node(local) if world > 1 else None
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -438,7 +439,8 @@ def main():
                           "rk_steps_per_eval_per_gpu": steps_per_eval, "segments_per_gpu": prob.count_segments(),
                           "n_theta_per_gpu": n_theta, "loss_value": loss_val, "grad_l1": grad_l1,
                           "l2": "inputs+stash larger than L2 (theta, grad, data = %.0f MB per step)" % (3 * 8 * prob.d * prob.n_cols / 1e6),
-                          "parallelism": f"dp{world} by series, {prob.n_pm + 1} doubles exchanged per step: {exchange}" if world > 1 else "single GPU"},
+                          "parallelism": f"dp{world} by series, {prob.n_pm + 1} doubles exchanged per step: {exchange}" if world > 1 else "single GPU",
+                          "cpu_affinity": numa},
                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
                "gpu_launches": eng.launches_per_eval() * args.steps, "clocks": clk, "other_configs": others}
         emit(out)
@@ -446,6 +448,29 @@ def main():
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def _bind_to_gpu_numa_node(index):
+    """One rank per GPU: pin this process (and the pinned host buffers it first-touches) to the CPUs NVML reports as local to
+    its GPU, so the 192 MB per step of the host-buffer path do not cross the socket interconnect.  Best effort."""
+    if os.environ.get("UDE_BENCH_NO_AFFINITY"):
+        return None
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[index]) if vis else index
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = [64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return f"{len(allowed)} cpus {allowed[0]}-{allowed[-1]}"
+    except Exception as ex:       # noqa: BLE001
+        return f"unavailable ({type(ex).__name__})"
+    return None
 
 
 def eng_kernel_name(eng):

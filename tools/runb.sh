@@ -1,5 +1,8 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-for c in c4 c2; do
-python bench.py --config $c --steps 20 --warmup 3 --no-other-configs --no-cpu-baseline --no-e2e 2>/dev/null | python -c "
-import sys,json; d=json.loads(sys.stdin.read()); print('$c value %.4e ms %.3f' % (d['value'], d['ms_per_step']), d['roofline']['kernel'][40:70])"
+nvidia-smi topo -m 2>&1 | head -12 > gpurun_out/topo.txt; lscpu | grep -E "NUMA|Socket|^CPU\(s\)" >> gpurun_out/topo.txt
+for a in 0 1; do
+if [ $a = 1 ]; then export UDE_BENCH_NO_AFFINITY=1; fi
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 2953$a bench.py --gpus 8 --steps 20 --warmup 3 --no-other-configs --no-cpu-baseline > gpurun_out/bench_n8_$a.json 2> gpurun_out/b8.err
+python -c "
+import json; d=json.load(open('gpurun_out/bench_n8_$a.json')); print('n8 noaff=$a', '%.4e steps/s' % d['value'], 'e2e %.4e' % d['e2e']['value'], d['config'].get('cpu_affinity'))" || tail -5 gpurun_out/b8.err
 done
+cat gpurun_out/topo.txt
