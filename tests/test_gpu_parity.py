@@ -324,3 +324,34 @@ def test_independent_handles_on_host_threads(ude):
     assert not errs, errs
     for (L, g), (Lr, gr) in zip(out, refs):
         assert abs(L[0] - Lr[0]) < TOL * abs(Lr[0]) and cases.relerr(g, gr) < TOL
+
+
+def test_error_paths_of_the_wider_api(ude):
+    """UNSUPPORTED / INVALID / STATE answers instead of wrong numbers: Euler with a trajectory loss, the UKF loss on a many-model
+    handle, a forecast chain on a handle whose series are not single intervals, peer attach without export, FP32 + tensor-core
+    request."""
+    prob, theta = cases.make_case("node_d2", "multi_shoot", 2)                      # UDE_EULER is state-space only
+    with pytest.raises(ude.UdeError) as ei:
+        with ude.Engine(prob) as eng:
+            eng.loss_grad(theta)
+    assert ei.value.code == -2
+    many, th_many = cases.make_case("node_d2", "cond_lik", 0, lengths=(5, 4, 6, 3), n_models=2)
+    with ude.Engine(many) as eng:
+        with pytest.raises(ude.UdeError) as ei:
+            eng.ukf_loss_grad(th_many, 0.3 * np.eye(2), 0.1 * np.eye(2))
+        assert ei.value.code == -2
+        with pytest.raises(ude.UdeError):
+            eng.forecast_chain(th_many, np.ones(2), np.ones(2), np.zeros(2), np.ones(2) * 0.5, 0.25, 0.1)
+        with pytest.raises(ude.UdeError):
+            eng.peer_attach([b"\0" * 128, b"\0" * 128], 2, 0)
+        with pytest.raises(ude.UdeError):
+            eng.peer_export(1)
+    one, th_one = cases.make_case("node_d2", "cond_lik", 0, lengths=(1,))           # a single point: nothing to filter
+    with ude.Engine(one) as eng:
+        with pytest.raises(ude.UdeError):
+            eng.ukf_loss_grad(th_one, 0.3 * np.eye(2), 0.1 * np.eye(2))
+        L, g = eng.loss_grad(th_one)                                                # ...but the ordinary loss is defined (observation term)
+        assert np.isfinite(L[0])
+    wide, th_w = cases.make_case("node_d8", "cond_lik", 0, hidden=128, lengths=(4, 3))
+    with ude.Engine(wide, dtype=1) as eng:                                          # FP32 mode never picks a DMMA kernel
+        assert eng.kernel_name().startswith("f32_")
