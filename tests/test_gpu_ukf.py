@@ -136,3 +136,22 @@ def test_kalman_filter_multi(ude):
     tr = mm.extra["loss_trace"]
     assert abs(tr[0] - ref) < 1e-10 * abs(ref)
     assert tr[-1] < tr[0] and Pn.shape == (2, 2) and Px.shape == (2, 2, 24) and np.all(np.isfinite(mm.uhat))
+
+
+def test_ukf_against_committed_fixtures(ude):
+    """the CUDA path against tests/golden/golden_ukf_twin.npz directly (no oracle evaluation at test time)."""
+    import os
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, "golden"))
+    import make_golden_ukf as mg
+    gold = np.load(os.path.join(here, "golden", "golden_ukf_twin.npz"))
+    for rhs, hidden, lengths, solver, alpha in mg.CASES:
+        prob, theta, F, Peta = mg.setup(rhs, hidden, lengths, solver)
+        key = f"{rhs}|{hidden}|{'-'.join(map(str, lengths))}|{solver}|{alpha}"
+        with ude.Engine(prob) as eng:
+            L, g, gF = eng.ukf_loss_grad(theta, F, Peta, alpha=alpha, reg=2e-3)
+        tl, tg = (1e-10, 1e-10) if alpha == 1.0 else (1e-5, 1e-4)
+        assert abs(L - gold[key + "|loss"][0]) < tl * abs(L)
+        assert cases.relerr(g[prob.d * prob.n_cols:], gold[key + "|g_pm"]) < tg
+        assert cases.relerr(gF.reshape(-1, order="F"), gold[key + "|g_F"]) < tg

@@ -148,3 +148,76 @@ def test_save_and_load_model_parameters(ude, tmp_path):
     c = ude.NODE(df, hidden_units=6, seed=2)
     with pytest.raises(ValueError):
         ude.load_model_parameters_(c, f)
+
+
+class _OracleEngine:
+    """stands in for ude.Engine on CPU: the C oracle evaluates the same Problem (test infrastructure only)."""
+
+    def __init__(self, prob):
+        self.prob = prob
+
+    def loss_grad(self, th):
+        from oracle import oracle
+        return oracle.loss_grad(self.prob, th)
+
+
+def test_spline_gradient_matching_formula_on_cpu(ude):
+    """the Euler / state-space restatement of spline_gradient_matching_loss (LFC.jl:888-931) equals the formula written out
+    with the NumPy RHS; its gradient equals central differences."""
+    from oracle import ude_oracle_np as onp
+    df = ude.LotkaVolterra(plot=False, datasize=15)
+    m = ude.NODE(df, hidden_units=4, seed=2)
+    sg = ude.SplineGradientMatching(m, T=12, regularization_weight=1e-3)
+    assert sg.n_knots == 17 and sg.problem.solver == ude.problem.EULER
+    x = sg.initial_parameters()
+    x[: sg.n_alpha] = 0.5 + 0.3 * np.random.default_rng(0).normal(size=sg.n_alpha)
+    eng = _OracleEngine(sg.problem)
+    L, g = sg.loss_grad(eng, x)
+    d, N, T = 2, 15, 12
+    alpha = x[: sg.n_alpha].reshape(sg.n_knots, d, order="F"); pm = x[sg.n_alpha + d * N:]
+    t = m.times; dt = (t[-1] - t[0]) / T; Dt = dt / ((t[-1] - t[0]) / N)
+    # the reference's interpolation: weight (t - ts1)/(ts2 - ts1) on the LEFT knot
+    uh = np.stack([alpha[sg.i1[j]] * sg.w1[j] + alpha[sg.i2[j]] * sg.w2[j] for j in range(N)], axis=1)
+    ref = np.sum(((m.data - uh) / 0.05 ** 2) ** 2)
+    That = sg.n_knots - 1
+    for k in range(That - 1):
+        r = (alpha[k + 1] - alpha[k]) / (sg.ts[k + 1] - sg.ts[k]) - onp.rhs(sg.problem, pm, 0, 0, alpha[k], sg.ts[k])
+        ref += N / That * np.sum((r / (np.sqrt(Dt) * 0.025 ** 2)) ** 2)
+    pr = sg.problem
+    ref += 1e-3 * (np.sum(pm[pr.off_w1:pr.off_w1 + 8] ** 2) + np.sum(pm[pr.off_w2:pr.off_w2 + 8] ** 2))
+    assert abs(L - ref) < 1e-12 * abs(ref)
+    for k in (0, 5, sg.n_alpha - 1, sg.n_alpha + d * N + 3):
+        e = np.zeros_like(x); h = 1e-6 * max(1.0, abs(x[k])); e[k] = h
+        fd = (sg.loss_grad(eng, x + e)[0] - sg.loss_grad(eng, x - e)[0]) / (2 * h)
+        assert abs(g[k] - fd) <= 1e-6 * max(1.0, abs(fd))
+
+
+def test_neural_gradient_matching_formula_on_cpu(ude):
+    """neural_gradient_matching_loss (LFC.jl:764-846) through Euler mini-series, with covariates, against the formula and
+    central differences; the pre-fit of the interpolating network reproduces the data."""
+    from oracle import ude_oracle_np as onp
+    df = ude.LotkaVolterra(plot=False, datasize=10)
+    X = pd.DataFrame({"time": np.linspace(-0.5, 4.5, 11), "X": np.sin(np.linspace(0, 3, 11))})
+    m = ude.NODE(df, X, hidden_units=4, seed=2)
+    ng = ude.NeuralGradientMatching(m, regularization_weight=1e-3, prefit=False)
+    x = ng.initial_parameters()
+    x = x + 0.01 * np.random.default_rng(0).normal(size=x.shape)
+    eng = _OracleEngine(ng.problem)
+    L, g = ng.loss_grad(eng, x)
+    d, N = 2, 10
+    n_theta = m.parameters.shape[0]
+    pm = x[d * N:n_theta]
+    U, dU, _ = ng.interp(ng.unpack(x[n_theta:]))
+    ref = np.sum((m.data - U) ** 2) / 0.1 ** 2
+    for j in range(N):
+        r = dU[:, j] - onp.rhs(ng.problem, pm, j, j, U[:, j], m.times[j])
+        ref += np.sum(r * r) / 0.5 ** 2
+    pr = ng.problem
+    ref += 1e-3 * (np.sum(pm[pr.off_w1:pr.off_w1 + pr.nn_hidden * pr.nn_in] ** 2) + np.sum(pm[pr.off_w2:pr.off_w2 + pr.nn_out * pr.nn_hidden] ** 2))
+    assert abs(L - ref) < 1e-12 * abs(ref)
+    for k in (d * N + 2, n_theta + 1, n_theta + N + 3, n_theta + 2 * N + 5, len(x) - 1):
+        e = np.zeros_like(x); e[k] = 1e-6
+        fd = (ng.loss_grad(eng, x + e)[0] - ng.loss_grad(eng, x - e)[0]) / 2e-6
+        assert abs(g[k] - fd) <= 1e-6 * max(1.0, abs(fd))
+    fit = ude.NeuralGradientMatching(m, prefit=True)
+    assert np.sum((m.data - fit.interp(fit.ip)[0]) ** 2) < 1e-3

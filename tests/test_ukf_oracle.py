@@ -128,3 +128,26 @@ def test_reverse_sweep_matches_complex_step(alpha):
     assert abs(L1 - L0) < 1e-12 * abs(L0)
     assert cases.relerr(h_pm, g_pm) < 1e-9 / alpha ** 2
     assert cases.relerr(h_nu.reshape(-1, order="F"), g_nu) < 1e-9 / alpha ** 2
+
+
+def _golden():
+    import os
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, "golden"))
+    import make_golden_ukf as mg
+    return mg, np.load(os.path.join(here, "golden", "golden_ukf_twin.npz"))
+
+
+def test_ukf_twin_matches_committed_fixtures():
+    """tests/golden/golden_ukf_twin.npz (written by make_golden_ukf.py): loss and both gradients of six cases."""
+    mg, gold = _golden()
+    for rhs, hidden, lengths, solver, alpha in mg.CASES:
+        prob, theta, F, Peta = mg.setup(rhs, hidden, lengths, solver)
+        key = f"{rhs}|{hidden}|{'-'.join(map(str, lengths))}|{solver}|{alpha}"
+        L = ukf.loss(prob, theta, F, Peta, alpha=alpha, reg_weight=1e-3, reg_mult=2.0)
+        tol = 1e-12 if alpha == 1.0 else 1e-6
+        assert abs(L - gold[key + "|loss"][0]) < tol * abs(L)
+        if rhs == "node_d2" and len(lengths) == 1:          # one gradient re-derived here; the rest are checked on the GPU
+            g_pm, g_F = ukf.complex_step_grad(prob, theta, F, Peta, alpha=alpha, reg_weight=1e-3, reg_mult=2.0)
+            assert cases.relerr(g_pm, gold[key + "|g_pm"]) < 1e-12 and cases.relerr(g_F, gold[key + "|g_F"]) < 1e-12
