@@ -256,7 +256,9 @@ def main():
     eng = ude.Engine(prob, device=local, lanes_per_segment=args.lanes, hidden_per_lane=args.hpl, weights_in_smem=args.ws,
                      dtype=1 if args.dtype == "f32" else 0)
     exchange = "none"
-    if world > 1:
+    if world > 1 and prob.n_models > 1:
+        exchange = "none: the models (folds x members) are independent, ranks only own different ones"
+    elif world > 1:
         if args.exchange == "peer":
             # fused finalize + allreduce over peer memory: the ranks swap the IPC descriptions of their exchange buffers
             mine = torch.frombuffer(bytearray(eng.peer_export(world)), dtype=torch.uint8).to(dev)
