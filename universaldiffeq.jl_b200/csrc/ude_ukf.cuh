@@ -45,7 +45,7 @@ struct ude_ukf_plan {
   ude_handle* aux = nullptr;
   int d = 0, K = 0;
   std::vector<UkfStep> steps;
-  DevBuf<int> d_active;
+  DevBuf<int> d_active, d_next;         // d_next[act0 + a]: index of the same series in the next step's list, or -1
   DevBuf<UkfStep> d_steps;
   DevBuf<double> d_xprev, d_Pprev, d_U;               // per (step, active series)
   DevBuf<double> d_x, d_P, d_xb, d_Pb, d_ll, d_pnub;  // per series
@@ -204,12 +204,9 @@ __global__ void ukf_bcast_pm(const double* __restrict__ pm, long long n_pm, cons
 }
 
 template <int d>
-__global__ void ukf_sigma_fwd(UkfStep st, const UkfConst* __restrict__ Cp, const int* __restrict__ active, const double* __restrict__ X,
-                              const double* __restrict__ P, double* __restrict__ xprev, double* __restrict__ Pprev,
-                              double* __restrict__ Usave, double* __restrict__ theta_aux) {
-  const UkfConst& C = *Cp;
-  const int a = blockIdx.x * blockDim.x + threadIdx.x;
-  if (a >= st.n_act) return;
+__device__ __forceinline__ void ukf_sigma_fwd_body(const UkfStep& st, int a, const UkfConst& C, const int* active, const double* X,
+                              const double* P, double* xprev, double* Pprev,
+                              double* Usave, double* theta_aux) {
   const int s = active[st.act0 + a];
   double x[d], A[d * d], U[d * d];
   #pragma unroll
@@ -236,12 +233,9 @@ __global__ void ukf_sigma_fwd(UkfStep st, const UkfConst* __restrict__ Cp, const
 }
 
 template <int d>
-__global__ void ukf_update_fwd(UkfStep st, const UkfConst* __restrict__ Cp, const int* __restrict__ active, const long long* __restrict__ starts,
-                               const double* __restrict__ data, const double* __restrict__ traj, double* __restrict__ X,
-                               double* __restrict__ P, double* __restrict__ ll, double* __restrict__ states, double* __restrict__ covs) {
-  const UkfConst& C = *Cp;
-  const int a = blockIdx.x * blockDim.x + threadIdx.x;
-  if (a >= st.n_act) return;
+__device__ __forceinline__ void ukf_update_fwd_body(const UkfStep& st, int a, const UkfConst& C, const int* active, const long long* starts,
+                               const double* data, const double* traj, double* X,
+                               double* P, double* ll, double* states, double* covs) {
   const int s = active[st.act0 + a];
   const long long col = starts[s] + st.k + 1;
   UkfUpdate<d> W;
@@ -272,12 +266,9 @@ __global__ void ukf_update_fwd(UkfStep st, const UkfConst* __restrict__ Cp, cons
 // adjoint of the update for loss = -sum ll: in (xb, Pb) = d loss / d (posterior mean, covariance); out: target columns
 // y_j - lambda_j / 2 and this series' share of d loss / d P_nu
 template <int d>
-__global__ void ukf_update_bwd(UkfStep st, const UkfConst* __restrict__ Cp, const int* __restrict__ active, const long long* __restrict__ starts,
-                               const double* __restrict__ data, const double* __restrict__ traj, const double* __restrict__ Xb,
-                               const double* __restrict__ Pb_in, double* __restrict__ pnub, double* __restrict__ theta_aux) {
-  const UkfConst& C = *Cp;
-  const int a = blockIdx.x * blockDim.x + threadIdx.x;
-  if (a >= st.n_act) return;
+__device__ __forceinline__ void ukf_update_bwd_body(const UkfStep& st, int a, const UkfConst& C, const int* active, const long long* starts,
+                               const double* data, const double* traj, const double* Xb,
+                               const double* Pb_in, double* pnub, double* theta_aux) {
   const int s = active[st.act0 + a];
   const long long col = starts[s] + st.k + 1, cf = st.col0 + 2LL * (2 * d + 1) * a;
   UkfUpdate<d> W;
@@ -372,11 +363,8 @@ __global__ void ukf_update_bwd(UkfStep st, const UkfConst* __restrict__ Cp, cons
 }
 
 template <int d>
-__global__ void ukf_sigma_bwd(UkfStep st, const UkfConst* __restrict__ Cp, const int* __restrict__ active, const double* __restrict__ Usave,
-                              const double* __restrict__ grad_aux, double* __restrict__ Xb, double* __restrict__ Pb) {
-  const UkfConst& C = *Cp;
-  const int a = blockIdx.x * blockDim.x + threadIdx.x;
-  if (a >= st.n_act) return;
+__device__ __forceinline__ void ukf_sigma_bwd_body(const UkfStep& st, int a, const UkfConst& C, const int* active, const double* Usave,
+                              const double* grad_aux, double* Xb, double* Pb) {
   const int s = active[st.act0 + a];
   const double* g = grad_aux + st.theta_base + (long long)d * 2 * (2 * d + 1) * a;
   double U[d * d], Ub[d * d], Ab[d * d];
@@ -396,6 +384,62 @@ __global__ void ukf_sigma_bwd(UkfStep st, const UkfConst* __restrict__ Cp, const
   ukf_chol_upper_adjoint<d>(U, Ub, Ab);
   #pragma unroll
   for (int i = 0; i < d * d; ++i) Pb[(long long)s * d * d + i] = C.c * Ab[i];
+}
+
+template <int d>
+__global__ void ukf_sigma_fwd(UkfStep st, const UkfConst* __restrict__ Cp, const int* __restrict__ active, const double* __restrict__ X,
+                              const double* __restrict__ P, double* __restrict__ xprev, double* __restrict__ Pprev,
+                              double* __restrict__ Usave, double* __restrict__ theta_aux) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= st.n_act) return;
+  ukf_sigma_fwd_body<d>(st, a, *Cp, active, X, P, xprev, Pprev, Usave, theta_aux);
+}
+
+template <int d>
+__global__ void ukf_update_fwd(UkfStep st, const UkfConst* __restrict__ Cp, const int* __restrict__ active, const long long* __restrict__ starts,
+                               const double* __restrict__ data, const double* __restrict__ traj, double* __restrict__ X,
+                               double* __restrict__ P, double* __restrict__ ll, double* __restrict__ states, double* __restrict__ covs) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= st.n_act) return;
+  ukf_update_fwd_body<d>(st, a, *Cp, active, starts, data, traj, X, P, ll, states, covs);
+}
+
+template <int d>
+__global__ void ukf_update_bwd(UkfStep st, const UkfConst* __restrict__ Cp, const int* __restrict__ active, const long long* __restrict__ starts,
+                               const double* __restrict__ data, const double* __restrict__ traj, const double* __restrict__ Xb,
+                               const double* __restrict__ Pb_in, double* __restrict__ pnub, double* __restrict__ theta_aux) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= st.n_act) return;
+  ukf_update_bwd_body<d>(st, a, *Cp, active, starts, data, traj, Xb, Pb_in, pnub, theta_aux);
+}
+
+template <int d>
+__global__ void ukf_sigma_bwd(UkfStep st, const UkfConst* __restrict__ Cp, const int* __restrict__ active, const double* __restrict__ Usave,
+                              const double* __restrict__ grad_aux, double* __restrict__ Xb, double* __restrict__ Pb) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= st.n_act) return;
+  ukf_sigma_bwd_body<d>(st, a, *Cp, active, Usave, grad_aux, Xb, Pb);
+}
+
+// update of step k followed, for the series that go on, by the sigma points of step k + 1: a thread only ever touches its own
+// series' state, so the two halves need no grid-wide ordering
+template <int d>
+__global__ void ukf_fwd_fused(UkfStep st, UkfStep nx, const int* __restrict__ next_idx, const UkfConst* __restrict__ Cp, const int* __restrict__ active, const long long* __restrict__ starts, const double* __restrict__ data, const double* __restrict__ traj, double* X, double* P, double* __restrict__ ll, double* __restrict__ states, double* __restrict__ covs, double* __restrict__ xprev, double* __restrict__ Pprev, double* __restrict__ Usave, double* __restrict__ theta_aux) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= st.n_act) return;
+  ukf_update_fwd_body<d>(st, a, *Cp, active, starts, data, traj, X, P, ll, states, covs);
+  const int an = next_idx[st.act0 + a];
+  if (an >= 0) ukf_sigma_fwd_body<d>(nx, an, *Cp, active, X, P, xprev, Pprev, Usave, theta_aux);
+}
+
+// adjoint of the sigma points of step k + 1 (for the series that had one) followed by the adjoint of the update of step k
+template <int d>
+__global__ void ukf_bwd_fused(UkfStep st, UkfStep nx, const int* __restrict__ next_idx, const UkfConst* __restrict__ Cp, const int* __restrict__ active, const double* __restrict__ Usave, const double* __restrict__ grad_aux, double* Xb, double* Pb, const long long* __restrict__ starts, const double* __restrict__ data, const double* __restrict__ traj, double* Pb_in, double* __restrict__ pnub, double* __restrict__ theta_aux) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= st.n_act) return;
+  const int an = next_idx[st.act0 + a];
+  if (an >= 0) ukf_sigma_bwd_body<d>(nx, an, *Cp, active, Usave, grad_aux, Xb, Pb);
+  ukf_update_bwd_body<d>(st, a, *Cp, active, starts, data, traj, Xb, Pb_in, pnub, theta_aux);
 }
 
 // out = [loss | d loss / d process_model (n_pm) | d loss / d Lf (d*d)], fixed summation order
@@ -530,7 +574,17 @@ int ukf_build(ude_handle* h, ude_ukf_plan*& out_plan) {
     if (pl->aux->theta_base[(size_t)k] != pl->steps[(size_t)k].theta_base) return fail(h, UDE_ERR_INVALID, "UKF loss: auxiliary layout mismatch");
   cudaStream_t s = h->stream;
   const size_t NA = active.size(), NS = (size_t)h->n_series;
+  std::vector<int> next_idx(active.size(), -1);
+  for (int k = 0; k + 1 < K; ++k) {
+    const UkfStep& a0 = pl->steps[(size_t)k]; const UkfStep& a1 = pl->steps[(size_t)k + 1];
+    int j = 0;                                   // both lists are in series order
+    for (int a = 0; a < a0.n_act; ++a) {
+      while (j < a1.n_act && active[(size_t)a1.act0 + j] < active[(size_t)a0.act0 + a]) ++j;
+      if (j < a1.n_act && active[(size_t)a1.act0 + j] == active[(size_t)a0.act0 + a]) next_idx[(size_t)a0.act0 + a] = j;
+    }
+  }
   UDE_CUDA_TRY(h, pl->d_active.upload(active.data(), NA, s));
+  UDE_CUDA_TRY(h, pl->d_next.upload(next_idx.data(), NA, s));
   UDE_CUDA_TRY(h, pl->d_steps.upload(pl->steps.data(), (size_t)K, s));
   UDE_CUDA_TRY(h, pl->d_xprev.reserve(NA * d)); UDE_CUDA_TRY(h, pl->d_Pprev.reserve(NA * d * d)); UDE_CUDA_TRY(h, pl->d_U.reserve(NA * d * d));
   UDE_CUDA_TRY(h, pl->d_x.reserve(NS * d)); UDE_CUDA_TRY(h, pl->d_P.reserve(NS * d * d));
@@ -559,14 +613,27 @@ int ukf_enqueue(ude_handle* h, ude_ukf_plan* pl, bool want_grad, double* d_state
   ukf_init<<<(int)((NS + TB - 1) / TB), TB, 0, s>>>((int)NS, d, h->d_starts.p, h->d_data.p, C, pl->d_x.p, pl->d_P.p, d_states, d_covs);
   ukf_bcast_pm<<<K, 128, 0, s>>>(pl->d_pm.p, D.n_pm, pl->d_steps.p, K, d, n_sig, pl->d_theta_aux.p);
   UDE_CUDA_TRY(h, cudaGetLastError());
+  // per step: [sigma points] -> segment kernel (2d+1 predicts per series) -> [update]; the update of step k and the sigma
+  // points of step k+1 are one launch
+  {
+    const UkfStep& st0 = pl->steps[0];
+    UKF_DISPATCH(d, ukf_sigma_fwd, <<<(st0.n_act + TB - 1) / TB, TB, 0, s>>>(st0, C, pl->d_active.p, pl->d_x.p, pl->d_P.p, pl->d_xprev.p, pl->d_Pprev.p,
+                                                                              pl->d_U.p, pl->d_theta_aux.p))
+  }
   for (int k = 0; k < K; ++k) {
     const UkfStep& st = pl->steps[(size_t)k];
     const int nb = (st.n_act + TB - 1) / TB;
-    UKF_DISPATCH(d, ukf_sigma_fwd, <<<nb, TB, 0, s>>>(st, C, pl->d_active.p, pl->d_x.p, pl->d_P.p, pl->d_xprev.p, pl->d_Pprev.p, pl->d_U.p, pl->d_theta_aux.p))
     int rc = launch_segments(ax, pl->d_theta_aux.p, nullptr, pl->d_traj_aux.p, ax->model_task0[(size_t)k], ax->model_task0[(size_t)k + 1], 0, s);
     if (rc != UDE_OK) return fail(h, rc, std::string("UKF predict: ") + ude_last_error(ax));
-    UKF_DISPATCH(d, ukf_update_fwd, <<<nb, TB, 0, s>>>(st, C, pl->d_active.p, h->d_starts.p, h->d_data.p, pl->d_traj_aux.p, pl->d_x.p,
-                                                      pl->d_P.p, pl->d_ll.p, d_states, d_covs))
+    if (k + 1 < K) {
+      const UkfStep& nx = pl->steps[(size_t)k + 1];
+      UKF_DISPATCH(d, ukf_fwd_fused, <<<nb, TB, 0, s>>>(st, nx, pl->d_next.p, C, pl->d_active.p, h->d_starts.p, h->d_data.p, pl->d_traj_aux.p,
+                                                       pl->d_x.p, pl->d_P.p, pl->d_ll.p, d_states, d_covs, pl->d_xprev.p, pl->d_Pprev.p, pl->d_U.p,
+                                                       pl->d_theta_aux.p))
+    } else {
+      UKF_DISPATCH(d, ukf_update_fwd, <<<nb, TB, 0, s>>>(st, C, pl->d_active.p, h->d_starts.p, h->d_data.p, pl->d_traj_aux.p, pl->d_x.p,
+                                                        pl->d_P.p, pl->d_ll.p, d_states, d_covs))
+    }
   }
   UDE_CUDA_TRY(h, cudaGetLastError());
   if (want_grad) {
@@ -575,14 +642,22 @@ int ukf_enqueue(ude_handle* h, ude_ukf_plan* pl, bool want_grad, double* d_state
     UDE_CUDA_TRY(h, cudaMemsetAsync(pl->d_Pb.p, 0, NS * d * d * sizeof(double), s));
     UDE_CUDA_TRY(h, cudaMemsetAsync(pl->d_pnub.p, 0, NS * d * d * sizeof(double), s));
     UDE_CUDA_TRY(h, cudaMemsetAsync(ax->d_model_loss.p, 0, (size_t)K * sizeof(double), s));
+    // reverse: [update adjoint] -> segment loss+adjoint kernel -> [sigma adjoint]; the sigma adjoint of step k+1 and the update
+    // adjoint of step k are one launch; the sigma adjoint of step 0 would differentiate w.r.t. the fixed initial state: skipped
+    {
+      const UkfStep& stl = pl->steps[(size_t)K - 1];
+      UKF_DISPATCH(d, ukf_update_bwd, <<<(stl.n_act + TB - 1) / TB, TB, 0, s>>>(stl, C, pl->d_active.p, h->d_starts.p, h->d_data.p, pl->d_traj_aux.p,
+                                                                                 pl->d_xb.p, pl->d_Pb.p, pl->d_pnub.p, pl->d_theta_aux.p))
+    }
     for (int k = K - 1; k >= 0; --k) {
-      const UkfStep& st = pl->steps[(size_t)k];
-      const int nb = (st.n_act + TB - 1) / TB;
-      UKF_DISPATCH(d, ukf_update_bwd, <<<nb, TB, 0, s>>>(st, C, pl->d_active.p, h->d_starts.p, h->d_data.p, pl->d_traj_aux.p, pl->d_xb.p,
-                                                        pl->d_Pb.p, pl->d_pnub.p, pl->d_theta_aux.p))
       int rc = launch_segments(ax, pl->d_theta_aux.p, pl->d_grad_aux.p, nullptr, ax->model_task0[(size_t)k], ax->model_task0[(size_t)k + 1], 0, s);
       if (rc != UDE_OK) return fail(h, rc, std::string("UKF adjoint: ") + ude_last_error(ax));
-      UKF_DISPATCH(d, ukf_sigma_bwd, <<<nb, TB, 0, s>>>(st, C, pl->d_active.p, pl->d_U.p, pl->d_grad_aux.p, pl->d_xb.p, pl->d_Pb.p))
+      if (k > 0) {
+        const UkfStep& st = pl->steps[(size_t)k - 1]; const UkfStep& nx = pl->steps[(size_t)k];
+        UKF_DISPATCH(d, ukf_bwd_fused, <<<(st.n_act + TB - 1) / TB, TB, 0, s>>>(st, nx, pl->d_next.p, C, pl->d_active.p, pl->d_U.p, pl->d_grad_aux.p,
+                                                                               pl->d_xb.p, pl->d_Pb.p, h->d_starts.p, h->d_data.p, pl->d_traj_aux.p,
+                                                                               pl->d_Pb.p, pl->d_pnub.p, pl->d_theta_aux.p))
+      }
     }
     UDE_CUDA_TRY(h, cudaGetLastError());
   }
