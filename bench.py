@@ -187,7 +187,7 @@ def run_reference(args):
     from oracle import oracle
     threads = oracle.max_threads()
     # one "step" = one loss+grad of a bounded sample of the workload (sized for ~0.3 s of wall time per step)
-    n_sample = args.cpu_sample or {"c2": 1500, "c3": 600, "c3mse": 600, "c4": 4, "c5": 1500}[args.config]
+    n_sample = args.cpu_sample or {"c2": 6000, "c3": 2500, "c3mse": 2500, "c4": 16, "c5": 6000}[args.config]
     prob, th, name = build_problem(ude, args, 0, n_override=n_sample)
     steps = prob.count_steps()
     for _ in range(args.warmup):
