@@ -503,9 +503,70 @@ def load_model_parameters_(model: UDE, file):
     model.process_model[:] = vals
 
 
+def _run_on_ranks(fns):
+    """run one callable per rank on its own host thread (the fused exchange makes every evaluation a collective)"""
+    import threading
+    out, errs = [None] * len(fns), []
+
+    def work(r):
+        try:
+            out[r] = fns[r]()
+        except Exception as ex:      # noqa: BLE001
+            errs.append(ex)
+
+    ts = [threading.Thread(target=work, args=(r,)) for r in range(len(fns))]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    if errs:
+        raise errs[0]
+    return out
+
+
+def adam_multi_gpu(prob: P.Problem, theta, step_size, maxiter, devices, want_states=False):
+    """Device-resident Adam on several GPUs of one box from ONE process: the series of a single-model problem are split into
+    contiguous blocks (sharding.shard_problem), one handle and one host thread per GPU, ude_peer_export / ude_peer_attach
+    by pointer; every iteration ends in the fused finalize + peer-memory exchange, so all ranks apply the identical
+    update to their copy of the shared parameters.  Returns (theta, loss_trace[, states d x n_cols])."""
+    from .sharding import shard_problem
+    world = len(devices)
+    theta = np.asarray(theta, dtype=np.float64)
+    shards = [shard_problem(prob, theta, r, world) for r in range(world)]
+    engines = []
+    try:
+        for r in range(world):
+            engines.append(Engine(shards[r].problem, device=devices[r]))
+        blobs = [e.peer_export(world) for e in engines]
+        for r, e in enumerate(engines):
+            e.peer_attach(blobs, world, r)
+        res = _run_on_ranks([lambda r=r: engines[r].adam(shards[r].theta, step_size, maxiter) for r in range(world)])
+        new = theta.copy()
+        pmg = prob.pm_base(0)
+        for r, sh in enumerate(shards):
+            glo, ghi, llo = sh.uhat_slices[0]
+            th_r = res[r][0]
+            new[glo:ghi] = th_r[llo:llo + (ghi - glo)]
+            n_u = ghi - glo
+            if r == 0:
+                new[pmg:pmg + sh.pm_shared] = th_r[n_u:n_u + sh.pm_shared]
+            if prob.has_series_param:
+                s0, s1 = sh.series
+                new[pmg + sh.pm_shared + s0: pmg + sh.pm_shared + s1] = th_r[n_u + sh.pm_shared:]
+        out = [new, res[0][1]]
+        if want_states:
+            parts = _run_on_ranks([lambda r=r: engines[r].forward(res[r][0]) for r in range(world)])
+            out.append(np.concatenate(parts, axis=1))
+        return tuple(out)
+    finally:
+        for e in engines:
+            e.close()
+
+
 def train_(model: UDE, loss_function=None, optimizer="ADAM", regularization_weight=0.0, verbose=True,
-           loss_options=None, optim_options=None, t_skip=None, device=0, on_device: Optional[bool] = None):
+           loss_options=None, optim_options=None, t_skip=None, device=0, on_device: Optional[bool] = None, devices=None):
     """train!(model; ...) (src/Optimizers.jl:352-570, :578-742) on the CUDA hot path.  Mutates model.parameters.
+    devices=(0, 1, ...): multi-series models with the ADAM optimiser are trained data-parallel over those GPUs (adam_multi_gpu).
     on_device=True keeps theta, Adam moments and the gradient on the GPU for all iterations (SURVEY.md 8f row 1);
     the default does so whenever no per-iteration printing is requested."""
     if loss_function is None:      # the reference's defaults: src/Optimizers.jl:354 (UDE), :579 (MultiUDE)
@@ -527,6 +588,18 @@ def train_(model: UDE, loss_function=None, optimizer="ADAM", regularization_weig
     prob = build_problem(model, loss_function, regularization_weight, loss_options, t_skip)
     opts = dict(default_options(loss_function)); opts.update(optim_options or {})
     on_device = (not verbose) if on_device is None else on_device
+    if devices is not None and len(devices) > 1:
+        if optimizer != "ADAM" or not model.multi or prob.n_models != 1:
+            raise ValueError("devices=...: data-parallel training needs a multi-series model and optimizer='ADAM'")
+        traj = loss_function in ("shooting", "multiple shooting")
+        res = adam_multi_gpu(prob, model.parameters, opts["step_size"], opts["maxiter"], list(devices), want_states=traj)
+        model.parameters = res[0]
+        if traj:
+            model.uhat[:, :] = res[2]
+        elif loss_function in ("derivative matching", "gradient matching", "smooth gradient matching"):
+            model.uhat[:, :] = prob.dm_u
+        model.extra["loss_trace"] = res[1]
+        return None
     with Engine(prob, device=device) as eng:
         if optimizer == "BFGS":
             # src/Optimizers.jl:506-510: Optim.BFGS on the same loss; here SciPy's BFGS driven by ude_loss_grad
