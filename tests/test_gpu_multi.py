@@ -95,3 +95,24 @@ def test_train_on_two_gpus_equals_one_gpu(loss_function):
     ude.train_(b, loss_function, devices=(0, 1), **kw)
     assert np.max(np.abs(a.extra["loss_trace"].ravel() - b.extra["loss_trace"].ravel()) / np.abs(a.extra["loss_trace"].ravel())) < 1e-9
     assert np.max(np.abs(a.parameters - b.parameters)) < 1e-9 * max(1.0, np.max(np.abs(a.parameters)))
+
+
+@pytest.mark.gpu
+def test_batched_cross_validation_on_two_gpus():
+    """leave_future_out_batched(devices=(0, 1)): folds x members are whole models per GPU; identical to one GPU (no exchange,
+    same arithmetic per model)."""
+    import numpy as np
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    sys.path.insert(0, ROOT)
+    import ude_b200 as ude
+    df = ude.LotkaVolterra(plot=False, datasize=18)
+    m = ude.NODE(df, hidden_units=5, seed=3)
+    kw = dict(k=3, loss_function="conditional likelihood", optim_options=dict(maxiter=10), member_seeds=[1, 2], do_forecast=False)
+    one = ude.leave_future_out_batched(m, **kw)
+    two = ude.leave_future_out_batched(m, devices=(0, 1), **kw)
+    assert len(one[0]) == len(two[0]) == 6
+    for a, b in zip(one[0], two[0]):
+        assert np.max(np.abs(a.parameters - b.parameters)) < 1e-12
+    assert np.max(np.abs(one[4] - two[4])) < 1e-10 * np.max(np.abs(one[4]))

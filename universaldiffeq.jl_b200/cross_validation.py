@@ -124,10 +124,11 @@ def stack_models(models: List[UDE], loss_function, regularization_weight=0.0, lo
 
 def leave_future_out_batched(model: UDE, k: int, skip: int = 1, loss_function="conditional likelihood", regularization_weight=0.0,
                              loss_options=None, optim_options=None, n_members: int = 1, member_seeds: Optional[List[int]] = None,
-                             device=0, do_forecast=True):
+                             device=0, do_forecast=True, devices=None):
     """All k folds x n_members ensemble members (same model re-initialised with different NN seeds through
     `model.extra['reseed'](data, seed)`; BASELINE config C4) trained in ONE device-resident Adam run: member-major,
-    fold-minor.  Returns (models, training_data, testing_data, forecasts, loss_trace)."""
+    fold-minor.  devices=(0, 1, ...) spreads the independent models over several GPUs (whole models per GPU, no exchange).
+    Returns (models, training_data, testing_data, forecasts, loss_trace)."""
     train, test = _split(model, k, int(round(skip)))
     if n_members > 1 or member_seeds is not None:
         seeds = list(member_seeds) if member_seeds is not None else list(range(1, n_members + 1))
@@ -140,8 +141,25 @@ def leave_future_out_batched(model: UDE, k: int, skip: int = 1, loss_function="c
         models = [model.constructor(tr) for tr in train]
     opts = dict(default_options(loss_function)); opts.update(optim_options or {})
     big, theta = stack_models(models, loss_function, regularization_weight, loss_options)
-    with Engine(big, device=device) as eng:
-        theta, trace = eng.adam(theta, opts["step_size"], opts["maxiter"])
+    if devices is not None and len(devices) > 1 and big.n_models >= len(devices):
+        from .sharding import shard_problem
+        from .training import _run_on_ranks
+        world = len(devices)
+        shards = [shard_problem(big, theta, r, world) for r in range(world)]
+
+        def fit(r):
+            with Engine(shards[r].problem, device=devices[r]) as eng:
+                return eng.adam(shards[r].theta, opts["step_size"], opts["maxiter"])
+
+        res = _run_on_ranks([lambda r=r: fit(r) for r in range(world)])
+        theta = theta.copy()
+        for sh, (th_r, _) in zip(shards, res):
+            lo, hi, _ = sh.uhat_slices[0]
+            theta[lo:hi] = th_r
+        trace = np.concatenate([tr for _, tr in res], axis=1)
+    else:
+        with Engine(big, device=device) as eng:
+            theta, trace = eng.adam(theta, opts["step_size"], opts["maxiter"])
     for mi, m in enumerate(models):
         lo = int(big.theta_base[mi]); hi = int(big.theta_base[mi + 1]) if mi + 1 < big.n_models else big.n_theta
         m.parameters = theta[lo:hi].copy()
