@@ -28,10 +28,11 @@ def _split(model: UDE, k: int, skip: int):
     for i in range(skip, skip * k + 1, skip):
         if not model.multi:
             train.append(data.iloc[:-i]); test.append(data.iloc[-i:])
-        else:   # src/CrossValidation.jl:242-255: drop the last i points of every series
-            parts = [data[data[model.series_column_name] == lab].sort_values(tcol) for lab in pd.unique(data[model.series_column_name])]
-            train.append(pd.concat([d.iloc[:-i] for d in parts], ignore_index=True))
-            test.append(pd.concat([d.iloc[-i:] for d in parts], ignore_index=True))
+        else:   # src/CrossValidation.jl:242-255: drop the last i points of every series (one sort, not one filter per series)
+            srt = data.sort_values([model.series_column_name, tcol], kind="stable")
+            from_end = srt.groupby(model.series_column_name, sort=False).cumcount(ascending=False).to_numpy()
+            train.append(srt[from_end >= i].reset_index(drop=True))
+            test.append(srt[from_end < i].reset_index(drop=True))
     return train, test
 
 

@@ -123,28 +123,39 @@ def process_multi_data(data: pd.DataFrame, time_column_name, series_column_name)
 
 def interpolate_covariates(X: pd.DataFrame, time_column_name, series_column_name=None, labels=None,
                            variable_column_name=None, value_column_name=None):
-    """-> (n_cov, knot_off, knot_t, knot_x): CSR knots per (series, variable); wide or long format (src/covariates.jl)."""
-    def one_series(df):
-        out = []
-        if variable_column_name is None:
-            d2 = df.sort_values(time_column_name, kind="stable")
-            t = d2[time_column_name].to_numpy(dtype=np.float64)
-            for c in [c for c in d2.columns if c not in (time_column_name, series_column_name)]:
-                out.append((t, d2[c].to_numpy(dtype=np.float64)))
-        else:
-            for var in pd.unique(X[variable_column_name]):
-                d2 = df[df[variable_column_name] == var].sort_values(time_column_name, kind="stable")
-                out.append((d2[time_column_name].to_numpy(dtype=np.float64), d2[value_column_name].to_numpy(dtype=np.float64)))
-        return out
-    groups = [one_series(X)] if series_column_name is None else [one_series(X[X[series_column_name] == lab]) for lab in labels]
-    n_cov = len(groups[0])
-    off, kt, kx = [0], [], []
-    for grp in groups:
-        if len(grp) != n_cov:
-            raise ValueError("every series needs the same covariates")
-        for t, x in grp:
-            kt.append(t); kx.append(x); off.append(off[-1] + len(t))
-    return n_cov, np.array(off, dtype=np.int64), np.concatenate(kt), np.concatenate(kx)
+    """-> (n_cov, knot_off, knot_t, knot_x): CSR knots per (series, variable); wide or long format (src/covariates.jl).
+    One sort of the whole frame (the reference filters the frame once per series, O(series x rows), src/covariates.jl:30-44)."""
+    n_rows = len(X)
+    if series_column_name is None:
+        s_code, n_series = np.zeros(n_rows, dtype=np.int64), 1
+    else:
+        code = {lab: i for i, lab in enumerate(labels)}
+        s_code = X[series_column_name].map(code).to_numpy(dtype=np.float64)
+        n_series = len(labels)
+    t = X[time_column_name].to_numpy(dtype=np.float64)
+    if variable_column_name is None:          # wide: one column per covariate
+        cols = [c for c in X.columns if c not in (time_column_name, series_column_name)]
+        n_cov = len(cols)
+        s_long = np.tile(s_code, n_cov)
+        v_long = np.repeat(np.arange(n_cov), n_rows)
+        t_long = np.tile(t, n_cov)
+        x_long = np.concatenate([X[c].to_numpy(dtype=np.float64) for c in cols]) if n_cov else np.zeros(0)
+    else:                                     # long: (variable, value) pairs
+        variables = list(pd.unique(X[variable_column_name]))
+        vcode = {v: i for i, v in enumerate(variables)}
+        n_cov = len(variables)
+        s_long, t_long = s_code, t
+        v_long = X[variable_column_name].map(vcode).to_numpy(dtype=np.int64)
+        x_long = X[value_column_name].to_numpy(dtype=np.float64)
+    keep = ~np.isnan(s_long) if s_long.dtype.kind == "f" else np.ones(s_long.shape[0], dtype=bool)    # rows of unknown series
+    s_long, v_long, t_long, x_long = s_long[keep].astype(np.int64), v_long[keep], t_long[keep], x_long[keep]
+    order = np.lexsort((t_long, v_long, s_long))              # by series, then variable, then time (stable)
+    cnt = np.bincount(s_long * n_cov + v_long, minlength=n_series * n_cov) if n_cov else np.zeros(0, dtype=np.int64)
+    per_series = cnt.reshape(n_series, n_cov) if n_cov else cnt
+    if n_cov and np.any((per_series == 0).any(axis=1) & (per_series > 0).any(axis=1)):
+        raise ValueError("every series needs the same covariates")
+    off = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)
+    return n_cov, off, t_long[order], x_long[order]
 
 
 # ---- model objects ---------------------------------------------------------------------------------------------------
