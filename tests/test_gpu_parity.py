@@ -355,3 +355,28 @@ def test_error_paths_of_the_wider_api(ude):
     wide, th_w = cases.make_case("node_d8", "cond_lik", 0, hidden=128, lengths=(4, 3))
     with ude.Engine(wide, dtype=1) as eng:                                          # FP32 mode never picks a DMMA kernel
         assert eng.kernel_name().startswith("f32_")
+
+
+def test_no_device_memory_leak_over_handle_lifetimes(ude):
+    """create -> evaluate (loss+grad, forward, Adam, UKF with its auxiliary handle, forecast chain) -> destroy, many times: the
+    free device memory reported by the driver must come back."""
+    import torch
+    prob, theta = cases.make_case("node_d4x1", "multi_shoot", 0, hidden=32, lengths=(9, 4, 12, 7, 3, 10))
+    sprob, stheta = cases.make_case("node_d2", "cond_lik", 0, hidden=5, lengths=(7, 4))
+
+    def cycle():
+        with ude.Engine(prob) as eng:
+            eng.loss_grad(theta); eng.forward(theta); eng.adam(theta, 1e-3, 3)
+        with ude.Engine(sprob) as eng:
+            eng.ukf_loss_grad(stheta, 0.3 * np.eye(2), 0.1 * np.eye(2), alpha=1.0)
+            eng.ukf_filter(stheta, 0.3 * np.eye(2), 0.1 * np.eye(2), alpha=1.0)
+
+    for _ in range(3):
+        cycle()
+    torch.cuda.synchronize()
+    free0 = torch.cuda.mem_get_info()[0]
+    for _ in range(40):
+        cycle()
+    torch.cuda.synchronize()
+    free1 = torch.cuda.mem_get_info()[0]
+    assert free0 - free1 < 64 * 2 ** 20, (free0, free1)      # the driver's own pools may keep a little
