@@ -454,7 +454,8 @@ def main():
                           "rk_steps_per_eval_per_gpu": steps_per_eval, "segments_per_gpu": prob.count_segments(),
                           "n_theta_per_gpu": n_theta, "loss_value": loss_val, "grad_l1": grad_l1,
                           "l2": "inputs+stash larger than L2 (theta, grad, data = %.0f MB per step)" % (3 * 8 * prob.d * prob.n_cols / 1e6),
-                          "parallelism": f"dp{world} by series, {prob.n_pm + 1} doubles exchanged per step: {exchange}" if world > 1 else "single GPU",
+                          "parallelism": ("single GPU" if world == 1 else (f"dp{world} by model, no exchange ({exchange})" if prob.n_models > 1 else
+                                          f"dp{world} by series, {prob.n_pm + 1} doubles exchanged per step: {exchange}")),
                           "cpu_affinity": numa},
                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
                "gpu_launches": eng.launches_per_eval() * args.steps, "clocks": clk, "other_configs": others}
