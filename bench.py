@@ -303,6 +303,7 @@ def main():
     # ---- device-resident timing -------------------------------------------------------------------------------
     clocks = ClockSampler(local)
     clocks.start()
+    barrier()          # ranks finish building their shards at different times; the fused exchange waits for peers (bounded)
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
@@ -331,6 +332,7 @@ def main():
         h_theta = torch.from_numpy(theta0).pin_memory()
         h_grad = torch.empty(n_theta, dtype=torch.float64).pin_memory()
         h_loss = torch.empty(prob.n_models, dtype=torch.float64).pin_memory()
+        barrier()
         for _ in range(3):
             eng.loss_grad_ptr(h_theta.data_ptr(), n_theta, h_loss.data_ptr(), h_grad.data_ptr())
         barrier()
