@@ -158,7 +158,7 @@ int ude_comm_init(ude_handle* h, const void* id_bytes, int32_t n_bytes, int32_t 
  *   2. the host exchanges the blobs (any transport; bench.py uses torch.distributed all_gather)
  *   3. every rank: ude_peer_attach(h, all_blobs, n_ranks, rank)   (all_blobs: n_ranks x 128 B in rank order)
  * Ranks are one process per GPU (CUDA IPC) or threads of one process with one GPU each.  Two ranks on the same GPU are
- * refused.  A rank that waits longer than UDE_PEER_TIMEOUT_MS (default 20000) for a peer returns NaN loss/gradient
+ * refused.  A rank that waits longer than UDE_PEER_TIMEOUT_MS (default 60000) for a peer returns NaN loss/gradient
  * (status UDE_NONFINITE) instead of hanging. */
 #define UDE_MAX_PEERS 16
 #define UDE_PEER_BLOB_BYTES 128

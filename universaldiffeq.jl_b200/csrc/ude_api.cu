@@ -698,7 +698,7 @@ int finalize_eval(ude_handle* h, const double* d_theta, double* d_loss, double* 
       T.status = T.epoch + h->x_blocks;
       T.stride = h->x_stride; T.n_ranks = h->x_ranks; T.rank = h->rank; T.n_blocks = h->x_blocks;
       const char* te = getenv("UDE_PEER_TIMEOUT_MS");
-      const unsigned long long tmo = (unsigned long long)(te ? atoll(te) : 20000) * 1000000ull;
+      const unsigned long long tmo = (unsigned long long)(te ? atoll(te) : 60000) * 1000000ull;
       ude_finalize_exchange<<<h->x_blocks, dim3(32, 8), 0, s>>>(h->d_block_part.p, grid, D.n_pm, n_shared, d_theta + pmb, D.off_w1, n_w1,
                                                                 D.off_w2, n_w2, h->d_reg_weight.p, want_grad ? d_grad + pmb : nullptr,
                                                                 d_loss, T, tmo);
