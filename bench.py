@@ -54,6 +54,8 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="series in the CPU-oracle sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--dense-e2e", action="store_true", help="e2e through dense copies of theta and gradient (no UDE_OPT_SPARSE_UHAT_IO)")
+    ap.add_argument("--total-series", type=int, default=0, help="N>1: series IN TOTAL of the strong-scaling C3 measurement (default 100000)")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the short C2/C4/C5 side measurements (N = 1 only)")
     return ap.parse_args()
 
@@ -177,6 +179,15 @@ def cpu_oracle_rate(ude, args, n_sample, threads, min_seconds=12.0, max_reps=400
     return steps * reps / el, prob, steps, reps, el
 
 
+def host_threads():
+    """Host threads the CPU arm may use: the affinity mask of this process.  torchrun exports OMP_NUM_THREADS=1 to every
+    rank, which must not shrink the reference arm to one core (the N>1 ratios compared N GPUs with ONE core)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path.  The reference is Julia and cannot run in this
     image (no julia binary, no depot, no network), so this arm times the CPU oracle port with all host threads."""
@@ -185,7 +196,7 @@ def run_reference(args):
         return
     import ude_b200 as ude
     from oracle import oracle
-    threads = oracle.max_threads()
+    threads = host_threads()
     # one "step" = one loss+grad of a bounded sample of the workload (sized for ~0.3 s of wall time per step)
     n_sample = args.cpu_sample or {"c2": 6000, "c3": 2500, "c3mse": 2500, "c4": 16, "c5": 6000}[args.config]
     prob, th, name = build_problem(ude, args, 0, n_override=n_sample)
@@ -202,6 +213,10 @@ def run_reference(args):
            "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": {"workload": name + " (bounded CPU sample)", "solver": args.solver, "substeps": args.substeps,
+                      "same_config": False,
+                      "sample": f"{prob.n_series} of the GPU arm's 100000 series per GPU: a RATE metric (steps/s), so the sample size does "
+                                f"not bias it; the arm runs on rank 0 only and does not grow with --gpus",
+                      "host_threads": threads, "omp_num_threads_env": os.environ.get("OMP_NUM_THREADS"),
                       "note": "Julia reference not runnable here (parity unpinned); CPU oracle port timed instead"},
            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -230,130 +245,200 @@ def emit(obj):
         sys.stdout.write(line.decode()); sys.stdout.flush()
 
 
+class Ctx:
+    """torch / distributed plumbing shared by every measurement of a run"""
+
+    def __init__(self, args):
+        import torch
+        import ude_b200 as ude
+        self.torch, self.ude, self.args = torch, ude, args
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a B200: the CUDA library is the only implementation (no CPU fallback)")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        self.numa = _bind_to_gpu_numa_node(self.local) if self.world > 1 else None
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=self.dev)
+            self.dist = dist
+        # a dedicated non-default stream: the C ABI treats a NULL stream as "the handle's own stream", and CUDA events
+        # only see the stream they are recorded on
+        self.tstream = torch.cuda.Stream(device=self.dev)
+        torch.cuda.set_stream(self.tstream)
+        self.stream = self.tstream.cuda_stream
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        if self.dist is not None:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def engine(self, prob, dtype=0):
+        """Engine for this rank's shard + the cross-rank exchange of [loss | shared process-model gradient] (single-model
+        problems only; folds x members shard by model and exchange nothing).  Collective: every rank calls it."""
+        torch, dist, ude, args = self.torch, self.dist, self.ude, self.args
+        eng = ude.Engine(prob, device=self.local, lanes_per_segment=args.lanes, hidden_per_lane=args.hpl, weights_in_smem=args.ws, dtype=dtype)
+        exchange = "none"
+        if self.world > 1 and prob.n_models > 1:
+            exchange = "none: the models (folds x members) are independent, ranks only own different ones"
+        elif self.world > 1:
+            if args.exchange == "peer":
+                # fused finalize + allreduce over peer memory: the ranks swap the IPC descriptions of their exchange buffers
+                mine = torch.frombuffer(bytearray(eng.peer_export(self.world)), dtype=torch.uint8).to(self.dev)
+                allb = [torch.zeros(128, dtype=torch.uint8, device=self.dev) for _ in range(self.world)]
+                dist.all_gather(allb, mine)
+                eng.peer_attach([b.cpu().numpy().tobytes() for b in allb], self.world, self.rank)
+                exchange = "fused finalize + peer-memory allreduce (ude_finalize_exchange)"
+            else:
+                idt = torch.zeros(128, dtype=torch.uint8, device=self.dev)
+                if self.rank == 0:
+                    idt.copy_(torch.frombuffer(bytearray(ude.get_unique_id()), dtype=torch.uint8))
+                dist.broadcast(idt, 0)
+                eng.comm_init(bytes(idt.cpu().numpy().tobytes()), self.world, self.rank)
+                exchange = "ncclAllReduce"
+            if self.rank != 0:   # the regulariser is a function of the shared parameters: count it once (rank 0)
+                prob.reg_weight = np.zeros_like(prob.reg_weight)
+                eng._check(eng.lib.ude_set_model_weights(eng.handle, prob.obs_scale.ctypes.data, prob.proc_scale.ctypes.data,
+                                                         prob.shoot_weight.ctypes.data, prob.reg_weight.ctypes.data))
+        return eng, exchange
+
+
+def time_resident(cx, eng, prob, theta0, steps, warmup, clocks=None):
+    """K evaluations with theta / loss / grad resident in HBM: CUDA events on the launching stream, barrier +
+    synchronize on both sides, max over ranks.  Returns a dict (ms_step, kernel_ms, loss, grad_l1, clocks)."""
+    torch = cx.torch
+    d_theta = torch.from_numpy(theta0).to(cx.dev)
+    d_grad = torch.empty(prob.n_theta, dtype=torch.float64, device=cx.dev)
+    d_loss = torch.empty(prob.n_models, dtype=torch.float64, device=cx.dev)
+
+    def step():
+        eng.loss_grad_device(d_theta.data_ptr(), d_loss.data_ptr(), d_grad.data_ptr(), cx.stream)
+
+    cx.barrier()     # ranks finish building their shards at different times; the fused exchange waits for peers (bounded)
+    for _ in range(max(warmup, 3)):
+        step()
+    cx.barrier()
+    c_first = clocks.mark() if clocks else 0
+    eng.profile_begin(steps)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    cx.barrier()
+    ms_total = e0.elapsed_time(e1)
+    kern_ms = eng.profile_read(steps)
+    clk = clocks.stop(c_first) if clocks else None
+    ms_step = cx.max_over_ranks(ms_total) / steps
+    out = {"ms_step": ms_step, "kernel_ms": float(np.mean(kern_ms)) if len(kern_ms) else None, "clocks": clk,
+           "loss": float(d_loss.sum().item()),
+           "grad_l1": float(d_grad.abs().sum().item())}    # cheap checksum: lets two builds of the kernel be compared at full size
+    del d_theta, d_grad, d_loss
+    return out
+
+
+def time_e2e(cx, eng, prob, theta0, steps, sparse=True):
+    """The same metric through the public host-buffer C-ABI call (ude_loss_grad): page-locked host theta in, loss + gradient
+    out, every step.  For the (multiple-)shooting losses UDE_OPT_SPARSE_UHAT_IO is on: only the block-start columns of uhat
+    are ever read / have a gradient (LFC.jl:281-296, :665-680), so the kernels fetch and store exactly those columns over PCIe
+    (zero-copy) and the caller's gradient buffer is zeroed ONCE, before the first call."""
+    torch = cx.torch
+    n = prob.n_theta
+    h_theta = torch.from_numpy(theta0).pin_memory()
+    h_grad = torch.zeros(n, dtype=torch.float64).pin_memory()
+    h_loss = torch.empty(prob.n_models, dtype=torch.float64).pin_memory()
+    if sparse:
+        eng.set_option(cx.ude.OPT_SPARSE_UHAT_IO, 1)
+    cx.barrier()
+    for _ in range(3):
+        eng.loss_grad_ptr(h_theta.data_ptr(), n, h_loss.data_ptr(), h_grad.data_ptr())
+    cx.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        eng.loss_grad_ptr(h_theta.data_ptr(), n, h_loss.data_ptr(), h_grad.data_ptr())
+    torch.cuda.synchronize()
+    el = cx.max_over_ranks(time.perf_counter() - t0)
+    h2d, d2h = eng.last_io_bytes()
+    if sparse:
+        eng.set_option(cx.ude.OPT_SPARSE_UHAT_IO, 0)
+    dense = h2d == 8 * n
+    return {"value": eng.steps_per_eval() * cx.world * steps / el, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "ms_per_step": 1e3 * el / steps,
+            "api": ("ude_loss_grad (page-locked host theta in, loss + gradient out; dense copies of theta and gradient)" if dense else
+                    "ude_loss_grad with UDE_OPT_SPARSE_UHAT_IO (page-locked host theta in, loss + gradient out; the block-start uhat "
+                    "columns are read / their gradient written zero-copy by the kernels, process model copied; gradient buffer "
+                    "zeroed once by the caller, structurally-zero entries never rewritten)"),
+            "loss_check": float(h_loss.sum().item()), "grad_l1_check": float(h_grad.abs().sum().item())}
+
+
+def side_config(cx, key, cfg, n_total, solver, dtype_k, steps=10, e2e=False):
+    """One of the other BASELINE configs at its BASELINE size, split evenly over the ranks (strong scaling: by series /
+    by (member, fold) / by segment), same protocol as the headline."""
+    args = cx.args
+    a2 = argparse.Namespace(**vars(args)); a2.config = cfg; a2.series = max(n_total // cx.world, 1); a2.solver = solver
+    p2, th2, nm2 = build_problem(cx.ude, a2, cx.rank)
+    eng, exch = cx.engine(p2, dtype=dtype_k)
+    try:
+        r = time_resident(cx, eng, p2, th2, steps, 3)
+        st = eng.steps_per_eval() * cx.world
+        fp = cx.fp64_peak
+        out = {"workload": nm2 + (f" -- BASELINE size split over {cx.world} GPUs" if cx.world > 1 else ""), "steps_per_s": st / (r["ms_step"] * 1e-3),
+               "ms_per_step": r["ms_step"], "kernel": eng.kernel_name(), "kernel_ms": r["kernel_ms"], "n_gpus": cx.world,
+               "fp64_frac": (st * p2.flops_per_step() / (r["ms_step"] * 1e-3) * 1e-12 / (fp * cx.world)) if dtype_k == 0 else None}
+        if e2e:
+            out["e2e"] = time_e2e(cx, eng, p2, th2, steps)
+        return out
+    finally:
+        cx.barrier()
+        eng.close()
+
+
 def main():
     args = parse()
     _quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
         return
-    import torch
-    import ude_b200 as ude
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a B200: the CUDA library is the only implementation (no CPU fallback)")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    numa = _bind_to_gpu_numa_node(local) if world > 1 else None
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+    cx = Ctx(args)
+    torch, ude, dist, world, rank, local = cx.torch, cx.ude, cx.dist, cx.world, cx.rank, cx.local
 
     prob, theta0, name = build_problem(ude, args, rank)
-    eng = ude.Engine(prob, device=local, lanes_per_segment=args.lanes, hidden_per_lane=args.hpl, weights_in_smem=args.ws,
-                     dtype=1 if args.dtype == "f32" else 0)
-    exchange = "none"
-    if world > 1 and prob.n_models > 1:
-        exchange = "none: the models (folds x members) are independent, ranks only own different ones"
-    elif world > 1:
-        if args.exchange == "peer":
-            # fused finalize + allreduce over peer memory: the ranks swap the IPC descriptions of their exchange buffers
-            mine = torch.frombuffer(bytearray(eng.peer_export(world)), dtype=torch.uint8).to(dev)
-            allb = [torch.zeros(128, dtype=torch.uint8, device=dev) for _ in range(world)]
-            dist.all_gather(allb, mine)
-            eng.peer_attach([b.cpu().numpy().tobytes() for b in allb], world, rank)
-            exchange = "fused finalize + peer-memory allreduce (ude_finalize_exchange)"
-        else:
-            idt = torch.zeros(128, dtype=torch.uint8, device=dev)
-            if rank == 0:
-                idt.copy_(torch.frombuffer(bytearray(ude.get_unique_id()), dtype=torch.uint8))
-            dist.broadcast(idt, 0)
-            eng.comm_init(bytes(idt.cpu().numpy().tobytes()), world, rank)
-            exchange = "ncclAllReduce"
-        if rank != 0:   # the regulariser is a function of the shared parameters: count it once (rank 0)
-            prob.reg_weight = np.zeros_like(prob.reg_weight)
-            eng._check(eng.lib.ude_set_model_weights(eng.handle, prob.obs_scale.ctypes.data, prob.proc_scale.ctypes.data,
-                                                     prob.shoot_weight.ctypes.data, prob.reg_weight.ctypes.data))
+    eng, exchange = cx.engine(prob, dtype=1 if args.dtype == "f32" else 0)
     steps_per_eval = eng.steps_per_eval()
     n_theta = prob.n_theta
-
-    d_theta = torch.from_numpy(theta0).to(dev)
-    d_grad = torch.empty(n_theta, dtype=torch.float64, device=dev)
-    d_loss = torch.empty(prob.n_models, dtype=torch.float64, device=dev)
-    # a dedicated non-default stream: the C ABI treats a NULL stream as "the handle's own stream", and CUDA events
-    # only see the stream they are recorded on
-    tstream = torch.cuda.Stream(device=dev)
-    torch.cuda.set_stream(tstream)
-    stream = tstream.cuda_stream
-
-    def step():
-        eng.loss_grad_device(d_theta.data_ptr(), d_loss.data_ptr(), d_grad.data_ptr(), stream)
-
-    def barrier():
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     fp64_peak = ude.measure_fp64_peak(local, f32=(args.dtype == "f32"))     # FP32 FMA peak in the optional FP32 mode
+    cx.fp64_peak = ude.measure_fp64_peak(local) if args.dtype == "f32" else fp64_peak
 
     # ---- device-resident timing -------------------------------------------------------------------------------
     clocks = ClockSampler(local)
     clocks.start()
-    barrier()          # ranks finish building their shards at different times; the fused exchange waits for peers (bounded)
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
-    c_first = clocks.mark()
-    eng.profile_begin(args.steps)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    barrier()
-    ms_total = e0.elapsed_time(e1)
-    kern_ms = eng.profile_read(args.steps)
-    clk = clocks.stop(c_first)
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = float(t.item()) / args.steps
+    res = time_resident(cx, eng, prob, theta0, args.steps, args.warmup, clocks)
+    ms_step, clk = res["ms_step"], res["clocks"]
     value = steps_per_eval * world / (ms_step * 1e-3)
-    loss_val = float(d_loss.sum().item())
-    grad_l1 = float(d_grad.abs().sum().item())          # cheap checksum: lets two builds of the kernel be compared at full size
+    loss_val, grad_l1 = res["loss"], res["grad_l1"]
 
     # ---- end-to-end through the public host-buffer call ----------------------------------------------------------
     e2e = None
     if not args.no_e2e:
-        h_theta = torch.from_numpy(theta0).pin_memory()
-        h_grad = torch.empty(n_theta, dtype=torch.float64).pin_memory()
-        h_loss = torch.empty(prob.n_models, dtype=torch.float64).pin_memory()
-        barrier()
-        for _ in range(3):
-            eng.loss_grad_ptr(h_theta.data_ptr(), n_theta, h_loss.data_ptr(), h_grad.data_ptr())
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            eng.loss_grad_ptr(h_theta.data_ptr(), n_theta, h_loss.data_ptr(), h_grad.data_ptr())
-        torch.cuda.synchronize()
-        el = time.perf_counter() - t0
-        te = torch.tensor([el], dtype=torch.float64, device=dev)
-        if dist is not None:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        el = float(te.item())
-        e2e = {"value": steps_per_eval * world * args.steps / el, "unit": UNIT, "h2d_bytes_per_step": 8 * n_theta,
-               "d2h_bytes_per_step": 8 * (n_theta + prob.n_models), "ms_per_step": 1e3 * el / args.steps,
-               "api": "ude_loss_grad (host pinned theta in, loss+grad out)", "loss_check": float(h_loss.sum().item())}
+        e2e = time_e2e(cx, eng, prob, theta0, args.steps, sparse=not args.dense_e2e)
+        if rank == 0 and world == 1 and not args.dense_e2e and e2e["h2d_bytes_per_step"] != 8 * n_theta:
+            d = time_e2e(cx, eng, prob, theta0, args.steps, sparse=False)      # context: the dense-copy path (round 1's e2e)
+            e2e["dense_copy_path"] = {k: d[k] for k in ("value", "h2d_bytes_per_step", "d2h_bytes_per_step", "ms_per_step")}
 
     # ---- CPU baseline (rank 0, N = 1 only) ------------------------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle import oracle
-        threads = oracle.max_threads()
+        threads = host_threads()
         n_sample = args.cpu_sample or {"c2": 6000, "c3": 2500, "c3mse": 2500, "c4": 16, "c5": 6000}[args.config]
         rate, sp, ssteps, reps, el = cpu_oracle_rate(ude, args, n_sample, threads)
         rate1 = cpu_oracle_rate(ude, args, max(n_sample // 8, 8), 1, min_seconds=4.0)[0] if threads > 1 else rate
@@ -361,36 +446,44 @@ def main():
                "sample": f"{sp.n_series} series = {ssteps} RK steps per evaluation x {reps} evaluations in {el:.1f} s "
                          f"(oracle/libude_oracle.so, OpenMP over series); Julia reference not runnable here"}
 
+    # ---- strong scaling of the configuration the north star names: C3 with 10^5 series IN TOTAL, sharded by series ----
+    strong = None
+    if args.config == "c3" and world > 1 and not args.no_other_configs:
+        try:
+            a2 = argparse.Namespace(**vars(args)); a2.series = max((args.total_series or 100_000) // world, 1)
+            p2, th2, nm2 = build_problem(ude, a2, rank)
+            e2, _ = cx.engine(p2)
+            k2 = max(args.steps, 50)
+            r2 = time_resident(cx, e2, p2, th2, k2, 5)
+            st2 = e2.steps_per_eval() * world
+            strong = {"scaling": "strong", "workload": f"C3, {a2.series * world} series x 30 pts IN TOTAL, {a2.series} per GPU (sharded by series)",
+                      "value": st2 / (r2["ms_step"] * 1e-3), "unit": UNIT, "ms_per_step": r2["ms_step"], "steps": k2,
+                      "segment_kernel_ms": r2["kernel_ms"],
+                      "outside_the_segment_kernel_ms": (r2["ms_step"] - r2["kernel_ms"]) if r2["kernel_ms"] else None,
+                      "limiter": "per step: one persistent segment-kernel launch + the fused finalize/exchange launch; what does not shrink with "
+                                 "1/N is launch latency, the block-partial reduction + peer exchange (~10-20 us) and the tail of the persistent "
+                                 "grid (tasks per warp no longer a large integer)",
+                      "e2e": None if args.no_e2e else time_e2e(cx, e2, p2, th2, k2)}
+            cx.barrier()
+            e2.close()
+        except Exception as ex:
+            strong = {"error": str(ex)[:300]}
+
     # ---- the other BASELINE configs, same protocol (resident inputs, CUDA events), a few steps each: context, not the headline
     others = None
-    if rank == 0 and world == 1 and args.config == "c3" and not args.no_other_configs:
+    if args.config == "c3" and not args.no_other_configs:
         others = {}
-        for key, cfg, n, solver2, dt2k in (("c2", "c2", 10_000, args.solver, 0), ("c4", "c4", 1000, args.solver, 0),
-                                           ("c5", "c5", 1_000_000, args.solver, 0), ("c3_tsit5", "c3", 100_000, "tsit5", 0),
-                                           ("c3_f32_mode", "c3", 100_000, args.solver, 1)):
+        todo = [("c2", "c2", 10_000, args.solver, 0), ("c4", "c4", 1000, args.solver, 0), ("c5", "c5", 1_000_000, args.solver, 0),
+                ("c5_f32_mode", "c5", 1_000_000, args.solver, 1)]
+        if world == 1:
+            todo += [("c3_tsit5", "c3", 100_000, "tsit5", 0), ("c3_f32_mode", "c3", 100_000, args.solver, 1)]
+        for key, cfg, n, solver2, dt2k in todo:
             try:
-                a2 = argparse.Namespace(**vars(args)); a2.config = cfg; a2.series = n; a2.solver = solver2
-                p2, th2, nm2 = build_problem(ude, a2, 0)
-                cfg = key
-                with ude.Engine(p2, device=local, dtype=dt2k) as e2:
-                    dt2 = torch.from_numpy(th2).to(dev); dg2 = torch.empty_like(dt2)
-                    dl2 = torch.empty(p2.n_models, dtype=torch.float64, device=dev)
-                    for _ in range(3):
-                        e2.loss_grad_device(dt2.data_ptr(), dl2.data_ptr(), dg2.data_ptr(), stream)
-                    torch.cuda.synchronize()
-                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    a.record()
-                    for _ in range(10):
-                        e2.loss_grad_device(dt2.data_ptr(), dl2.data_ptr(), dg2.data_ptr(), stream)
-                    b.record(); torch.cuda.synchronize()
-                    ms2 = a.elapsed_time(b) / 10
-                    st2 = e2.steps_per_eval()
-                    others[cfg] = {"workload": nm2, "steps_per_s": st2 / (ms2 * 1e-3), "ms_per_step": ms2, "kernel": e2.kernel_name(),
-                                   "fp64_frac": (st2 * p2.flops_per_step() / (ms2 * 1e-3) * 1e-12 / fp64_peak) if dt2k == 0 else None}
-                del dt2, dg2, dl2
+                others[key] = side_config(cx, key, cfg, n, solver2, dt2k, e2e=(key in ("c2", "c4") and not args.no_e2e))
             except Exception as ex:        # a side measurement must never take the headline down
-                others[cfg] = {"error": str(ex)[:200]}
-
+                others[key] = {"error": str(ex)[:200]}
+                cx.barrier()
+    if others is not None and rank == 0 and world == 1:
         try:       # UKF marginal likelihood on the C1 tutorial model (host buffers in and out, loss + gradient)
             p3, th3 = ude.synthetic.config_c1()
             with ude.Engine(p3, device=local) as e3:
@@ -419,7 +512,7 @@ def main():
             others["c1_train_500_adam_iterations"] = {"error": str(ex)[:200]}
 
     if rank == 0:
-        kms = float(np.mean(kern_ms)) if len(kern_ms) else None
+        kms = res["kernel_ms"]
         flops_step = prob.flops_per_step()
         achieved = steps_per_eval * flops_step / (kms * 1e-3) * 1e-12 if kms else None
         traffic = None      # dram__bytes_read+write of the dominant kernel per launch, from the committed ncu capture (per RK step x steps)
@@ -458,8 +551,8 @@ def main():
                           "l2": "inputs+stash larger than L2 (theta, grad, data = %.0f MB per step)" % (3 * 8 * prob.d * prob.n_cols / 1e6),
                           "parallelism": ("single GPU" if world == 1 else (f"dp{world} by model, no exchange ({exchange})" if prob.n_models > 1 else
                                           f"dp{world} by series, {prob.n_pm + 1} doubles exchanged per step: {exchange}")),
-                          "cpu_affinity": numa},
-               "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+                          "cpu_affinity": cx.numa},
+               "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "strong_scaling": strong,
                "gpu_launches": eng.launches_per_eval() * args.steps, "clocks": clk, "other_configs": others}
         emit(out)
     eng.close()

@@ -38,7 +38,8 @@ typedef enum ude_status {
   UDE_ERR_NO_DEVICE = -4,    /* no usable sm_100 device: there is NO CPU fallback */
   UDE_ERR_STATE = -5,        /* call order (e.g. loss_grad before set_data) */
   UDE_ERR_NCCL = -6,
-  UDE_NONFINITE = -7         /* loss or gradient is not finite; outputs are still written (loss = Inf/NaN as computed) */
+  UDE_NONFINITE = -7         /* the LOSS is not finite (checked on the host after the call; the gradient is not scanned);
+                                outputs are still written (loss = Inf/NaN as computed) */
 } ude_status;
 
 /* solver: fixed-step explicit RK replacing OrdinaryDiffEq.solve(..., Tsit5(), abstol=1e-6, reltol=1e-6)
@@ -120,6 +121,23 @@ int ude_set_targets(ude_handle* h, const double* smoothed_states, const double* 
 /* skip_mask[c] != 0: the process term of the interval ENDING at column c is left out (t_skip, LFC.jl:82) */
 int ude_set_skip(ude_handle* h, const uint8_t* skip_mask);
 
+/* Handle options (value 0 = off, the default).
+ *   UDE_OPT_SPARSE_UHAT_IO  multiple-shooting and shooting losses read only the BLOCK-START columns of uhat, and only those
+ *     columns have a non-zero gradient (LFC.jl:281-296, :665-680: `uhats[:,t]` at block starts; :196-232: `uhat[:,1]`).
+ *     With this option ude_loss_grad, when theta and grad are page-locked host buffers (cudaHostAlloc / cudaHostRegister),
+ *     lets the kernels read those columns of theta and write those columns of grad directly over PCIe (zero-copy): only
+ *     8*(d*n_blocks + n_pm) bytes move each way instead of 8*n_theta.  CONTRACT: the structurally-zero entries of grad are
+ *     NOT written -- the caller zeroes the gradient buffer once and reuses it (every entry the library does not write stays
+ *     exactly 0).  Ignored (dense copies, every entry written) for other losses, many-model handles or pageable buffers.
+ *   UDE_OPT_UKF_CAUSAL_INTERVAL  the reference's UKF hands (times[t], dt) to predict, i.e. it integrates the sigma points
+ *     over [times[t], times[t] + dt] -- the window starts at the END of the observation interval
+ *     (src/UnscentedKalmanFilter.jl:67, :83, :93, :121).  Default 0 reproduces that; 1 uses [times[t-1], times[t]].
+ *     Identical for autonomous right-hand sides, different with covariates or a time input. */
+enum { UDE_OPT_SPARSE_UHAT_IO = 1, UDE_OPT_UKF_CAUSAL_INTERVAL = 2 };
+int ude_set_option(ude_handle* h, int32_t option, int64_t value);
+/* bytes the last ude_loss_grad call moved host->device and device->host (copies + zero-copy reads/writes) */
+int ude_last_io_bytes(const ude_handle* h, int64_t* h2d_bytes, int64_t* d2h_bytes);
+
 int64_t ude_n_theta(const ude_handle* h);
 int64_t ude_n_models(const ude_handle* h);
 /* RK steps one loss evaluation integrates (unit of the throughput metric) and kernels launched per call */
@@ -158,8 +176,11 @@ int ude_comm_init(ude_handle* h, const void* id_bytes, int32_t n_bytes, int32_t 
  *   2. the host exchanges the blobs (any transport; bench.py uses torch.distributed all_gather)
  *   3. every rank: ude_peer_attach(h, all_blobs, n_ranks, rank)   (all_blobs: n_ranks x 128 B in rank order)
  * Ranks are one process per GPU (CUDA IPC) or threads of one process with one GPU each.  Two ranks on the same GPU are
- * refused.  A rank that waits longer than UDE_PEER_TIMEOUT_MS (default 60000) for a peer returns NaN loss/gradient
- * (status UDE_NONFINITE) instead of hanging. */
+ * refused.  From here on EVERY loss evaluation on the handle (ude_loss_grad*, ude_adam, loss-only calls) is a collective:
+ * all ranks must make the same sequence of calls.  ude_forward is not (it needs no loss) and may be called by one rank
+ * alone.  A rank that waits longer than UDE_PEER_TIMEOUT_MS (default 60000) for a peer returns NaN loss/gradient (status
+ * UDE_NONFINITE) instead of hanging; that state is STICKY -- the ranks' call counters have diverged, every later evaluation
+ * on the handle returns NaN too: destroy the handles and attach again. */
 #define UDE_MAX_PEERS 16
 #define UDE_PEER_BLOB_BYTES 128
 int ude_peer_export(ude_handle* h, int32_t n_ranks, void* blob, int32_t n_bytes);
@@ -167,7 +188,14 @@ int ude_peer_attach(ude_handle* h, const void* blobs, int32_t n_ranks, int32_t r
 
 /* Device-resident Adam (Optimisers.jl semantics: beta=(0.9,0.999), eps=1e-8, bias-corrected), SURVEY.md 8f row 1.
  * Runs n_iter iterations of loss_grad + update without leaving the device; theta is read and written back.
- * loss_trace (n_iter doubles per model, may be NULL) receives the loss before each update. */
+ * loss_trace (n_iter doubles per model, may be NULL) receives the loss before each update.
+ * RETURNED ITERATE: theta after the LAST update (iteration n_iter), not the best-seen one.  The reference's
+ * `Optimization.solve(prob, Adam(eta); maxiters)` (src/Optimizers.jl:500, :685) goes through OptimizationOptimisers, which
+ * in the versions the compat range allows (0.1 - 0.3, Project.toml:61) returns the iterate with the lowest objective seen
+ * when the iteration limit is hit; that is third-party behaviour that cannot be checked here (no Julia).  A caller that
+ * wants it takes argmin(loss_trace) and re-runs that many iterations (the iterates are deterministic), as
+ * training.train_(..., return_best=True) does.  Returns UDE_NONFINITE (theta still written) when the loss of the last
+ * iteration is not finite. */
 int ude_adam(ude_handle* h, double* theta, int64_t n_theta, double step_size, int32_t n_iter, double* loss_trace);
 /* 1 if the last ude_adam call replayed a captured CUDA graph (one iteration = memset + segment kernel + finalize + update),
  * which is what makes small, launch-bound models train at kernel speed; UDE_ADAM_GRAPH=0 disables it. */

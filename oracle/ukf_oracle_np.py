@@ -60,8 +60,15 @@ def ukf_update(y, x, Px, f, Pnu, Peta, L, alpha, beta, kappa):
     return xn, Pn, ll
 
 
-def filter_series(p, pm, s, Pnu, Peta, alpha, beta, kappa, dtype=float):
-    """(sum of log-likelihood terms, filtered states d x n, covariances d x d x n) of series s."""
+def filter_series(p, pm, s, Pnu, Peta, alpha, beta, kappa, dtype=float, causal=False):
+    """(sum of log-likelihood terms, filtered states d x n, covariances d x d x n) of series s.
+
+    Prediction window of filter step t (1-based t = 2..T in the reference).  ukf_likelihood / ukf_smoothing call
+    `ukf_update(y[:,t], x, Px, times[t], dt, ...)` with dt = times[t] - times[t-1] (src/UnscentedKalmanFilter.jl:67, :83) and
+    ukf_update hands (t, dt) to predict (:93, multi :121): the sigma points are integrated over [times[t], times[t] + dt],
+    i.e. the window STARTS at the END of the observation interval.  For an autonomous right-hand side this equals the causal
+    window [times[t-1], times[t]]; with covariates or a time input it does not.  causal=False (default) reproduces the
+    reference; causal=True is the window one would expect, kept as an opt-in (UDE_OPT_UKF_CAUSAL_INTERVAL)."""
     d = p.d
     c0, n = int(p.starts[s]), int(p.lengths[s])
     y = p.data[:, c0:c0 + n]
@@ -72,14 +79,15 @@ def filter_series(p, pm, s, Pnu, Peta, alpha, beta, kappa, dtype=float):
     xs[:, 0] = x
     ll = 0
     for t in range(1, n):
-        f = lambda u, t0=tt[t - 1], t1=tt[t]: onp.flow(p, pm, s, s, u, t0, t1)      # noqa: E731
+        ta, tb = (tt[t - 1], tt[t]) if causal else (tt[t], tt[t] + (tt[t] - tt[t - 1]))
+        f = lambda u, t0=ta, t1=tb: onp.flow(p, pm, s, s, u, t0, t1)      # noqa: E731
         x, Px, l1 = ukf_update(y[:, t], x, Px, f, Pnu, Peta, d, alpha, beta, kappa)
         ll = ll + l1
         xs[:, t] = x; Ps[:, :, t] = Px
     return ll, xs, Ps
 
 
-def loss(p, theta, pnu, Peta, alpha=1e-3, beta=2.0, kappa=0.0, reg_weight=0.0, reg_mult=1.0):
+def loss(p, theta, pnu, Peta, alpha=1e-3, beta=2.0, kappa=0.0, reg_weight=0.0, reg_mult=1.0, causal=False):
     """-sum_series loglik + reg_mult * reg_weight * (|W1|^2 + |W2|^2).  theta = [uhat | process_model] of a single-model
     problem (uhat does not enter); pnu = d x d factor with P_nu = pnu pnu^T.  reg_mult = 1 (UDE) or n_series + 1 (MultiUDE)."""
     theta = np.asarray(theta); pnu = np.asarray(pnu)
@@ -90,7 +98,7 @@ def loss(p, theta, pnu, Peta, alpha=1e-3, beta=2.0, kappa=0.0, reg_weight=0.0, r
     Pnu = Lf @ Lf.T
     tot = 0
     for s in range(p.n_series):
-        tot = tot - filter_series(p, pm, s, Pnu, Peta, alpha, beta, kappa, dtype)[0]
+        tot = tot - filter_series(p, pm, s, Pnu, Peta, alpha, beta, kappa, dtype, causal=causal)[0]
     w1 = pm[p.off_w1:p.off_w1 + p.nn_hidden * p.nn_in]; w2 = pm[p.off_w2:p.off_w2 + p.nn_out * p.nn_hidden]
     return tot + reg_mult * reg_weight * (np.sum(w1 * w1) + np.sum(w2 * w2))
 

@@ -123,3 +123,38 @@ def make_case(rhs="node_d2", loss="cond_lik", solver=P.RK4, hidden=10, lengths=(
 def relerr(a, b):
     a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
     return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+def leaf_groups(prob, m=0):
+    """(name, lo, hi) index ranges of model m's gradient leaves inside theta: uhat, W1, b1, W2, b2, each scalar, the
+    per-series vector (SURVEY.md App. B layout)."""
+    b0 = int(prob.theta_base[m]); pb = prob.pm_base(m)
+    H, din, dout = prob.nn_hidden, prob.nn_in, prob.nn_out
+    g = [("uhat", b0, pb), ("W1", pb + prob.off_w1, pb + prob.off_w1 + H * din), ("b1", pb + prob.off_b1, pb + prob.off_b1 + H),
+         ("W2", pb + prob.off_w2, pb + prob.off_w2 + dout * H), ("b2", pb + prob.off_b2, pb + prob.off_b2 + dout)]
+    for k, o in enumerate(prob.off_scalar):
+        g.append((f"scalar{k}", pb + o, pb + o + 1))
+    if prob.has_series_param:
+        g.append(("series_param", pb + prob.off_series_param, pb + prob.n_pm))
+    return g
+
+
+def grad_mismatch(prob, g, g_ref, rtol=1e-10, floor=1e-3):
+    """Element-wise gradient check per leaf group: every entry must satisfy
+    |g - g_ref| <= rtol |g_ref| + rtol * floor * max|g_ref over its leaf group|.  A norm-wise check over the whole vector
+    lets a small-magnitude leaf (b2, scalar parameters) be 100% wrong; this does not.  Returns the worst violation as
+    (ratio, model, leaf) with ratio <= 1 meaning pass."""
+    worst = (0.0, -1, "")
+    for m in range(prob.n_models):
+        for name, lo, hi in leaf_groups(prob, m):
+            if hi <= lo:
+                continue
+            a = np.asarray(g[lo:hi], dtype=np.float64); b = np.asarray(g_ref[lo:hi], dtype=np.float64)
+            tol = rtol * np.abs(b) + rtol * floor * max(float(np.max(np.abs(b))), 1e-300)
+            r = float(np.max(np.abs(a - b) / tol))
+            if not np.isfinite(r):
+                r = np.inf
+            if r > worst[0]:
+                worst = (r, m, name)
+    return worst
+

@@ -25,10 +25,10 @@ def _check(prob, theta, ude, **kw):
     assert np.all(np.isfinite(L)) and np.all(np.isfinite(g))
     assert np.max(np.abs(L - L_ref) / np.abs(L_ref)) < TOL, (L, L_ref)
     assert np.max(np.abs(L2 - L_ref) / np.abs(L_ref)) < TOL, (L2, L_ref)
-    # gradient: norm-wise per model block (entries that are structurally zero must be exactly zero)
-    for m in range(prob.n_models):
-        lo = int(prob.theta_base[m]); hi = int(prob.theta_base[m + 1]) if m + 1 < prob.n_models else prob.n_theta
-        assert cases.relerr(g[lo:hi], g_ref[lo:hi]) < TOL, (m, cases.relerr(g[lo:hi], g_ref[lo:hi]))
+    # gradient: element-wise per leaf group (uhat, W1, b1, W2, b2, scalars, per-series vector) -- a norm over the whole
+    # vector would let a small leaf be wrong; entries that are structurally zero must be exactly zero
+    worst = cases.grad_mismatch(prob, g, g_ref, rtol=TOL)
+    assert worst[0] <= 1.0, worst
     assert np.all(g[g_ref == 0.0] == 0.0)
 
 
@@ -71,6 +71,45 @@ def test_parity_group_shapes_c3(ude, g_hpl, hidden, ws, loss):
         _check(prob, theta, ude, lanes_per_segment=g_hpl[0], hidden_per_lane=g_hpl[1], weights_in_smem=ws)
 
 
+@pytest.mark.parametrize("kernel", ["mma2_h32_nt2", "mma2_h32_nt1"])
+@pytest.mark.parametrize("loss", ["multi_shoot", "multi_shoot_preroll", "shoot_theta", "shoot_data", "cond_lik", "mse"])
+def test_parity_mma2_family(ude, kernel, loss, monkeypatch):
+    """Round-2 tensor-core kernels (ude_kernel_mma2.cuh): 8 / 16 segments per warp, per-interval register prefetch of
+    times / data / covariate knots, knot-by-knot covariate advance.  Ragged series, 1-point series, trailing one-point
+    blocks, covariate knots that do not cover the span (flat extrapolation both sides), hidden widths below the padded 32."""
+    monkeypatch.setenv("UDE_KERNEL", kernel)
+    for solver in (0, 1):
+        for hidden, lengths, substeps in ((32, (30, 30, 7, 12, 1, 30, 26, 3, 30, 30, 11, 2, 30, 17, 30, 30, 5, 30), 4),
+                                          (27, (9, 1, 2, 64, 3), 3), (8, (16,) * 5 + (1,) * 3 + (6,) * 30, 1)):
+            prob, theta = cases.make_case("node_d4x1", loss, solver, hidden=hidden, lengths=lengths, substeps=substeps,
+                                          skip=(loss in ("cond_lik", "mse")))
+            with ude.Engine(prob) as eng:
+                assert kernel in eng.kernel_name()
+            _check(prob, theta, ude)
+
+
+@pytest.mark.parametrize("kernel", ["mma2_h32_nt2", "mma2_h32_nt1"])
+def test_parity_mma2_dense_knots_and_forward(ude, kernel, monkeypatch):
+    """More covariate knots than RK stages per interval (several knot crossings inside one stage advance) and the
+    forward-only trajectories of the new kernels."""
+    monkeypatch.setenv("UDE_KERNEL", kernel)
+    rng = np.random.default_rng(5)
+    for loss in ("multi_shoot", "shoot_theta", "cond_lik"):
+        prob, theta = cases.make_case("node_d4x1", loss, 0, hidden=32, lengths=(12, 7, 30, 1, 9), substeps=2, skip=False)
+        off, kt, kx = [0], [], []
+        for s in range(prob.n_series):
+            t = prob.times[prob.starts[s]:prob.starts[s] + prob.lengths[s]]
+            k = np.sort(rng.uniform(t[0] - 0.05, t[-1] + 0.05, size=40 * max(len(t), 2)))
+            kt.append(k); kx.append(rng.normal(size=k.shape[0])); off.append(off[-1] + k.shape[0])
+        prob.knot_off = np.array(off); prob.knot_t = np.concatenate(kt); prob.knot_x = np.concatenate(kx)
+        prob.finalize()
+        _check(prob, theta, ude)
+        ref = oracle.forward(prob, theta)
+        with ude.Engine(prob) as eng:
+            out = eng.forward(theta)
+        assert cases.relerr(out, ref) < TOL, loss
+
+
 @pytest.mark.parametrize("kernel", ["mma", "g32h4"])
 def test_parity_wide_node(ude, kernel, monkeypatch):
     """d = 8, hidden 128 (BASELINE config C5): the DMMA kernel with the hidden layer split over four warps, and the
@@ -96,6 +135,39 @@ def test_parity_baseline_configs_reduced(ude, name, kw):
         rng = np.random.default_rng(7)
         theta = theta + 0.01 * rng.normal(size=theta.shape)
         _check(prob, theta, ude)
+
+
+def test_sparse_uhat_io_zero_copy(ude):
+    """UDE_OPT_SPARSE_UHAT_IO: with page-locked host buffers the kernels read the block-start columns of uhat from, and
+    write their gradient to, the caller's memory; nothing else of uhat crosses PCIe and the structurally-zero entries of
+    the (pre-zeroed) gradient buffer are left alone.  Dense fallbacks: state-space losses, pageable buffers."""
+    import torch
+    for rhs, hidden in (("node_d4x1", 32), ("node_d2", 10), ("lv_ude", 10)):
+        for loss in ("multi_shoot", "multi_shoot_preroll", "shoot_theta", "shoot_data", "cond_lik"):
+            prob, theta = cases.make_case(rhs, loss, 0, hidden=hidden, lengths=(30, 7, 12, 1, 26, 3, 5, 6, 11))
+            L_ref, g_ref = oracle.loss_grad(prob, theta)
+            n = prob.n_theta
+            h_theta = torch.from_numpy(theta.copy()).pin_memory()
+            h_grad = torch.zeros(n, dtype=torch.float64).pin_memory()
+            h_loss = torch.zeros(1, dtype=torch.float64).pin_memory()
+            with ude.Engine(prob) as eng:
+                eng.set_option(ude.OPT_SPARSE_UHAT_IO, 1)
+                for rep in range(2):        # the second call reuses the buffer: entries the library does not write stay 0
+                    eng.loss_grad_ptr(h_theta.data_ptr(), n, h_loss.data_ptr(), h_grad.data_ptr())
+                    g = h_grad.numpy()
+                    assert abs(h_loss[0].item() - L_ref[0]) < TOL * abs(L_ref[0]), (rhs, loss)
+                    assert cases.grad_mismatch(prob, g, g_ref, rtol=TOL)[0] <= 1.0, (rhs, loss, rep)
+                    assert np.all(g[g_ref == 0.0] == 0.0)
+                h2d, d2h = eng.last_io_bytes()
+                if loss == "cond_lik":
+                    assert h2d == 8 * n
+                else:
+                    cols = 0 if loss == "shoot_data" else prob.count_segments()
+                    assert h2d == 8 * (prob.d * cols + prob.n_pm) and d2h == h2d + 8, (rhs, loss, h2d)
+                # pageable buffers: same option, dense copies, same numbers
+                L, g2 = eng.loss_grad(theta)
+                assert cases.grad_mismatch(prob, g2, g_ref, rtol=TOL)[0] <= 1.0
+                assert eng.last_io_bytes()[0] == 8 * n
 
 
 def test_forward_states(ude):

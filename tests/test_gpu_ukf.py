@@ -40,6 +40,35 @@ def test_ukf_parity_alpha_one(ude, rhs, hidden, lengths, solver):
     assert cases.relerr(gF.reshape(-1, order="F"), g_F) < 1e-10
 
 
+@pytest.mark.parametrize("rhs,hidden,lengths", [("node_time_d3", 5, (6, 3)), ("node_d4x1", 6, (5, 4)), ("node_d2", 5, (6, 2))])
+def test_ukf_prediction_window(ude, rhs, hidden, lengths):
+    """Default = the reference's window [times[t], times[t] + dt] (src/UnscentedKalmanFilter.jl:83, :93); the causal window
+    [times[t-1], times[t]] is an option.  Both against the twin; they differ unless the right-hand side is autonomous.  The
+    option change and a second ude_set_data on the same handle must rebuild the cached filter plan."""
+    prob, theta, F, Peta = _setup(rhs, hidden, lengths, 0)
+    n_u = prob.d * prob.n_cols
+    out = {}
+    with ude.Engine(prob) as eng:
+        for causal in (False, True, False):
+            ref = ukf.loss(prob, theta, F, Peta, alpha=1.0, causal=causal)
+            g_pm, g_F = ukf.complex_step_grad(prob, theta, F, Peta, alpha=1.0, causal=causal)
+            L, g, gF = eng.ukf_loss_grad(theta, F, Peta, alpha=1.0, causal=causal)
+            assert abs(L - ref) < 1e-10 * abs(ref), (rhs, causal)
+            assert cases.relerr(g[n_u:], g_pm) < 1e-10 and cases.relerr(gF.reshape(-1, order="F"), g_F) < 1e-10
+            out[causal] = L
+        assert (abs(out[True] - out[False]) < 1e-12 * abs(out[True])) == (rhs == "node_d2")
+        # new data on the same handle (more series, other lengths): the plan of the first problem must not be replayed
+        prob2, theta2, F2, Peta2 = _setup(rhs, hidden, tuple(lengths) + (7, 2), 0, seed=3)
+        eng._check(eng.lib.ude_set_data(eng.handle, prob2.n_series, prob2.starts.ctypes.data, prob2.lengths.ctypes.data, None,
+                                        prob2.n_cols, prob2.times.ctypes.data, prob2.data.ctypes.data))
+        if prob2.n_cov:
+            eng._check(eng.lib.ude_set_covariates(eng.handle, prob2.knot_off.ctypes.data, prob2.knot_t.ctypes.data, prob2.knot_x.ctypes.data))
+        eng.problem = prob2
+        ref2 = ukf.loss(prob2, theta2, F2, Peta2, alpha=1.0)
+        L2, _, _ = eng.ukf_loss_grad(theta2, F2, Peta2, alpha=1.0)
+        assert abs(L2 - ref2) < 1e-10 * abs(ref2)
+
+
 def test_ukf_reference_default_alpha(ude):
     prob, theta, F, Peta = _setup("node_d2", 5, (8, 5), 0)
     ref = ukf.loss(prob, theta, F, Peta, alpha=1e-3)

@@ -151,3 +151,30 @@ def test_ukf_twin_matches_committed_fixtures():
         if rhs == "node_d2" and len(lengths) == 1:          # one gradient re-derived here; the rest are checked on the GPU
             g_pm, g_F = ukf.complex_step_grad(prob, theta, F, Peta, alpha=alpha, reg_weight=1e-3, reg_mult=2.0)
             assert cases.relerr(g_pm, gold[key + "|g_pm"]) < 1e-12 and cases.relerr(g_F, gold[key + "|g_F"]) < 1e-12
+
+
+def test_prediction_window_is_the_reference_one():
+    """ukf_likelihood passes times[t] -- the END of the observation interval -- as the start time of predict
+    (src/UnscentedKalmanFilter.jl:83, :93): the sigma points are integrated over [times[t], times[t] + dt].  The twin does
+    the same by default; `causal=True` is the window [times[t-1], times[t]].  Equal for an autonomous right-hand side,
+    different with a time input or covariates -- and the default must be the reference's window, written out here."""
+    for rhs, autonomous in (("node_d2", True), ("node_time_d3", False), ("node_d4x1", False)):
+        prob, theta, Lf, Peta = _case(rhs, hidden=4, lengths=(5, 3))
+        a = ukf.loss(prob, theta, Lf, Peta, alpha=1.0)
+        b = ukf.loss(prob, theta, Lf, Peta, alpha=1.0, causal=True)
+        assert (abs(a - b) < 1e-13 * abs(a)) == autonomous, (rhs, a, b)
+        # the default, step by step, with the window written as the reference computes it
+        d = prob.d
+        pm = theta[d * prob.n_cols: d * prob.n_cols + prob.n_pm]
+        tot = 0.0
+        for s in range(prob.n_series):
+            c0, n = int(prob.starts[s]), int(prob.lengths[s])
+            y, tt = prob.data[:, c0:c0 + n], prob.times[c0:c0 + n]
+            x, P = y[:, 0].copy(), np.asarray(Peta, dtype=float)
+            for t in range(1, n):
+                dt = tt[t] - tt[t - 1]
+                f = lambda u, t0=tt[t], t1=tt[t] + dt: onp.flow(prob, pm, s, s, u, t0, t1)      # noqa: E731
+                x, P, ll = ukf.ukf_update(y[:, t], x, P, f, Lf @ Lf.T, Peta, d, 1.0, 2.0, 0.0)
+                tot -= ll
+        assert abs(tot - a) < 1e-13 * abs(a), rhs
+

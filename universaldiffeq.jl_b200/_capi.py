@@ -25,7 +25,7 @@ STATUS = {0: "UDE_OK", -1: "UDE_ERR_INVALID", -2: "UDE_ERR_UNSUPPORTED", -3: "UD
 UDE_NONFINITE = -7
 
 EXPORTS = ["ude_abi_version", "ude_device_count", "ude_create", "ude_destroy", "ude_last_error", "ude_set_data",
-           "ude_set_model_weights", "ude_set_covariates", "ude_set_targets", "ude_set_skip", "ude_n_theta",
+           "ude_set_model_weights", "ude_set_covariates", "ude_set_targets", "ude_set_skip", "ude_set_option", "ude_last_io_bytes", "ude_n_theta",
            "ude_n_models", "ude_steps_per_eval", "ude_kernel_name", "ude_launches_per_eval", "ude_loss_grad", "ude_loss_grad_device",
            "ude_forward", "ude_comm_unique_id", "ude_comm_init", "ude_adam", "ude_adam_used_graph", "ude_profile_begin", "ude_profile_read",
            "ude_measure_fp64_peak", "ude_measure_fp32_peak", "ude_peer_export", "ude_peer_attach",
@@ -133,6 +133,10 @@ def load_library():
     lib.ude_peer_attach.argtypes = [vp, vp, i32, i32]
     lib.ude_measure_fp32_peak.restype = C.c_int
     lib.ude_measure_fp32_peak.argtypes = [i32, C.POINTER(C.c_double)]
+    lib.ude_set_option.restype = C.c_int
+    lib.ude_set_option.argtypes = [vp, i32, i64]
+    lib.ude_last_io_bytes.restype = C.c_int
+    lib.ude_last_io_bytes.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     if lib.ude_abi_version() != ABI_VERSION:
         raise RuntimeError("libude_cuda ABI version mismatch")
     _LIB = lib
@@ -191,6 +195,10 @@ def measure_fp64_peak(device: int = 0, f32: bool = False) -> float:
     if rc != UDE_OK:
         raise UdeError(rc, lib.ude_last_error(None).decode())
     return float(out.value)
+
+
+OPT_SPARSE_UHAT_IO = 1
+OPT_UKF_CAUSAL_INTERVAL = 2
 
 
 class Engine:
@@ -298,6 +306,17 @@ class Engine:
         self._check(self.lib.ude_adam(self.handle, _ptr(theta), theta.shape[0], float(step_size), int(n_iter), _ptr(trace)))
         return theta, trace[:n_iter]
 
+    def set_option(self, option: int, value: int = 1):
+        """ude_set_option; OPT_SPARSE_UHAT_IO = 1: zero-copy block-start columns for (multiple-)shooting losses with
+        page-locked host buffers -- the caller zeroes the gradient buffer once (include/ude_cuda.h)."""
+        self._check(self.lib.ude_set_option(self.handle, int(option), int(value)))
+
+    def last_io_bytes(self):
+        """(host->device, device->host) bytes the last loss_grad call moved."""
+        a, b = C.c_int64(0), C.c_int64(0)
+        self._check(self.lib.ude_last_io_bytes(self.handle, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
     def profile_begin(self, max_evals: int):
         self._check(self.lib.ude_profile_begin(self.handle, int(max_evals)))
 
@@ -331,9 +350,11 @@ class Engine:
                 o.Peta[i + d * j] = Pe[i, j]
         return o
 
-    def ukf_loss_grad(self, theta, pnu_factor, Peta, alpha=1e-3, beta=2.0, kappa=0.0, reg=0.0, want_grad=True):
+    def ukf_loss_grad(self, theta, pnu_factor, Peta, alpha=1e-3, beta=2.0, kappa=0.0, reg=0.0, want_grad=True, causal=False):
         """Unscented-Kalman-filter marginal likelihood (src/UnscentedKalmanFilter.jl:76-87): returns
-        (loss, grad_theta, grad_pnu_factor) with P_nu = F F', F = pnu_factor (d x d)."""
+        (loss, grad_theta, grad_pnu_factor) with P_nu = F F', F = pnu_factor (d x d).  causal=False (default) integrates the
+        sigma points over [times[t], times[t] + dt] as the reference does (:83, :93); causal=True over [times[t-1], times[t]]."""
+        self.set_option(OPT_UKF_CAUSAL_INTERVAL, int(bool(causal)))
         d = self.problem.d
         th = np.ascontiguousarray(theta, dtype=np.float64)
         F = np.ascontiguousarray(np.asarray(pnu_factor, dtype=np.float64).reshape(d, d).T)      # column-major bytes
@@ -347,8 +368,9 @@ class Engine:
             self._check(rc)
         return float(loss.value), g, (gF.T.copy() if want_grad else None)
 
-    def ukf_filter(self, theta, pnu_factor, Peta, alpha=1e-3, beta=2.0, kappa=0.0):
+    def ukf_filter(self, theta, pnu_factor, Peta, alpha=1e-3, beta=2.0, kappa=0.0, causal=False):
         """ukf_smoothing (src/UnscentedKalmanFilter.jl:59-72): filtered states (d x n_cols) and covariances (d x d x n_cols)."""
+        self.set_option(OPT_UKF_CAUSAL_INTERVAL, int(bool(causal)))
         d = self.problem.d
         th = np.ascontiguousarray(theta, dtype=np.float64)
         F = np.ascontiguousarray(np.asarray(pnu_factor, dtype=np.float64).reshape(d, d).T)

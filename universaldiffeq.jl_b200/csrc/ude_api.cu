@@ -100,6 +100,9 @@ struct ude_handle {
   std::vector<uint8_t> skip;
   std::vector<double> obs_scale, proc_scale, shoot_weight, reg_weight;
   bool have_data = false, have_cov = false, have_targets = false, dirty = true;
+  bool sparse_uhat_io = false;          // UDE_OPT_SPARSE_UHAT_IO
+  bool ukf_causal = false;              // UDE_OPT_UKF_CAUSAL_INTERVAL
+  int64_t last_h2d = 0, last_d2h = 0, n_segments = 0;
   // device buffers
   DevBuf<long long> d_starts, d_lengths, d_theta_base, d_model_col0, d_model_series0, d_knot_off;
   DevBuf<double> d_times, d_data, d_obs_scale, d_proc_scale, d_shoot_weight, d_reg_weight;
@@ -467,6 +470,8 @@ int build_plan(ude_handle* h) {
   pad_model();
   h->n_tasks = (int64_t)segs.size() / SPW;
   h->model_task0[(size_t)h->n_models] = h->n_tasks;
+  h->n_segments = 0;
+  for (const Seg& z : segs) if (!(z.flags & ude::SEG_NULL)) ++h->n_segments;
   for (int64_t t = 0; t < h->n_tasks; ++t) {
     int64_t mx = 0;
     for (int q = 0; q < SPW; ++q) {
@@ -635,6 +640,7 @@ DevProblem make_dev_problem(const ude_handle* h, const double* d_theta, double* 
   P.dm_u = h->d_dm_u.p; P.dm_dudt = h->d_dm_dudt.p;
   P.segs = h->d_segs.p; P.task_begin = 0; P.n_tasks = h->n_tasks; P.n_models = (int)h->n_models;
   P.theta = d_theta; P.grad = d_grad; P.traj_out = d_traj;
+  P.uhat_x = nullptr; P.guhat_x = nullptr;
   P.block_part = h->d_block_part.p; P.model_loss = h->d_model_loss.p;
   P.stash = h->d_stash.p; P.stash_rows_per_warp = h->stash_rows_per_warp;
   { const char* e = getenv("UDE_STASH_DISCARD"); P.stash_discard = e ? atoi(e) : 1; }
@@ -645,12 +651,13 @@ int finalize_eval(ude_handle* h, const double* d_theta, double* d_loss, double* 
 
 // launch the segment kernel over tasks [t0, t1) writing its per-block rows at row offset `row0`
 int launch_segments(ude_handle* h, const double* d_theta, double* d_grad, double* d_traj, int64_t t0, int64_t t1, int row0,
-                    cudaStream_t s) {
+                    cudaStream_t s, const double* uhat_x = nullptr, double* guhat_x = nullptr) {
   const bool want_grad = d_grad != nullptr;
   const KernelEntry* k = want_grad ? h->k_grad : h->k_fwd;
   const int grid = want_grad ? h->grid_grad : h->grid_fwd;
   DevProblem P = make_dev_problem(h, d_theta, d_grad, d_traj);
   P.task_begin = t0; P.n_tasks = t1;
+  P.uhat_x = uhat_x; P.guhat_x = guhat_x;
   P.block_part = h->d_block_part.p + (size_t)row0 * (size_t)(h->desc.n_pm + 1);
   void* args[] = {&P};
   const bool timed = h->ev_used < h->ev_cap;
@@ -669,6 +676,9 @@ int enqueue_eval(ude_handle* h, const double* d_theta, double* d_loss, double* d
   if (h->n_models > 1) UDE_CUDA_TRY(h, cudaMemsetAsync(h->d_model_loss.p, 0, (size_t)h->n_models * sizeof(double), s));
   int rc = launch_segments(h, d_theta, d_grad, d_traj, 0, h->n_tasks, 0, s);
   if (rc != UDE_OK) return rc;
+  // trajectories only (ude_forward): the loss is not used, so no reduction and -- on a peer-attached / NCCL handle -- no
+  // cross-rank exchange: a forward call is NOT a collective and may be made by one rank alone
+  if (d_traj != nullptr && !want_grad) return UDE_OK;
   return finalize_eval(h, d_theta, d_loss, d_grad, grid, s);
 }
 
@@ -778,6 +788,9 @@ int ude_create(const ude_desc* desc, ude_handle** out) {
 int ude_destroy(ude_handle* h) {
   if (!h) return UDE_OK;
   cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);      // nothing of this handle may still be running when its buffers go
+  if (h->s_h2d) cudaStreamSynchronize(h->s_h2d);
+  if (h->s_d2h) cudaStreamSynchronize(h->s_d2h);
   delete h->ukf;
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   for (int r = 0; r < UDE_MAX_PEERS; ++r) if (h->x_opened[r] && h->x_peer[r]) cudaIpcCloseMemHandle(h->x_peer[r]);
@@ -839,6 +852,7 @@ int ude_set_data(ude_handle* h, int64_t n_series, const int64_t* starts, const i
   UDE_CUDA_TRY(h, h->d_loss.reserve((size_t)M));
   h->have_data = true; h->dirty = true;
   h->skip.clear();
+  ukf_invalidate(h);
   int rc = ude_set_model_weights(h, nullptr, nullptr, nullptr, nullptr);
   if (rc != UDE_OK) return rc;
   UDE_CUDA_TRY(h, cudaStreamSynchronize(s));
@@ -885,6 +899,7 @@ int ude_set_covariates(ude_handle* h, const int64_t* knot_off, const double* kno
   UDE_CUDA_TRY(h, h->d_knot_inv.upload(inv.data(), nk, h->stream));
   UDE_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   h->have_cov = true;
+  ukf_invalidate(h);
   return UDE_OK;
 }
 
@@ -906,6 +921,24 @@ int ude_set_skip(ude_handle* h, const uint8_t* skip_mask) {
   if (!h->have_data) return fail(h, UDE_ERR_STATE, "ude_set_data first");
   if (skip_mask) h->skip.assign(skip_mask, skip_mask + h->n_cols); else h->skip.clear();
   h->dirty = true;
+  return UDE_OK;
+}
+
+int ude_set_option(ude_handle* h, int32_t option, int64_t value) {
+  if (!h) return UDE_ERR_INVALID;
+  switch (option) {
+    case UDE_OPT_SPARSE_UHAT_IO: h->sparse_uhat_io = value != 0; return UDE_OK;
+    case UDE_OPT_UKF_CAUSAL_INTERVAL:
+      if (h->ukf_causal != (value != 0)) { h->ukf_causal = value != 0; ukf_invalidate(h); }
+      return UDE_OK;
+    default: return fail(h, UDE_ERR_INVALID, "unknown option");
+  }
+}
+
+int ude_last_io_bytes(const ude_handle* h, int64_t* h2d_bytes, int64_t* d2h_bytes) {
+  if (!h) return UDE_ERR_INVALID;
+  if (h2d_bytes) *h2d_bytes = h->last_h2d;
+  if (d2h_bytes) *d2h_bytes = h->last_d2h;
   return UDE_OK;
 }
 
@@ -941,6 +974,36 @@ int ude_loss_grad(ude_handle* h, const double* theta, int64_t n_theta, double* l
   if (h->dirty) { int rc = build_plan(h); if (rc != UDE_OK) return rc; }
   cudaStream_t s = h->stream;
   const size_t K = h->chunks.size();
+  // ---- zero-copy path (UDE_OPT_SPARSE_UHAT_IO): the kernels read the block-start columns of uhat from, and write their
+  // gradient to, the caller's page-locked buffers; only the process model is copied.  One launch, no chunk pipeline.
+  const double* z_theta = nullptr; double* z_grad = nullptr;
+  if (grad && h->sparse_uhat_io && h->n_models == 1 &&
+      (h->desc.loss_kind == UDE_LOSS_MULTI_SHOOT || h->desc.loss_kind == UDE_LOSS_SHOOT)) {
+    cudaPointerAttributes at{}, ag{};
+    if (cudaPointerGetAttributes(&at, theta) == cudaSuccess && cudaPointerGetAttributes(&ag, grad) == cudaSuccess &&
+        at.type == cudaMemoryTypeHost && ag.type == cudaMemoryTypeHost && at.devicePointer && ag.devicePointer) {
+      z_theta = (const double*)at.devicePointer; z_grad = (double*)ag.devicePointer;
+    }
+    cudaGetLastError();      // a pageable pointer makes cudaPointerGetAttributes report an error on old drivers: not ours
+  }
+  if (z_theta) {
+    const int d = h->desc.d;
+    const size_t pmb = (size_t)d * h->n_cols, npm = (size_t)h->desc.n_pm;
+    double* dth = h->d_theta.p; double* dg = h->d_grad.p;
+    UDE_CUDA_TRY(h, cudaMemcpyAsync(dth + pmb, theta + pmb, npm * sizeof(double), cudaMemcpyHostToDevice, s));
+    UDE_CUDA_TRY(h, cudaMemsetAsync(dg + pmb, 0, npm * sizeof(double), s));      // the per-series tail is accumulated by atomics
+    int rc = launch_segments(h, dth, dg, nullptr, 0, h->n_tasks, 0, s, z_theta, z_grad);
+    if (rc != UDE_OK) return rc;
+    rc = finalize_eval(h, dth, h->d_loss.p, dg, h->grid_grad, s);
+    if (rc != UDE_OK) return rc;
+    UDE_CUDA_TRY(h, cudaMemcpyAsync(loss, h->d_loss.p, sizeof(double), cudaMemcpyDeviceToHost, s));
+    UDE_CUDA_TRY(h, cudaMemcpyAsync(grad + pmb, dg + pmb, npm * sizeof(double), cudaMemcpyDeviceToHost, s));
+    UDE_CUDA_TRY(h, cudaStreamSynchronize(s));
+    const bool reads_uhat = h->desc.loss_kind == UDE_LOSS_MULTI_SHOOT || h->desc.shoot_from_theta;
+    const int64_t cols = reads_uhat ? h->n_segments : 0;
+    h->last_h2d = 8 * ((int64_t)d * cols + (int64_t)npm);
+    h->last_d2h = 8 * ((int64_t)d * cols + (int64_t)npm + 1);
+  } else
   if (K > 1 && grad) {
     // ---- pipelined host path: chunk k+1's uhat columns are uploaded and chunk k-1's gradient columns downloaded while
     // chunk k is on the SMs (PCIe is full duplex; the copies use their own streams and the copy engines).
@@ -974,6 +1037,7 @@ int ude_loss_grad(ude_handle* h, const double* theta, int64_t n_theta, double* l
     UDE_CUDA_TRY(h, cudaMemcpyAsync(grad + pmb, dg + pmb, (size_t)h->desc.n_pm * sizeof(double), cudaMemcpyDeviceToHost, s));
     UDE_CUDA_TRY(h, cudaStreamSynchronize(s));
     UDE_CUDA_TRY(h, cudaStreamSynchronize(h->s_d2h));
+    h->last_h2d = 8 * n_theta; h->last_d2h = 8 * (n_theta + 1);
   } else {
     UDE_CUDA_TRY(h, cudaMemcpyAsync(h->d_theta.p, theta, (size_t)n_theta * sizeof(double), cudaMemcpyHostToDevice, s));
     int rc = enqueue_eval(h, h->d_theta.p, h->d_loss.p, grad ? h->d_grad.p : nullptr, nullptr, s);
@@ -981,6 +1045,7 @@ int ude_loss_grad(ude_handle* h, const double* theta, int64_t n_theta, double* l
     UDE_CUDA_TRY(h, cudaMemcpyAsync(loss, h->d_loss.p, (size_t)h->n_models * sizeof(double), cudaMemcpyDeviceToHost, s));
     if (grad) UDE_CUDA_TRY(h, cudaMemcpyAsync(grad, h->d_grad.p, (size_t)n_theta * sizeof(double), cudaMemcpyDeviceToHost, s));
     UDE_CUDA_TRY(h, cudaStreamSynchronize(s));
+    h->last_h2d = 8 * n_theta; h->last_d2h = 8 * ((grad ? n_theta : 0) + h->n_models);
   }
   for (int64_t m = 0; m < h->n_models; ++m)
     if (!std::isfinite(loss[m])) return fail(h, UDE_NONFINITE, "loss is not finite (diverged trajectory?)");
@@ -1219,7 +1284,12 @@ int ude_adam(ude_handle* h, double* theta, int64_t n_theta, double step_size, in
   }
   UDE_CUDA_TRY(h, cudaMemcpyAsync(theta, h->d_theta.p, n * sizeof(double), cudaMemcpyDeviceToHost, s));
   if (loss_trace && n_iter > 0) UDE_CUDA_TRY(h, cudaMemcpyAsync(loss_trace, d_trace.p, M * (size_t)n_iter * sizeof(double), cudaMemcpyDeviceToHost, s));
+  std::vector<double> last(M, 0.0);
+  if (n_iter > 0) UDE_CUDA_TRY(h, cudaMemcpyAsync(last.data(), d_trace.p + (size_t)(n_iter - 1) * M, M * sizeof(double), cudaMemcpyDeviceToHost, s));
   UDE_CUDA_TRY(h, cudaStreamSynchronize(s));
+  // a diverged fit, or a peer that never arrived at the exchange (the fused exchange then writes NaN), must not look like success
+  for (size_t m = 0; m < M && n_iter > 0; ++m)
+    if (!std::isfinite(last[m])) return fail(h, UDE_NONFINITE, "ude_adam: the loss of the last iteration is not finite (diverged fit, or a peer timed out in the exchange)");
   return UDE_OK;
 }
 

@@ -47,6 +47,11 @@ struct DevProblem {
   const Seg* segs; long long task_begin, n_tasks; int n_models;   // this launch covers tasks [task_begin, n_tasks)
   // io
   const double* theta; double* grad; double* traj_out;
+  // Single-model trajectory losses read only the block-start columns of uhat and each of those columns receives exactly
+  // one gradient contribution (LFC.jl:281-296, :665-680).  When uhat_x / guhat_x are set, those columns are read from /
+  // written (plain stores, no atomics) to these bases instead of theta / grad -- the host-buffer path points them at the
+  // caller's pinned theta and gradient, so nothing but the block starts ever crosses PCIe (ude_loss_grad, zero-copy).
+  const double* uhat_x; double* guhat_x;
   double* block_part;   // [grid][n_pm + 1]: per-block gradient of process_model and loss (n_models == 1)
   double* model_loss;   // [n_models], atomics                                       (n_models  > 1)
   void* stash; long long stash_rows_per_warp;      // rows of 32 elements of the kernel's arithmetic type

@@ -3,6 +3,7 @@
 #pragma once
 #include "ude_kernel.cuh"
 #include "ude_kernel_mma.cuh"
+#include "ude_kernel_mma2.cuh"
 #include "ude_registry.h"
 
 namespace ude {
@@ -74,5 +75,31 @@ void register_mma_combo(const char* name, int priority) {
   register_mma_one<D, NX, HT, HW, MINB, 1, LK_STATE, TB>(name, priority);
   register_mma_one<D, NX, HT, HW, MINB, 1, LK_TRAJ, TB>(name, priority);
   register_mma_one<D, NX, HT, HW, MINB, 1, LK_DM, TB>(name, priority);
+}
+
+// round-2 tensor-core family (ude_kernel_mma2.cuh): NT M-tiles (8 segments each) per warp, state-space and trajectory
+// loss families (derivative matching keeps ude_mma_kernel); OPT = MMA2_* bits, TB = tanh chains interleaved per batch
+template <int D, int NX, int HT, int NT, int MINB, int SOLVER, int LK, int OPT, int TB>
+void register_mma2_one(const char* name, int priority) {
+  using MG = Mma2Geo<D, NX, HT, NT, OPT, TB>;
+  const int G = 4, HPLcap = 2 * HT;
+  kernel_registry().push_back(KernelEntry{UDE_RHS_NODE, D, NX, D + NX, D, UDE_F64, G, HPLcap, SOLVER, LK, 1, MG::RECW / 32, 8, 0,
+                                          MG::NFRAG * 32 * 8, MG::WARP_GRAD * 8, 1, 8 * NT, 1, priority,
+                                          (const void*)ude_mma2_kernel<D, NX, HT, NT, SOLVER, LK, true, MINB, OPT, TB>, name});
+  kernel_registry().push_back(KernelEntry{UDE_RHS_NODE, D, NX, D + NX, D, UDE_F64, G, HPLcap, SOLVER, LK, 0, MG::RECW / 32, 8, 0,
+                                          MG::NFRAG * 32 * 8, 0, 1, 8 * NT, 1, priority,
+                                          (const void*)ude_mma2_kernel<D, NX, HT, NT, SOLVER, LK, false, MINB, OPT, TB>, name});
+}
+template <int D, int NX, int HT, int NT, int MINB, int OPT = 0, int TB = 4>
+void register_mma2_combo(const char* name, int priority) {
+  register_mma2_one<D, NX, HT, NT, MINB, 0, LK_STATE, OPT, TB>(name, priority);
+  register_mma2_one<D, NX, HT, NT, MINB, 0, LK_TRAJ, OPT, TB>(name, priority);
+  register_mma2_one<D, NX, HT, NT, MINB, 1, LK_STATE, OPT, TB>(name, priority);
+  register_mma2_one<D, NX, HT, NT, MINB, 1, LK_TRAJ, OPT, TB>(name, priority);
+}
+// tuning variants: RK4 + trajectory family only (what the C3 sweep measures)
+template <int D, int NX, int HT, int NT, int MINB, int OPT = 0, int TB = 4>
+void register_mma2_probe(const char* name, int priority) {
+  register_mma2_one<D, NX, HT, NT, MINB, 0, LK_TRAJ, OPT, TB>(name, priority);
 }
 }  // namespace ude

@@ -239,8 +239,8 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) ude_mma_kernel(const DevP
   }
   double loss = 0.0;
 
-  const double* __restrict__ uh = P.theta;        // single model: uhat is indexed by global column
-  double* __restrict__ guh = P.grad;
+  const double* __restrict__ uh = P.uhat_x ? P.uhat_x : P.theta;        // single model: uhat is indexed by global column
+  double* __restrict__ guh = P.guhat_x ? P.guhat_x : P.grad;
 
   for (long long task = P.task_begin + group_global; task < P.n_tasks; task += total_groups) {
     const Seg sg = P.segs[task * 8 + r];
@@ -618,7 +618,7 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) ude_mma_kernel(const DevP
             if (LK == LK_STATE) {
               atomicAdd(guh + D * sg.col + slot[e], gc[e]);
               if (has_prev) atomicAdd(guh + D * c0 + slot[e], gp[e] + lam[e]);
-            } else if (from_theta) atomicAdd(guh + D * c0 + slot[e], lam[e]);
+            } else if (from_theta) { if (P.guhat_x) guh[D * c0 + slot[e]] = lam[e]; else atomicAdd(guh + D * c0 + slot[e], lam[e]); }
           }
         }
       }

@@ -79,6 +79,11 @@ __constant__ double c_ude_exp2_tab[64] = {
 __device__ __forceinline__ void ude_load_exp2_tab(double* s_tab /* shared, 64 doubles */) {
   for (int i = threadIdx.x; i < 64; i += blockDim.x) s_tab[i] = c_ude_exp2_tab[i];
 }
+// COPIES interleaved copies: entry j of copy q at [j * COPIES + q]
+template <int COPIES>
+__device__ __forceinline__ void ude_load_exp2_tab_n(double* s_tab /* shared, 64 * COPIES doubles */) {
+  for (int i = threadIdx.x; i < 64 * COPIES; i += blockDim.x) s_tab[i] = c_ude_exp2_tab[i / COPIES];
+}
 
 // tanh via E = expm1(2|x|) = 2^n T_j (1 + p(r)) - 1 with 2|x| = (64 n + j) ln2/64 + r, |r| <= ln2/128.
 // |error| <= ~1.5e-16 absolute everywhere (relative ~1e-16 except for |x| in [0.003, 0.3] where E = T(1+p)-1
@@ -166,10 +171,77 @@ __device__ __forceinline__ void ude_tanh_tab_vec(const double (&x)[N], double (&
   for (int i = 0; i < N; ++i) out[i] = copysign(fma(e[i], y[i], q[i]), x[i]);
 }
 
+// Round-2 evaluation: 14 FP64-pipe instructions per tanh instead of 19 (tanh is ~30% of the FP64 issue of the flagship
+// kernel).  With w = exp(2|x|) = 2^n T_j (1 + p):   tanh|x| = 1 - 2 / (w + 1).
+//   * argument reduction on |x| directly (no doubling) and with ONE constant: rh = |x| - k (ln2/128) = r/2.  The rounding
+//     of the constant puts an error of 1.1e-16 |x| on r, which the result sees scaled by 2w/(w+1)^2 <= e^(-2|x|)/2...1/2:
+//     below 3e-17 for every x, so the second Cody-Waite term of ude_tanh_tab buys nothing here;
+//   * P = p/2 = rh + rh^2 (1 + 2/3 rh + 1/3 rh^2 + 2/15 rh^3)  (expm1(2 rh)/2 to r^5; the r^6/720 term is 3.4e-17);
+//   * w + 1 = fma(2s, P, s + 1) with s = 2^n T_j assembled in the integer pipe;
+//   * reciprocal by MUFU.RCP64H (~2^-20) and ONE cubically convergent step y(1 + e + e^2): (2^-20)^3 = 2^-60;
+//   * 1 - 2y with a single fma.  Absolute error <= 2.2e-16 (same floor as ude_tanh_tab; relative accuracy is lost only
+//     where |tanh| < 1e-6, where the absolute floor is what the sums this feeds can see anyway).
+// TS / toff: table stride and offset -- TS = 16, toff = lane & 15 reads an interleaved 16-copy table without bank conflicts
+template <int N, int TS = 1>
+__device__ __forceinline__ void ude_tanh_fast_vec(const double (&x)[N], double (&out)[N], const double* __restrict__ s_tab, int toff = 0) {
+  const double INV   = 184.6649652337873;              // 128 / ln 2
+  const double CH    = 0x1.62e42fefa39efp-8;           // (ln 2)/128
+  const double SHIFT = 6755399441055744.0;
+  double ax[N], kf[N], rh[N], q[N], P[N], T[N], s[N], s2[N], den[N], y[N], e[N];
+  int Nn[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    int hi = __double2hiint(x[i]) & 0x7fffffff;
+    hi = min(hi, 0x40340000);                          // |x| <= 20
+    ax[i] = __hiloint2double(hi, __double2loint(x[i]));
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) kf[i] = fma(ax[i], INV, SHIFT);
+#pragma unroll
+  for (int i = 0; i < N; ++i) { Nn[i] = __double2loint(kf[i]); kf[i] -= SHIFT; }
+#pragma unroll
+  for (int i = 0; i < N; ++i) T[i] = s_tab[(Nn[i] & 63) * TS + toff];
+#pragma unroll
+  for (int i = 0; i < N; ++i) rh[i] = fma(kf[i], -CH, ax[i]);
+#pragma unroll
+  for (int i = 0; i < N; ++i) q[i] = fma(rh[i], 1.3333333333333333e-01, 3.3333333333333331e-01);
+#pragma unroll
+  for (int i = 0; i < N; ++i) q[i] = fma(q[i], rh[i], 6.6666666666666663e-01);
+#pragma unroll
+  for (int i = 0; i < N; ++i) q[i] = fma(q[i], rh[i], 1.0);
+#pragma unroll
+  for (int i = 0; i < N; ++i) P[i] = fma(q[i], rh[i] * rh[i], rh[i]);
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const int hi = __double2hiint(T[i]) + ((Nn[i] >> 6) << 20);
+    s[i] = __hiloint2double(hi, __double2loint(T[i]));                     // 2^n T_j
+    s2[i] = __hiloint2double(hi + (1 << 20), __double2loint(T[i]));        // 2 s
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) den[i] = fma(s2[i], P[i], s[i] + 1.0);       // w + 1
+#pragma unroll
+  for (int i = 0; i < N; ++i) asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y[i]) : "d"(den[i]));
+#pragma unroll
+  for (int i = 0; i < N; ++i) e[i] = fma(-den[i], y[i], 1.0);
+#pragma unroll
+  for (int i = 0; i < N; ++i) e[i] = fma(e[i], e[i], e[i]);
+#pragma unroll
+  for (int i = 0; i < N; ++i) y[i] = fma(y[i], e[i], y[i]);
+#pragma unroll
+  for (int i = 0; i < N; ++i) out[i] = copysign(fma(-2.0, y[i], 1.0), x[i]);
+}
+
 // type-dispatched front end used by the typed kernel body
+#ifndef UDE_TANH_FAST
+#define UDE_TANH_FAST 1
+#endif
 template <int N>
 __device__ __forceinline__ void ude_tanh_vec(const double (&x)[N], double (&out)[N], const double* __restrict__ s_tab) {
+#if UDE_TANH_FAST
+  ude_tanh_fast_vec<N>(x, out, s_tab);
+#else
   ude_tanh_tab_vec<N>(x, out, s_tab);
+#endif
 }
 
 // single-precision twin for the optional FP32 mode (1e-4 parity bar): hardware tanh is too coarse

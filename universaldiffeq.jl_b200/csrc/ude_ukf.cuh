@@ -61,6 +61,17 @@ struct ude_ukf_plan {
   }
 };
 
+// the plan caches host copies of times / knots, buffers sized by n_series / n_cols and captured graphs with baked-in
+// pointers: it must not survive ude_set_data / ude_set_covariates / a change of the prediction window
+void ukf_invalidate(ude_handle* h) {
+  if (h->ukf) {
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    delete h->ukf;
+    h->ukf = nullptr;
+  }
+}
+
 // ---- small dense algebra, compile-time D <= 8 (everything stays in registers), column-major M[i + D*j] ---------------------------------------------------
 template <int d>
 __device__ __forceinline__ void ukf_chol_upper(const double* A, double* U) {      // reads the upper triangle of A
@@ -524,7 +535,12 @@ int ukf_build(ude_handle* h, ude_ukf_plan*& out_plan) {
     for (int64_t s = 0; s < h->n_series; ++s) {
       if (h->lengths[s] <= k + 1) continue;
       active.push_back((int)s); ++st.n_act;
-      const double ta = times[(size_t)(h->starts[s] + k)], tb = times[(size_t)(h->starts[s] + k + 1)];
+      // Reference window: ukf_update receives (times[t], dt) and predict integrates over [times[t], times[t] + dt]
+      // (src/UnscentedKalmanFilter.jl:67, :83, :93, :121) -- it STARTS at the end of the observation interval.  Same flow
+      // for an autonomous RHS, different with covariates / a time input.  UDE_OPT_UKF_CAUSAL_INTERVAL opts into
+      // [times[t-1], times[t]].
+      const double t_lo = times[(size_t)(h->starts[s] + k)], t_hi = times[(size_t)(h->starts[s] + k + 1)];
+      const double ta = h->ukf_causal ? t_lo : t_hi, tb = h->ukf_causal ? t_hi : t_hi + (t_hi - t_lo);
       for (int j = 0; j < n_sig; ++j) {
         a_starts.push_back(col); a_lengths.push_back(2); a_model.push_back(k);
         a_times.push_back(ta); a_times.push_back(tb);
