@@ -218,6 +218,15 @@ int ude_ukf_loss_grad(ude_handle* h, const ude_ukf_opts* opts, const double* the
 int ude_ukf_filter(ude_handle* h, const ude_ukf_opts* opts, const double* theta, int64_t n_theta, const double* pnu_factor,
                    double* states, double* covariances);
 
+/* Derivative-matching pre-step, batched (LFC.jl:161-171, :510-522: RegularizationSmooth(u, t, d; alg = :gcv_svd) per state and
+ * series + DataInterpolations.derivative at the observation times).  All `rows` rows of U (rows x n, row-major) share one time
+ * grid, whose operators the host builds once: Vt (r x n, right singular vectors of the d-th order derivative matrix D), s (r,
+ * its singular values), M (n x n: knot derivatives of the natural cubic spline as a matrix).  Per row the kernel minimises
+ * GCV(lambda) over [lambda_lo, lambda_hi] (RegularizationTools defaults 1e-4, 1e3), and writes the smoothed values, their
+ * time derivative and the chosen lambda.  Host buffers in and out; no handle. */
+int ude_reg_smooth(int32_t device, int32_t n, int32_t r, int64_t rows, const double* Vt, const double* s, const double* M,
+                   const double* U, double lambda_lo, double lambda_hi, double* out_u, double* out_dudt, double* out_lambda);
+
 /* Kernel timing for roofline reports: after ude_profile_begin(h, n) the next n evaluations bracket the segment
  * kernel (the dominant launch) with CUDA events on the launching stream; ude_profile_read synchronises and returns
  * how many were recorded, writing their durations in milliseconds. */

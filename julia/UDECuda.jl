@@ -16,6 +16,7 @@
 module UDECuda
 
 using ComponentArrays
+using LinearAlgebra
 
 const lib = "libude_cuda"                       # on LD_LIBRARY_PATH (universaldiffeq.jl_b200/csrc/libude_cuda.so)
 
@@ -90,7 +91,6 @@ function errors_to_matrix(e, d)
     ndims(e) == 1 && return Matrix{Float64}(Diagonal(e))
     return Matrix{Float64}(e)
 end
-using LinearAlgebra
 
 """
     desc_from(UDE, loss_function, loss_options; rhs_kind = RHS_NODE, scalar_names = (), time_scale = 1.0, time_shift = 0.0, device = 0)
@@ -139,7 +139,7 @@ function desc_from(UDE, loss_function::String, loss_options::NamedTuple; rhs_kin
          rhs_kind, d, n_cov, din, H, dout, length(scalar_names), series_param === nothing ? 0 : 1,
          off_w1, off_b1, off_w2, off_b2, pad8(offs), off_sp, o, time_scale, time_shift,
          loss_kind, pl, inv_dt, from_theta, first_scored, remove_ends, eps,
-         pad64(vcat([vcat(A[:, j], zeros(0)) for j in 1:d]...)), pad64(vcat([B[:, j] for j in 1:d]...)),
+         pad64(vec(A)), pad64(vec(B)),                 # d x d column-major in the first d*d entries
          0, 0, 0, ntuple(_ -> Int32(0), 5))
 end
 

@@ -4,7 +4,7 @@ Host-side mirror of the reference's API for the hot path only (SURVEY.md section
 train!, cross-validation drivers, all calling libude_cuda.so through its C ABI (include/ude_cuda.h).
 The directory name carries a dot, so import it through the repo-root shim:  ``import ude_b200 as ude``.
 """
-from . import problem, synthetic, sharding, simulate  # noqa: F401
+from . import problem, smoothing, synthetic, sharding, simulate  # noqa: F401
 from .problem import Problem  # noqa: F401
 from . import _capi  # noqa: F401
 from ._capi import (Engine, UdeError, device_count, measure_fp64_peak, get_unique_id, load_library, LIB_PATH,  # noqa: F401

@@ -29,7 +29,7 @@ EXPORTS = ["ude_abi_version", "ude_device_count", "ude_create", "ude_destroy", "
            "ude_n_models", "ude_steps_per_eval", "ude_kernel_name", "ude_launches_per_eval", "ude_loss_grad", "ude_loss_grad_device",
            "ude_forward", "ude_comm_unique_id", "ude_comm_init", "ude_adam", "ude_adam_used_graph", "ude_profile_begin", "ude_profile_read",
            "ude_measure_fp64_peak", "ude_measure_fp32_peak", "ude_peer_export", "ude_peer_attach",
-           "ude_ukf_loss_grad", "ude_ukf_filter", "ude_forecast_chain"]
+           "ude_ukf_loss_grad", "ude_ukf_filter", "ude_forecast_chain", "ude_reg_smooth"]
 
 
 class UkfOpts(C.Structure):
@@ -133,6 +133,8 @@ def load_library():
     lib.ude_peer_attach.argtypes = [vp, vp, i32, i32]
     lib.ude_measure_fp32_peak.restype = C.c_int
     lib.ude_measure_fp32_peak.argtypes = [i32, C.POINTER(C.c_double)]
+    lib.ude_reg_smooth.restype = C.c_int
+    lib.ude_reg_smooth.argtypes = [i32, i32, i32, i64, vp, vp, vp, vp, C.c_double, C.c_double, vp, vp, vp]
     lib.ude_set_option.restype = C.c_int
     lib.ude_set_option.argtypes = [vp, i32, i64]
     lib.ude_last_io_bytes.restype = C.c_int

@@ -738,6 +738,9 @@ int finalize_eval(ude_handle* h, const double* d_theta, double* d_loss, double* 
 
 #include "ude_ukf.cuh"
 
+// other translation units of the library (ude_smooth.cu) report handle-less failures through the same channel
+int ude_fail_create(int code, const std::string& msg) { return fail(nullptr, code, msg); }
+
 // ==================================================================================================================
 #pragma GCC visibility push(default)
 extern "C" {

@@ -16,6 +16,7 @@ from typing import Optional
 import numpy as np
 
 from . import problem as P
+from . import smoothing
 from ._capi import Engine
 from .models import UDE
 
@@ -101,46 +102,22 @@ def shooting_loss(model: UDE, regularization_weight=0.0) -> P.Problem:
     return p.finalize()
 
 
-def _smoother_operators(t, lam_grid=None):
-    """hat matrices (I + lam D'D)^-1 of the second-difference smoother on the grid t for every lam of the grid, with traces"""
-    n = t.shape[0]
-    D = np.zeros((n - 2, n))
-    for i in range(n - 2):
-        h0, h1 = t[i + 1] - t[i], t[i + 2] - t[i + 1]
-        D[i, i], D[i, i + 1], D[i, i + 2] = 2 / (h0 * (h0 + h1)), -2 / (h0 * h1), 2 / (h1 * (h0 + h1))
-    DtD = D.T @ D
-    lam_grid = np.logspace(-8, 2, 41) * (t[-1] - t[0]) ** 4 if lam_grid is None else lam_grid
-    ops = []
-    for lam in lam_grid:
-        Hm = np.linalg.solve(np.eye(n) + lam * DtD, np.eye(n))
-        ops.append((Hm, float(np.trace(Hm))))
-    return ops
-
-
-def smooth_derivs_batch(U, t, lam_grid=None):
-    """Host pre-step of derivative matching (LFC.jl:161-171) for MANY rows that share one time grid: U is (rows, n) -- every
-    row one state variable of one series -- each smoothed with its own GCV-chosen weight; returns (smoothed, d/dt).  The
-    reference calls RegularizationTools.RegularizationSmooth (third-party, not in /root/reference); this is a second-difference
-    Tikhonov smoother with the same role.  The hat matrices depend on the grid only, so 10^5 series on a common grid cost 41
-    matrix products instead of 10^5 x 41 solves."""
+def smooth_derivs_batch(U, t, d=12, device=0):
+    """Host pre-step of derivative matching (LFC.jl:161-171, :510-522) for MANY rows that share one time grid: U is (rows, n)
+    -- every row one state variable of one series.  `RegularizationSmooth(u, t, d; alg = :gcv_svd)` + the derivative of its
+    cubic-spline interpolant, restated in smoothing.py and evaluated on the GPU (csrc/ude_smooth.cu): the grid operators are
+    built once on the host, one warp per row does the GCV minimisation.  Returns (smoothed, d/dt)."""
     U = np.asarray(U, dtype=np.float64); t = np.asarray(t, dtype=np.float64)
     n = t.shape[0]
-    if n < 4:
+    if n < 3:                   # the reference's smoother has nothing to penalise here (it would throw for n <= d)
         return U.copy(), (np.gradient(U, t, axis=1) if n > 1 else np.zeros_like(U))
-    best_gcv = np.full(U.shape[0], np.inf)
-    best_fit = np.zeros_like(U)
-    for Hm, tr in _smoother_operators(t, lam_grid):
-        fit = U @ Hm.T
-        gcv = n * np.sum((U - fit) ** 2, axis=1) / max(n - tr, 1e-9) ** 2
-        take = gcv < best_gcv
-        best_gcv = np.where(take, gcv, best_gcv)
-        best_fit[take] = fit[take]
-    return best_fit, np.gradient(best_fit, t, axis=1)
+    fit, der, _ = smoothing.reg_smooth_batch(U, t, d=d, device=device)
+    return fit, der
 
 
-def smooth_derivs(u, t, lam_grid=None):
-    """one series: u is (d, n)"""
-    return smooth_derivs_batch(u, t, lam_grid)
+def smooth_derivs(u, t, d=12):
+    """one series: u is (d_state, n)"""
+    return smooth_derivs_batch(u, t, d)
 
 
 def derivative_matching_loss(model: UDE, regularization_weight=0.0, d=12, remove_ends=0) -> P.Problem:
@@ -150,7 +127,7 @@ def derivative_matching_loss(model: UDE, regularization_weight=0.0, d=12, remove
     us, du = np.zeros_like(model.data), np.zeros_like(model.data)
     starts = model.starts if model.multi else [0]
     lengths = model.lengths if model.multi else [model.data.shape[1]]
-    # series that share a time grid are smoothed in one batch (the hat matrices depend on the grid only)
+    # series that share a time grid are smoothed in one batch on the GPU (the operators depend on the grid only)
     groups = {}
     for s, n in zip(starts, lengths):
         groups.setdefault(np.asarray(model.times[s:s + n]).tobytes(), []).append((int(s), int(n)))
@@ -158,7 +135,7 @@ def derivative_matching_loss(model: UDE, regularization_weight=0.0, d=12, remove
     for members in groups.values():
         s0, n = members[0]
         rows = np.concatenate([model.data[:, s:s + n] for s, _ in members], axis=0)
-        fit, der = smooth_derivs_batch(rows, model.times[s0:s0 + n])
+        fit, der = smooth_derivs_batch(rows, model.times[s0:s0 + n], d=d)
         for q, (s, _) in enumerate(members):
             us[:, s:s + n], du[:, s:s + n] = fit[dd * q: dd * (q + 1)], der[dd * q: dd * (q + 1)]
     p.dm_u, p.dm_dudt = us, du
