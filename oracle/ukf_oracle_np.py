@@ -34,6 +34,26 @@ def chol_upper(A):
     return U
 
 
+def _inv_det(S):
+    """inverse and determinant of a small dense matrix: LAPACK for double / complex double, Gauss-Jordan with partial pivoting
+    for everything else (np.longdouble: the extended-precision runs that size the alpha = 1e-3 tolerance)"""
+    if S.dtype in (np.float64, np.complex128):
+        return np.linalg.inv(S), np.linalg.det(S)
+    n = S.shape[0]
+    A = np.concatenate([S.copy(), np.eye(n, dtype=S.dtype)], axis=1)
+    det = S.dtype.type(1)
+    for c in range(n):
+        piv = c + int(np.argmax(np.abs(A[c:, c])))
+        if piv != c:
+            A[[c, piv]] = A[[piv, c]]; det = -det
+        det = det * A[c, c]
+        A[c] = A[c] / A[c, c]
+        for r in range(n):
+            if r != c:
+                A[r] = A[r] - A[r, c] * A[c]
+    return A[:, n:], det
+
+
 def weights(L, alpha, beta, kappa):
     lam = alpha ** 2 * (L - kappa) - L
     return lam + L, lam / (lam + L), lam / (lam + L) + (1 - alpha ** 2 + beta), 1.0 / (2 * (L + lam))
@@ -51,12 +71,12 @@ def ukf_update(y, x, Px, f, Pnu, Peta, L, alpha, beta, kappa):
         P1 = P1 + Wi * np.outer(q - m, q - m)
     P1 = P1 + Pnu
     S = P1 + Peta
-    Sinv = np.linalg.inv(S)
+    Sinv, detS = _inv_det(S)
     K = P1 @ Sinv
     r = y - m
     xn = m + K @ r
     Pn = P1 - K @ P1
-    ll = -0.5 * (r @ (Sinv @ r)) - 0.5 * np.log(np.linalg.det(S)) - L / 2 * np.log(2 * 3.14159)
+    ll = -0.5 * (r @ (Sinv @ r)) - 0.5 * np.log(detS) - L / 2 * np.log(2 * 3.14159)
     return xn, Pn, ll
 
 
@@ -91,7 +111,9 @@ def loss(p, theta, pnu, Peta, alpha=1e-3, beta=2.0, kappa=0.0, reg_weight=0.0, r
     """-sum_series loglik + reg_mult * reg_weight * (|W1|^2 + |W2|^2).  theta = [uhat | process_model] of a single-model
     problem (uhat does not enter); pnu = d x d factor with P_nu = pnu pnu^T.  reg_mult = 1 (UDE) or n_series + 1 (MultiUDE)."""
     theta = np.asarray(theta); pnu = np.asarray(pnu)
-    dtype = complex if (np.iscomplexobj(theta) or np.iscomplexobj(pnu)) else float
+    dtype = complex if (np.iscomplexobj(theta) or np.iscomplexobj(pnu)) else (np.longdouble if theta.dtype == np.longdouble else float)
+    if dtype is np.longdouble:
+        Peta = np.asarray(Peta, dtype=np.longdouble); pnu = pnu.astype(np.longdouble)
     d = p.d
     pm = theta[d * p.n_cols: d * p.n_cols + p.n_pm]
     Lf = pnu.reshape(d, d, order="F")

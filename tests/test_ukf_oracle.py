@@ -178,3 +178,27 @@ def test_prediction_window_is_the_reference_one():
                 tot -= ll
         assert abs(tot - a) < 1e-13 * abs(a), rhs
 
+
+def test_alpha_conditioning_extended_precision():
+    """How well CAN two FP64 evaluations of the reference's UKF loss agree?  The twin in np.longdouble (64-bit mantissa) is the
+    yardstick: at alpha = 1 the FP64 twin matches it to rounding; at the reference default alpha = 1e-3 the sigma-point weights
+    (~ +-1e6) cancel and the FP64 value sits ~1e-11 away -- growing like 1 / alpha^2.  This is what sizes the tolerance of the
+    alpha = 1e-3 GPU tests (1e-9 / 5e-8), and shows 1e-10 on the gradient is not attainable in FP64 for that alpha."""
+    prob, theta, Lf, Peta = _case("node_d2", hidden=5, lengths=(8, 5))
+    err = {}
+    for alpha in (1.0, 1e-2, 1e-3):
+        a = ukf.loss(prob, theta, Lf, Peta, alpha=alpha)
+        b = float(ukf.loss(prob, theta.astype(np.longdouble), Lf, Peta, alpha=alpha))
+        err[alpha] = abs(a - b) / abs(b)
+    assert err[1.0] < 1e-15 and err[1e-2] < 1e-11 and err[1e-3] < 1e-9
+    assert err[1e-3] > 30 * max(err[1.0], 1e-16)          # the cancellation is real: well above FP64 rounding
+    # gradient: complex step in double vs in extended precision, three process-model entries
+    n_u = prob.d * prob.n_cols
+    eps = 1e-30
+    for k in (0, 7, prob.n_pm - 1):
+        t64 = theta.astype(complex); t64[n_u + k] += 1j * eps
+        tld = theta.astype(np.clongdouble); tld[n_u + k] += np.clongdouble(1j * eps)
+        g64 = np.imag(ukf.loss(prob, t64, Lf, Peta, alpha=1e-3)) / eps
+        gld = float(np.imag(ukf.loss(prob, tld, Lf.astype(np.clongdouble), np.asarray(Peta, dtype=np.clongdouble), alpha=1e-3)) / eps)
+        assert abs(g64 - gld) < 1e-7 * max(abs(gld), 1e-3)
+

@@ -17,7 +17,12 @@ def ncu(page):
 raw = list(csv.reader(io.StringIO(ncu("raw"))))
 hdr, unit, val = raw[0], raw[1], raw[2]
 m = {h: (v, u) for h, u, v in zip(hdr, unit, val)}
-want = ["Kernel Name", "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+want = ["Kernel Name", "gpu__time_duration.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct_of_peak_sustained_active", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+        "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "lts__t_sector_hit_rate.pct", "sm__warps_active.avg.per_cycle_active",
+        "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
         "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
         "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
@@ -46,13 +51,12 @@ if rd is not None and wr is not None:
     lines.append(f"traffic (dram read + write per launch) = {tot:.6g} bytes")
     if units:
         lines.append(f"traffic per RK step = {tot / units:.1f} bytes")
-fl = sum((num(f"smsp__sass_thread_inst_executed_op_{k}_pred_on.sum") or 0) * w for k, w in (("dfma", 2), ("dadd", 1), ("dmul", 1)))
 t = num("gpu__time_duration.sum")
+tms = None
 if t:
     tms = t * {"ms": 1.0, "us": 1e-3, "s": 1e3, "ns": 1e-6}.get(m["gpu__time_duration.sum"][1], 1.0)
-    lines.append(f"executed FP64 flop/s (DFMA x2 + DADD + DMUL, thread-level, under ncu clocks) = {fl / (tms * 1e-3) * 1e-12:.3f} TFLOP/s")
     if units:
-        lines.append(f"executed FP64 flops per RK step = {fl / units:.0f};  warp instructions per RK step = {num('smsp__inst_executed.sum') / units:.1f}")
+        lines.append(f"warp instructions per RK step = {num('smsp__inst_executed.sum') / units:.1f}")
 
 src = list(csv.reader(io.StringIO(ncu("source"))))
 h2, data = src[1], src[2:]
@@ -60,6 +64,20 @@ ix = {h: i for i, h in enumerate(h2)}
 tot = sum(int(r[ix["# Samples"]]) for r in data) or 1
 stalls = [h for h in h2 if h.startswith("stall_") and "Not Issued" not in h]
 agg = {s: sum(int(r[ix[s]]) for r in data) for s in stalls}
+# executed FP64 flops from the instruction-level counts: DFMA = 2 per thread, DADD / DMUL = 1, DMMA.8x8x4 = 512 per warp instruction
+ex_thr = collections.Counter(); ex_warp = collections.Counter()
+for r in data:
+    sp = r[ix["Source"]].strip().split()
+    op = (sp[1] if sp[0].startswith("@") else sp[0]).split(".")[0]
+    ex_warp[op] += int(r[ix["Instructions Executed"]])
+    ex_thr[op] += int(r[ix["Predicated-On Thread Instructions Executed"]])
+flops = 2 * ex_thr["DFMA"] + ex_thr["DADD"] + ex_thr["DMUL"] + 512 * ex_warp["DMMA"]
+if t:
+    lines.append(f"executed FP64 flops (source page: 2 x DFMA + DADD + DMUL thread-level, 512 per DMMA.8x8x4) = {flops:.4g} per launch "
+                 f"= {flops / (tms * 1e-3) * 1e-12:.2f} TFLOP/s under ncu clocks; DMMA share {512 * ex_warp['DMMA'] / max(flops, 1):.2f}")
+    if units:
+        lines.append(f"executed FP64 flops per RK step = {flops / units:.0f} (algorithmic: SURVEY 8d count, see bench.py roofline.flops_per_step); "
+                     f"DMMA warp instructions per RK step = {ex_warp['DMMA'] / units:.2f}")
 lines.append("\nstall mix (% of warp samples): " + ", ".join(f"{k[6:]} {100 * v / tot:.1f}" for k, v in sorted(agg.items(), key=lambda kv: -kv[1]) if v * 200 > tot))
 c = collections.Counter(); ti = 0
 for r in data:
