@@ -87,7 +87,7 @@ void register_mma2_one(const char* name, int priority) {
                                           MG::NFRAG * 32 * 8, MG::WARP_GRAD * 8, 1, 8 * NT, 1, priority,
                                           (const void*)ude_mma2_kernel<D, NX, HT, NT, SOLVER, LK, true, MINB, OPT, TB>, name});
   kernel_registry().push_back(KernelEntry{UDE_RHS_NODE, D, NX, D + NX, D, UDE_F64, G, HPLcap, SOLVER, LK, 0, MG::RECW / 32, 8, 0,
-                                          MG::NFRAG * 32 * 8, 0, 1, 8 * NT, 1, priority,
+                                          MG::NFRAG * 32 * 8, MG::WARP_FWD * 8, 1, 8 * NT, 1, priority,
                                           (const void*)ude_mma2_kernel<D, NX, HT, NT, SOLVER, LK, false, MINB, OPT, TB>, name});
 }
 template <int D, int NX, int HT, int NT, int MINB, int OPT = 0, int TB = 4>

@@ -29,6 +29,10 @@ enum { MMA2_PARK_GW = 1,      // park the weight-gradient accumulators in shared
                               // 32-byte sectors) instead of staging them in shared memory for a TMA bulk store: no
                               // fence.proxy.async / __syncwarp / wait_group per stage; the reverse sweep still bulk-loads
        MMA2_NO_PIN = 8,       // A/B: plain loads for the interval prefetch (ptxas sinks them to the use)
+       MMA2_SMEM_PF = 32,     // the one-interval-ahead prefetch of times / data / covariate knots goes global -> shared memory with
+                              // cp.async (LDGSTS) and is read back with LDS when needed, instead of living in registers: register
+                              // prefetches share the 6 scoreboards of a warp with every other pending load, so their consumers
+                              // still showed long_sb stalls (profiles/ncu_c3_mma2_r02b.txt, DSETP at the covariate check)
        MMA2_ROT = 16,         // A/B: round-1 [segment][hidden] tiles with the column rotated by 4*segment (dense rows, 11% less
                               // stash traffic) instead of rows padded by 4 doubles.  Padded rows make every shared-memory
                               // address of the stage loop "lane base + immediate": the rotation costs two integer
@@ -58,7 +62,10 @@ struct Mma2Geo : MmaGeo<D_, NX_, HT_, 1, 4> {
   static constexpr int SCR1 = 8 * HS + 64;             // z-bar tile + k-bar tile of one M tile
   static constexpr int NGW = (Base::MT + 1) * HT_ * 2 + 2;   // accumulator doubles per lane (GW1, GW2, gb2)
   static constexpr int PARK = (OPT_ & MMA2_PARK_GW) ? ((NGW * 32 > NT_ * SCR1) ? NGW * 32 - NT_ * SCR1 : 0) : 0;   // beyond the scratch tiles it aliases
-  static constexpr int WARP_GRAD = 2 * RECW + NT_ * SCR1 + PARK;
+  static constexpr int PFL = 1 + KSU + 3 * Base::NX;       // prefetch slots (doubles) per lane and tile: time, data, 3 per covariate
+  static constexpr int PFW = (OPT_ & 32) ? NT_ * 32 * PFL : 0;   // per warp
+  static constexpr int WARP_FWD = PFW;
+  static constexpr int WARP_GRAD = 2 * RECW + NT_ * SCR1 + PARK + PFW;
   static constexpr int NA = (NT_ == 1) ? HT_ : (HT_ >= 2 ? 2 : 1);   // accumulators per tile for K-long products
   static constexpr int TABN = (OPT_ & MMA2_TAB16) ? 64 * 16 : 64;
 };
@@ -75,12 +82,25 @@ __device__ __forceinline__ double ld_pf_opt(const double* p) {
   if constexpr (OPT & 8) return *p; else return ld_pf(p);
 }
 
+// ---- staged prefetch: an 8-byte global -> shared copy now, an LDS when the value is needed -------------------------------
+__device__ __forceinline__ void pf_issue(uint32_t saddr, const double* g) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void pf_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ double pf_read(uint32_t saddr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(saddr) : "memory");
+  return v;
+}
+
 // piecewise-linear covariate, referenced at the UPPER knot of the current interval:  x(t) = xhi + slope (t - vhi).
-// Flat extrapolation = slope 0.  (p_t, p_x, p_inv) describe the next interval and were loaded when this one was entered.
+// Flat extrapolation = slope 0.  The description of the NEXT interval is requested when this one is entered: into the
+// registers (p_t, p_x, p_inv) by default, into three shared-memory slots with MMA2_SMEM_PF (pf != 0).
 struct CovLin {
   double vhi, xhi, slope;
   double p_t, p_x, p_inv;
   int j, kend;               // absolute index of the interval's lower knot (kbeg - 1 before the first knot), end of the knots
+  uint32_t pf;               // shared-memory address of this lane's three prefetch slots (0: register prefetch)
 };
 constexpr double kCovBig = 1.0e300;
 
@@ -88,6 +108,10 @@ constexpr double kCovBig = 1.0e300;
 __device__ __forceinline__ void cov_prefetch(const DevProblem& P, CovLin& c, int jn) {
   const bool inner = jn + 1 < c.kend;
   const int ix = inner ? jn + 1 : c.kend - 1;
+  if (c.pf) {
+    pf_issue(c.pf, P.knot_t + ix); pf_issue(c.pf + 8, P.knot_x + ix); pf_issue(c.pf + 16, P.knot_inv + (inner ? jn : ix));
+    return;
+  }
   const double pt = ld_pf(P.knot_t + ix), px = ld_pf(P.knot_x + ix), pi = ld_pf(P.knot_inv + (inner ? jn : ix));
   c.p_t = inner ? pt : kCovBig;
   c.p_x = px;
@@ -95,8 +119,8 @@ __device__ __forceinline__ void cov_prefetch(const DevProblem& P, CovLin& c, int
 }
 
 // one search per segment (task start): the interval that holds t
-__device__ __forceinline__ void cov_init(const DevProblem& P, long long k0, int n, double t, CovLin& c) {
-  c.j = 0; c.kend = 0; c.vhi = kCovBig; c.xhi = 0.0; c.slope = 0.0; c.p_t = kCovBig; c.p_x = 0.0; c.p_inv = 0.0;
+__device__ __forceinline__ void cov_init(const DevProblem& P, long long k0, int n, double t, CovLin& c, uint32_t pf) {
+  c.j = 0; c.kend = 0; c.vhi = kCovBig; c.xhi = 0.0; c.slope = 0.0; c.p_t = kCovBig; c.p_x = 0.0; c.p_inv = 0.0; c.pf = pf;
   if (n <= 0) return;
   const int kbeg = (int)k0;
   c.kend = kbeg + n;
@@ -114,6 +138,12 @@ __device__ __forceinline__ void cov_init(const DevProblem& P, long long k0, int 
 
 __device__ __forceinline__ double cov_value(const DevProblem& P, CovLin& c, double t) {
   while (t >= c.vhi) {                        // stage times never decrease inside a forward sweep
+    if (c.pf) {                               // the request made when the current interval was entered has landed by now
+      pf_wait();
+      const bool inner = c.j + 2 < c.kend;    // the prefetched interval is j + 1
+      const double pt = pf_read(c.pf), px = pf_read(c.pf + 8), pi = pf_read(c.pf + 16);
+      c.p_t = inner ? pt : kCovBig; c.p_x = px; c.p_inv = inner ? pi : 0.0;
+    }
     c.slope = (c.p_x - c.xhi) * c.p_inv; c.xhi = c.p_x; c.vhi = c.p_t;
     ++c.j;
     cov_prefetch(P, c, c.j + 1);
@@ -230,10 +260,14 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) ude_mma2_kernel(const Dev
   // [n_pm + 1 (block partial) padded even][weight fragments][per warp: 2 stage records (NT tiles each) | NT scratch tiles (+ park)]
   double* s_red = s_dyn;
   double* s_w = s_dyn + (P.n_pm + 1 + 1) / 2 * 2;
-  constexpr int kPerWarp = GRAD ? MG::WARP_GRAD : 0;
+  constexpr int kPerWarp = GRAD ? MG::WARP_GRAD : MG::WARP_FWD;
+  constexpr bool SPF = (OPT & MMA2_SMEM_PF) != 0;
   double* s_warp = s_w + MG::NFRAG * 32 + (size_t)(threadIdx.x >> 5) * kPerWarp;
   double* s_stage = s_warp;
-  double* s_scr = s_warp + 2 * MG::RECW;
+  double* s_scr = s_warp + (GRAD ? 2 * MG::RECW : 0);
+  // MMA2_SMEM_PF: this lane's prefetch slots, [tile][lane][time | data (KSU) | 3 per covariate]
+  const uint32_t s_pf = SPF ? smem_u32(s_warp + (GRAD ? 2 * MG::RECW + NT * MG::SCR1 + MG::PARK : 0)) + (uint32_t)((threadIdx.x & 31) * MG::PFL * 8) : 0u;
+  auto pf_slot = [&](int tl, int k) -> uint32_t { return s_pf + (uint32_t)((tl * 32 * MG::PFL + k) * 8); };
   uint64_t* bar = s_bar[threadIdx.x >> 5];
 
   const int lane = threadIdx.x & 31;
@@ -368,12 +402,17 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) ude_mma2_kernel(const Dev
 #pragma unroll
     for (int tl = 0; tl < NT; ++tl) {
       tq0[tl] = P.times[c0[tl]];
-      tq1[tl] = P.times[c0[tl] + min(1, L[tl])];
+      if constexpr (SPF) { pf_issue(pf_slot(tl, 0), P.times + c0[tl] + min(1, L[tl])); tq1[tl] = 0.0; }
+      else tq1[tl] = P.times[c0[tl] + min(1, L[tl])];
 #pragma unroll
       for (int e = 0; e < KSU; ++e) {
         const int s = c + 4 * e;
         u[tl][e] = (s < D) ? (from_theta ? uh[(long long)D * c0[tl] + s] : P.data[(long long)D * c0[tl] + s]) : 0.0;
-        dq[tl][e] = (s < D && LK == LK_TRAJ) ? P.data[(long long)D * c0[tl] + s] : 0.0;
+        dq[tl][e] = 0.0;
+        if (s < D && LK == LK_TRAJ) {
+          if constexpr (SPF) pf_issue(pf_slot(tl, 1 + e), P.data + (long long)D * c0[tl] + s);
+          else dq[tl][e] = P.data[(long long)D * c0[tl] + s];
+        }
       }
     }
     CovLin cov[NT][NXA];
@@ -384,7 +423,7 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) ude_mma2_kernel(const Dev
         for (int v = 0; v < NX; ++v) {
           const long long k0 = P.knot_off[(long long)sg[tl].series * NX + v];
           const int n = (int)(P.knot_off[(long long)sg[tl].series * NX + v + 1] - k0);
-          cov_init(P, k0, n, tq0[tl] - eps, cov[tl][v]);
+          cov_init(P, k0, n, tq0[tl] - eps, cov[tl][v], SPF ? pf_slot(tl, 1 + KSU + 3 * v) : 0u);
         }
     }
 
@@ -396,6 +435,17 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) ude_mma2_kernel(const Dev
       for (int tl = 0; tl < NT; ++tl) { t0[tl] = tq0[tl] - eps; hs[tl] = is_null[tl] ? 0.0 : eps; }
       for (int k = 0; k < nsteps; ++k) {
         if (k >= pre && n == 0) {
+          if constexpr (SPF) {                 // what the previous event (or the task start) requested has landed
+            pf_wait();
+#pragma unroll
+            for (int tl = 0; tl < NT; ++tl) {
+              tq1[tl] = pf_read(pf_slot(tl, 0));
+              if (LK == LK_TRAJ) {
+#pragma unroll
+                for (int e = 0; e < KSU; ++e) if (c + 4 * e < D) dq[tl][e] = pf_read(pf_slot(tl, 1 + e));
+              }
+            }
+          }
 #pragma unroll
           for (int tl = 0; tl < NT; ++tl) {
             if (LK == LK_TRAJ) {
@@ -411,10 +461,14 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) ude_mma2_kernel(const Dev
             hs[tl] = (i < L[tl]) ? (tq1[tl] - tq0[tl]) * invS : 0.0;
             // loads for the NEXT interval: consumed a whole interval (S steps) from now
             tq0[tl] = tq1[tl];
-            tq1[tl] = ld_pf_opt<OPT>(P.times + c0[tl] + min(i + 2, L[tl]));
+            if constexpr (SPF) pf_issue(pf_slot(tl, 0), P.times + c0[tl] + min(i + 2, L[tl]));
+            else tq1[tl] = ld_pf_opt<OPT>(P.times + c0[tl] + min(i + 2, L[tl]));
             if (LK == LK_TRAJ) {
 #pragma unroll
-              for (int e = 0; e < KSU; ++e) if (c + 4 * e < D) dq[tl][e] = ld_pf_opt<OPT>(P.data + (long long)D * (c0[tl] + min(i + 1, L[tl])) + c + 4 * e);
+              for (int e = 0; e < KSU; ++e) if (c + 4 * e < D) {
+                const double* src = P.data + (long long)D * (c0[tl] + min(i + 1, L[tl])) + c + 4 * e;
+                if constexpr (SPF) pf_issue(pf_slot(tl, 1 + e), src); else dq[tl][e] = ld_pf_opt<OPT>(src);
+              }
             }
           }
           nd = 0.0;
@@ -512,6 +566,13 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) ude_mma2_kernel(const Dev
       }
     }
     // ------------------------------------------ loss at the last point ------------------------------------------------
+    if constexpr (SPF && LK == LK_TRAJ) {      // data at point min(maxL, L): requested by the last event (or at task start)
+      pf_wait();
+#pragma unroll
+      for (int tl = 0; tl < NT; ++tl)
+#pragma unroll
+        for (int e = 0; e < KSU; ++e) if (c + 4 * e < D) dq[tl][e] = pf_read(pf_slot(tl, 1 + e));
+    } else if constexpr (SPF) pf_wait();
     double lam[NT][KSU], gc[NT][KSU], gp[NT][KSU];
     // reverse-sweep prefetch registers: times of the interval being reversed, data column at its lower end
     double rt_lo[NT], rt_hi[NT], dr[NT][KSU];
@@ -587,16 +648,26 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) ude_mma2_kernel(const Dev
       for (int k = nsteps - 1; k >= 0; --k) {
         if (k >= pre) {
           if (n == S - 1) {
+            if constexpr (SPF) {
+              if (i != maxL - 1) {             // the lower time of this interval was requested when the one above started
+                pf_wait();
+#pragma unroll
+                for (int tl = 0; tl < NT; ++tl) { rt_hi[tl] = rt_lo[tl]; rt_lo[tl] = pf_read(pf_slot(tl, 0)); }
+              }
+            }
 #pragma unroll
             for (int tl = 0; tl < NT; ++tl) {
               hs[tl] = (i < L[tl]) ? (rt_hi[tl] - rt_lo[tl]) * invS : 0.0;
               // loads for the interval below and for this interval's lower-end data column (both used S steps from now)
               if (LK == LK_TRAJ) {
 #pragma unroll
-                for (int e = 0; e < KSU; ++e) if (c + 4 * e < D) dr[tl][e] = ld_pf_opt<OPT>(P.data + (long long)D * (c0[tl] + min(i, L[tl])) + c + 4 * e);
+                for (int e = 0; e < KSU; ++e) if (c + 4 * e < D) {
+                  const double* src = P.data + (long long)D * (c0[tl] + min(i, L[tl])) + c + 4 * e;
+                  if constexpr (SPF) pf_issue(pf_slot(tl, 1 + e), src); else dr[tl][e] = ld_pf_opt<OPT>(src);
+                }
               }
-              rt_hi[tl] = rt_lo[tl];
-              rt_lo[tl] = ld_pf_opt<OPT>(P.times + c0[tl] + min(max(i - 1, 0), L[tl]));
+              if constexpr (SPF) pf_issue(pf_slot(tl, 0), P.times + c0[tl] + min(max(i - 1, 0), L[tl]));
+              else { rt_hi[tl] = rt_lo[tl]; rt_lo[tl] = ld_pf_opt<OPT>(P.times + c0[tl] + min(max(i - 1, 0), L[tl])); }
             }
           }
         } else {
@@ -735,6 +806,13 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) ude_mma2_kernel(const Dev
         if (k >= pre) {
           if (n == 0) {
             if (LK == LK_TRAJ) {
+              if constexpr (SPF) {             // this interval's lower-end data column, requested S steps ago
+                pf_wait();
+#pragma unroll
+                for (int tl = 0; tl < NT; ++tl)
+#pragma unroll
+                  for (int e = 0; e < KSU; ++e) if (c + 4 * e < D) dr[tl][e] = pf_read(pf_slot(tl, 1 + e));
+              }
 #pragma unroll
               for (int tl = 0; tl < NT; ++tl) {
                 const double w = (i <= L[tl] && i >= first_scored) ? wpt[tl] : 0.0;
