@@ -105,7 +105,7 @@ def test_multinode_leave_future_out_and_kfold(ude):
     models, tr, te, fc, trace = ude.leave_future_out_batched(m, k=2, skip=1, loss_function="multiple shooting", optim_options=opts)
     assert len(fc) == 2 and set(fc[0]["series"]) == {"a", "b"} and np.all(np.isfinite(fc[1][["x1", "x2"]].to_numpy()))
     m1 = ude.NODE(df, hidden_units=10)
-    out = ude.kfold_cv(m1, lambda mi, ts: ude.train_(mi, "conditional likelihood", verbose=False, t_skip=ts, optim_options=dict(maxiter=2)), k=3)
+    out = ude.interval_holdout_cv(m1, lambda mi, ts: ude.train_(mi, "conditional likelihood", verbose=False, t_skip=ts, optim_options=dict(maxiter=2)), k=3)
     assert len(out) == 3 and np.all(np.isfinite(out["mean_absolute_error"]))
 
 

@@ -68,6 +68,18 @@ def test_default_loss_and_multi_reg_quirk(ude):
     assert abs(L[0] - ref) < 1e-11 * abs(ref)
 
 
+def test_t_skip_rules_differ_between_losses(ude):
+    """conditional_likelihood skips the interval whose 1-based END INDEX equals t_skip (LFC.jl:82); the default loss
+    UDE.loss_function(x, t_skip) skips intervals whose START TIME VALUE is in t_skip (src/helpers.jl:63)."""
+    df = _lv_frame(ude, n=12)
+    m = ude.NODE(df, hidden_units=4)
+    a = ude.conditional_likelihood(m, t_skip=5).skip_mask
+    assert a.sum() == 1 and a[4] == 1                                   # interval 4 -> 5 (1-based), stored at its end column
+    b = ude.default_loss(m, t_skip=[m.times[2], m.times[7], 123.0]).skip_mask
+    assert b.sum() == 2 and b[3] == 1 and b[8] == 1                     # intervals STARTING at times[2] and times[7]
+    assert ude.default_loss(m, t_skip=5).skip_mask.sum() == int(np.any(m.times[:-1] == 5.0))
+
+
 def test_shooting_and_multiple_shooting_builders(ude):
     df = _lv_frame(ude, n=16)
     m = ude.NODE(df, hidden_units=5)

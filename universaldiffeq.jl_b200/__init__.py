@@ -14,5 +14,5 @@ from .models import (CustomDerivatives, NODE, MultiNODE, MultiCustomDerivatives,
 from .training import (train_, adam_multi_gpu, gradient_descent_, marginal_likelihood_, spline_gradient_matching_, SplineGradientMatching, neural_gradient_matching_, NeuralGradientMatching, kalman_filter_, save_model_parameters, load_model_parameters_, conditional_likelihood, default_loss, multiple_shooting_loss, shooting_loss,  # noqa: F401
                        derivative_matching_loss, errors_to_matrix, build_problem, predictions, forecast, adam_host)
 from .cross_validation import (leave_future_out, leave_future_out_batched, leave_future_out_predict, summarize_leave_future_out,  # noqa: F401
-                               kfold_cv, stack_models, leave_site_out, energy_score, predict)
+                               interval_holdout_cv, stack_models, leave_site_out, energy_score, predict)
 from .simulate import LotkaVolterra, LorenzLotkaVolterra, simulate_coral_data  # noqa: F401

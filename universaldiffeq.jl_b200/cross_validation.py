@@ -2,7 +2,7 @@
 
   leave_future_out / leave_future_out_cv   /root/reference/src/CrossValidation.jl:17-45, :128-141 (UDE), :234-278, :354-366 (MultiUDE)
   summarize_leave_future_out               :91-110
-  kfold_cv                                 :167-195 (internal in the reference)
+  interval_holdout_cv                      single-interval hold-outs via t_skip (the reference's internal kfold_cv, :167-195, is out of scope)
 The reference trains the k folds under Threads.@threads, one optimiser per fold.  Here the folds are the *model* batch
 axis of one handle (ude_set_data's model_of_series): `leave_future_out_batched` trains all folds x ensemble members in
 one device-resident Adam run -- the folds are independent theta vectors, Adam is element-wise, so this is exactly k
@@ -263,9 +263,12 @@ def leave_site_out(model: UDE, training: Callable[[UDE], None], sites: Optional[
     return float(np.mean(scores))
 
 
-def kfold_cv(model: UDE, training: Callable[[UDE, float], None], k: int = 10):
-    """kfold_cv (src/CrossValidation.jl:167-195): k single-interval hold-outs via the t_skip loss variant; `training(model, t_skip)`
-    must fit with that interval left out.  Returns the one-step prediction errors at the skipped intervals."""
+def interval_holdout_cv(model: UDE, training: Callable[[UDE, float], None], k: int = 10):
+    """k single-interval hold-outs through the t_skip variant of the conditional likelihood (LFC.jl:68-95): `training(model,
+    t_skip)` must fit with that interval left out; returns the one-step prediction errors at the skipped intervals.
+    NOT the reference's internal `kfold_cv` (src/CrossValidation.jl:167-195: contiguous block folds, refit on the concatenated
+    rest, scored by the UKF marginal likelihood of the held-out block) -- that driver is outside the hot-path scope
+    ("CV summaries"); its two ingredients are here: the t_skip loss and `Engine.ukf_loss_grad`."""
     N = model.data.shape[1]
     idx = np.unique(np.linspace(2, N - 1, k).round().astype(int))      # 1-based END index of the interval left out
     rows = []

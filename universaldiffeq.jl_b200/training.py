@@ -37,11 +37,21 @@ def _n_series(model: UDE) -> int:
     return len(model.starts) if model.multi else 1
 
 
-def _skip_mask(model: UDE, t_skip):
+def _skip_mask(model: UDE, t_skip, by="index"):
+    """Column mask of the process terms left out.  The reference has TWO rules for single-series models:
+      by="index"  conditional_likelihood: `if t != t_skip` on the 1-based END index of the interval (LFC.jl:82);
+      by="time"   UDE.loss_function(x, t_skip) -- the default loss: `if !(times[t-1] in t_skip)`, i.e. intervals whose START
+                  TIME VALUE is in t_skip, a scalar or a collection (src/helpers.jl:63).
+    Multi-series models match start times per series in both (src/MultipleTimeSeries.jl:101)."""
     if t_skip is None or (np.isscalar(t_skip) and np.isnan(t_skip)):
         return None
     m = np.zeros(model.data.shape[1], dtype=np.uint8)
-    if not model.multi:
+    if not model.multi and by == "time":
+        tt = np.asarray(model.times)
+        for ts in np.atleast_1d(np.asarray(t_skip, dtype=np.float64)):
+            for j in np.nonzero(tt[:-1] == ts)[0]:
+                m[j + 1] = 1
+    elif not model.multi:
         # LFC.jl:82: the interval whose END index t (1-based) equals t_skip is left out
         idx = int(t_skip) - 1
         if 1 <= idx < m.shape[0]:
@@ -72,7 +82,7 @@ def default_loss(model: UDE, t_skip=None) -> P.Problem:
     p.proc_inv_dt = True
     p.obs_scale = model.weights["observation"] / model.obs_divisor
     p.proc_scale = model.T * model.weights["process"] / float(model.N) ** 2
-    p.skip_mask = _skip_mask(model, t_skip)
+    p.skip_mask = _skip_mask(model, t_skip, by="time")
     # multi-series: the regulariser sits inside single_loss and is counted once per series (src/MultipleTimeSeries.jl:77-79)
     p.reg_weight = model.weights["regularization"] * _n_series(model)
     return p.finalize()
