@@ -307,6 +307,26 @@ def test_parity_fp32_mode(ude, rhs, hidden, loss):
         assert cases.relerr(g, g_ref) < TOL32, cases.relerr(g, g_ref)
 
 
+@pytest.mark.parametrize("loss", ["cond_lik", "mse", "multi_shoot", "multi_shoot_preroll", "shoot_theta", "shoot_data"])
+def test_parity_fp32_tensor_core_kernel(ude, loss):
+    """FP32 mode on the wide NODE (C5 shape, d = 8): the 3xTF32 tensor-core kernel (csrc/ude_kernel_tf32.cuh, 16 segments per
+    block, hidden layer split over four warps) against the FP64 oracle at the FP32-mode bar, per gradient leaf; ragged series,
+    hidden widths below the padded 128, both solvers, and the forward-only trajectories."""
+    for solver in (0, 1):
+        for hidden, lengths, substeps in ((128, (14, 1, 9, 2, 30, 6, 11, 3, 3, 5, 17, 8, 2, 2, 4, 6, 7, 9, 1, 12), 2), (100, (5, 4, 3), 3), (9, (6,) * 37, 1)):
+            prob, theta = cases.make_case("node_d8", loss, solver, hidden=hidden, lengths=lengths, substeps=substeps,
+                                          skip=(loss in ("cond_lik", "mse")))
+            L_ref, g_ref = oracle.loss_grad(prob, theta)
+            with ude.Engine(prob, dtype=1) as eng:
+                assert "tf32" in eng.kernel_name()
+                L, g = eng.loss_grad(theta)
+                out = eng.forward(theta)
+            assert np.max(np.abs(L - L_ref) / np.abs(L_ref)) < TOL32, (L, L_ref)
+            assert cases.grad_mismatch(prob, g, g_ref, rtol=TOL32, floor=1e-1)[0] <= 1.0, cases.grad_mismatch(prob, g, g_ref, rtol=TOL32, floor=1e-1)
+            assert np.all(g[g_ref == 0.0] == 0.0)
+            assert cases.relerr(out, oracle.forward(prob, theta)) < TOL32
+
+
 @pytest.mark.parametrize("name", ["c2", "c3", "c4", "c5"])
 def test_full_size_configs_sampled_and_additive(ude, name):
     """BASELINE.json's configurations at FULL size (C2 10^4 series, C3 10^5 series, C4 10^4 models, C5 10^6 segments),

@@ -101,6 +101,7 @@ struct ude_handle {
   std::vector<double> obs_scale, proc_scale, shoot_weight, reg_weight;
   bool have_data = false, have_cov = false, have_targets = false, dirty = true;
   bool sparse_uhat_io = false;          // UDE_OPT_SPARSE_UHAT_IO
+  double* h_stage = nullptr; size_t h_stage_n = 0;       // pinned [loss | process-model gradient] staging: one D2H copy per call
   bool ukf_causal = false;              // UDE_OPT_UKF_CAUSAL_INTERVAL
   int64_t last_h2d = 0, last_d2h = 0, n_segments = 0;
   // device buffers
@@ -798,6 +799,7 @@ int ude_destroy(ude_handle* h) {
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   for (int r = 0; r < UDE_MAX_PEERS; ++r) if (h->x_opened[r] && h->x_peer[r]) cudaIpcCloseMemHandle(h->x_peer[r]);
   if (h->x_local) cudaFree(h->x_local);
+  if (h->h_stage) cudaFreeHost(h->h_stage);
   if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
   if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
   if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
@@ -982,6 +984,7 @@ int ude_loss_grad(ude_handle* h, const double* theta, int64_t n_theta, double* l
   const double* z_theta = nullptr; double* z_grad = nullptr;
   if (grad && h->sparse_uhat_io && h->n_models == 1 &&
       (h->desc.loss_kind == UDE_LOSS_MULTI_SHOOT || h->desc.loss_kind == UDE_LOSS_SHOOT)) {
+    // queried on every call: a cached answer would go stale if the caller frees a pinned buffer and reuses the address
     cudaPointerAttributes at{}, ag{};
     if (cudaPointerGetAttributes(&at, theta) == cudaSuccess && cudaPointerGetAttributes(&ag, grad) == cudaSuccess &&
         at.type == cudaMemoryTypeHost && ag.type == cudaMemoryTypeHost && at.devicePointer && ag.devicePointer) {
@@ -993,15 +996,33 @@ int ude_loss_grad(ude_handle* h, const double* theta, int64_t n_theta, double* l
     const int d = h->desc.d;
     const size_t pmb = (size_t)d * h->n_cols, npm = (size_t)h->desc.n_pm;
     double* dth = h->d_theta.p; double* dg = h->d_grad.p;
+    if (h->h_stage_n < npm + 1) {
+      if (h->h_stage) cudaFreeHost(h->h_stage);
+      h->h_stage = nullptr; h->h_stage_n = 0;
+      UDE_CUDA_TRY(h, cudaMallocHost((void**)&h->h_stage, (npm + 1) * sizeof(double)));
+      h->h_stage_n = npm + 1;
+    }
     UDE_CUDA_TRY(h, cudaMemcpyAsync(dth + pmb, theta + pmb, npm * sizeof(double), cudaMemcpyHostToDevice, s));
-    UDE_CUDA_TRY(h, cudaMemsetAsync(dg + pmb, 0, npm * sizeof(double), s));      // the per-series tail is accumulated by atomics
+    if (h->desc.has_series_param)                                              // the per-series tail is accumulated by atomics
+      UDE_CUDA_TRY(h, cudaMemsetAsync(dg + pmb, 0, npm * sizeof(double), s));
     int rc = launch_segments(h, dth, dg, nullptr, 0, h->n_tasks, 0, s, z_theta, z_grad);
     if (rc != UDE_OK) return rc;
-    rc = finalize_eval(h, dth, h->d_loss.p, dg, h->grid_grad, s);
-    if (rc != UDE_OK) return rc;
-    UDE_CUDA_TRY(h, cudaMemcpyAsync(loss, h->d_loss.p, sizeof(double), cudaMemcpyDeviceToHost, s));
-    UDE_CUDA_TRY(h, cudaMemcpyAsync(grad + pmb, dg + pmb, npm * sizeof(double), cudaMemcpyDeviceToHost, s));
-    UDE_CUDA_TRY(h, cudaStreamSynchronize(s));
+    if (!h->desc.has_series_param) {
+      // finalize writes [loss | process-model gradient] into ONE contiguous device buffer (d_red): the gradient pointer is
+      // biased so that finalize's `grad + pmb` lands on d_red + 1; one device-to-host copy into pinned staging per call
+      rc = finalize_eval(h, dth, h->d_red.p, h->d_red.p + 1 - (ptrdiff_t)pmb, h->grid_grad, s);
+      if (rc != UDE_OK) return rc;
+      UDE_CUDA_TRY(h, cudaMemcpyAsync(h->h_stage, h->d_red.p, (npm + 1) * sizeof(double), cudaMemcpyDeviceToHost, s));
+      UDE_CUDA_TRY(h, cudaStreamSynchronize(s));
+      loss[0] = h->h_stage[0];
+      memcpy(grad + pmb, h->h_stage + 1, npm * sizeof(double));
+    } else {
+      rc = finalize_eval(h, dth, h->d_loss.p, dg, h->grid_grad, s);
+      if (rc != UDE_OK) return rc;
+      UDE_CUDA_TRY(h, cudaMemcpyAsync(loss, h->d_loss.p, sizeof(double), cudaMemcpyDeviceToHost, s));
+      UDE_CUDA_TRY(h, cudaMemcpyAsync(grad + pmb, dg + pmb, npm * sizeof(double), cudaMemcpyDeviceToHost, s));
+      UDE_CUDA_TRY(h, cudaStreamSynchronize(s));
+    }
     const bool reads_uhat = h->desc.loss_kind == UDE_LOSS_MULTI_SHOOT || h->desc.shoot_from_theta;
     const int64_t cols = reads_uhat ? h->n_segments : 0;
     h->last_h2d = 8 * ((int64_t)d * cols + (int64_t)npm);

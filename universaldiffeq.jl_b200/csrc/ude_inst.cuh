@@ -4,6 +4,7 @@
 #include "ude_kernel.cuh"
 #include "ude_kernel_mma.cuh"
 #include "ude_kernel_mma2.cuh"
+#include "ude_kernel_tf32.cuh"
 #include "ude_registry.h"
 
 namespace ude {
@@ -101,5 +102,26 @@ void register_mma2_combo(const char* name, int priority) {
 template <int D, int NX, int HT, int NT, int MINB, int OPT = 0, int TB = 4>
 void register_mma2_probe(const char* name, int priority) {
   register_mma2_one<D, NX, HT, NT, MINB, 0, LK_TRAJ, OPT, TB>(name, priority);
+}
+
+// FP32-mode tensor-core kernel (ude_kernel_tf32.cuh): NODE d = 8, hidden <= 32 * HTW, 16 segments per block-task, the hidden
+// layer split over the block's four warps; state-space and trajectory loss families
+template <int D, int HTW, int MINB, int SOLVER, int LK>
+void register_tf32_one(const char* name, int priority) {
+  using TG = Tf32Geo<D, HTW>;
+  const int G = 4, HPLcap = 2 * HTW * TG::HW;
+  kernel_registry().push_back(KernelEntry{UDE_RHS_NODE, D, 0, D, D, UDE_F32, G, HPLcap, SOLVER, LK, 1, TG::REC / 32, 4, 0,
+                                          TG::BLOCK_BYTES, TG::WARP_F * 4, 1, 16, TG::HW, priority,
+                                          (const void*)ude_tf32_kernel<D, HTW, SOLVER, LK, true, MINB>, name});
+  kernel_registry().push_back(KernelEntry{UDE_RHS_NODE, D, 0, D, D, UDE_F32, G, HPLcap, SOLVER, LK, 0, TG::REC / 32, 4, 0,
+                                          TG::BLOCK_BYTES, 0, 1, 16, TG::HW, priority,
+                                          (const void*)ude_tf32_kernel<D, HTW, SOLVER, LK, false, MINB>, name});
+}
+template <int D, int HTW, int MINB>
+void register_tf32_combo(const char* name, int priority) {
+  register_tf32_one<D, HTW, MINB, 0, LK_STATE>(name, priority);
+  register_tf32_one<D, HTW, MINB, 0, LK_TRAJ>(name, priority);
+  register_tf32_one<D, HTW, MINB, 1, LK_STATE>(name, priority);
+  register_tf32_one<D, HTW, MINB, 1, LK_TRAJ>(name, priority);
 }
 }  // namespace ude
