@@ -30,10 +30,22 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], 
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+// x = hi + lo with hi the top 10 mantissa bits (truncated) and lo the exact remainder.  The tensor core reads only the TF32
+// part of an FP32 register (the low 13 mantissa bits are ignored), so lo needs no conversion: 2 instructions per split
+// (LOP3 + FADD).  `cvt.rna.tf32.f32` is emulated on sm_100a with FSETP / LOP3 / IADD / SEL sequences -- the round-1 profile of
+// this kernel (profiles/ncu_c5_tf32_r02c.txt) had FSETP alone at 14 % of the issued instructions.  Truncation instead of
+// round-to-nearest costs one bit: 2^-21 per operand instead of 2^-22.
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
-  const float r = x - __uint_as_float(hi);
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+  hi = __float_as_uint(x) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
+}
+// FP32 tanh for this kernel: 1 - 2 / (exp(2|x|) + 1) with ex2.approx and rcp.approx (absolute error ~1e-7; the FP32-mode
+// bar is 1e-4): 6 instructions instead of ude_tanhf's ~20.  exp overflow -> inf -> rcp 0 -> 1, no clamp needed.
+__device__ __forceinline__ float tf_tanhf(float x) {
+  float e, y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fabsf(x) * 2.8853900817779268f));      // 2 log2(e)
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(e + 1.0f));
+  return copysignf(fmaf(-2.0f, y, 1.0f), x);
 }
 // c += A B, A given in FP32 (split here), B pre-split: small terms first
 __device__ __forceinline__ void mma3(float (&c)[4], const float (&a)[4], const uint4 b /* b0hi b1hi b0lo b1lo */) {
@@ -182,7 +194,7 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) ude_tf32_kernel(const Dev
 #pragma unroll
     for (int j = 0; j < HTW; ++j)
 #pragma unroll
-      for (int q = 0; q < 4; ++q) h[j][q] = ude_tanhf(h[j][q]);
+      for (int q = 0; q < 4; ++q) h[j][q] = tf_tanhf(h[j][q]);
     float yc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int j = 0; j < HTW; ++j) {
@@ -342,6 +354,20 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) ude_tf32_kernel(const Dev
           }
         }
         __syncwarp();
+      }
+    }
+    // the next task's first columns: bring their lines into L2 now (its segment entries were requested at this task's start)
+#pragma unroll
+    for (int tl = 0; tl < 2; ++tl) {
+      const long long cn = (LK == LK_STATE && !(nxt[tl].flags & SEG_NO_PREV)) ? nxt[tl].col - 1 : nxt[tl].col;
+      if (t == 0) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(P.times + cn));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(P.data + (long long)D * cn));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(uh + (long long)D * cn));
+        if (LK == LK_STATE) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(P.data + (long long)D * (cn + 1)));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(uh + (long long)D * (cn + 1)));
+        }
       }
     }
     // ------------------------------------------ loss at the last point ------------------------------------------------
