@@ -3,8 +3,7 @@
 namespace {
 using namespace ude;
 RegisterKernels reg([] {
+  register_mma2_probe<4, 1, 4, 1, 3, MMA2_PARK_GW | MMA2_TAB16>("node_d4x1_mma2_h32_p1_noaff", 9);
   register_mma2_probe<4, 1, 4, 1, 3, MMA2_PARK_GW | MMA2_TAB16 | MMA2_SMEM_PF>("node_d4x1_mma2_h32_p1_spf", 9);
-  register_mma2_probe<4, 1, 4, 1, 4, MMA2_PARK_GW | MMA2_SMEM_PF>("node_d4x1_mma2_h32_p1_spfb4", 9);
-  register_mma2_probe<4, 1, 4, 2, 2, MMA2_PARK_GW | MMA2_TAB16 | MMA2_SMEM_PF>("node_d4x1_mma2_h32_p2_spf", 9);
 });
 }  // namespace

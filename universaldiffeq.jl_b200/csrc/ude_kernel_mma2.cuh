@@ -33,6 +33,9 @@ enum { MMA2_PARK_GW = 1,      // park the weight-gradient accumulators in shared
                               // cp.async (LDGSTS) and is read back with LDS when needed, instead of living in registers: register
                               // prefetches share the 6 scoreboards of a warp with every other pending load, so their consumers
                               // still showed long_sb stalls (profiles/ncu_c3_mma2_r02b.txt, DSETP at the covariate check)
+       MMA2_AFFINE = 64,      // D a multiple of 4: the covariate and constant-1 input slots leave the layer-1 MMA (they would cost a
+                              // whole extra k-step for 1 + NX useful slots of 4); the accumulator starts at b1 + sum_q x_q W1[:, D+q]
+                              // instead (NX DFMAs per hidden unit, weights read as LDS.128 pairs): 4 DMMAs -> 8 DFMAs per stage
        MMA2_ROT = 16,         // A/B: round-1 [segment][hidden] tiles with the column rotated by 4*segment (dense rows, 11% less
                               // stash traffic) instead of rows padded by 4 doubles.  Padded rows make every shared-memory
                               // address of the stage loop "lane base + immediate": the rotation costs two integer
@@ -68,6 +71,8 @@ struct Mma2Geo : MmaGeo<D_, NX_, HT_, 1, 4> {
   static constexpr int WARP_GRAD = 2 * RECW + NT_ * SCR1 + PARK + PFW;
   static constexpr int NA = (NT_ == 1) ? HT_ : (HT_ >= 2 ? 2 : 1);   // accumulators per tile for K-long products
   static constexpr int TABN = (OPT_ & MMA2_TAB16) ? 64 * 16 : 64;
+  static constexpr bool AFF = (OPT_ & 64) != 0 && D_ == 4 * KSU && KSU < Base::KS;
+  static constexpr int NAFF = AFF ? (Base::NX + 1) * 8 * HT_ : 2;        // [bias | covariate columns][hidden]
 };
 
 // loads whose value is first needed an observation interval later: `volatile` pins the load where it is written (ptxas
@@ -193,18 +198,35 @@ __device__ __forceinline__ void tanh_batches(double (&v)[N], const double* s_tab
 template <class MG>
 __device__ __forceinline__ void mma2_stage_forward(const double* __restrict__ s_w, const double* s_tab, int lane,
                                                    const double (&xs)[MG::NT][MG::KS], const double (&b2own)[2],
-                                                   double (&h)[MG::NT][MG::HT][2], double (&y)[MG::NT][2]) {
-  constexpr int NT = MG::NT, HT = MG::HT, KS = MG::KS, NA = MG::NA;
+                                                   double (&h)[MG::NT][MG::HT][2], double (&y)[MG::NT][2],
+                                                   const double* s_aff, const double (&X)[MG::NT][MG::NXA]) {
+  constexpr int NT = MG::NT, HT = MG::HT, KS = MG::AFF ? MG::KSU : MG::KS, NA = MG::NA;
   double z[NT][HT][2];
+  if constexpr (MG::AFF) {
+    // lane (r, c) owns hidden units 8t + 2c, 8t + 2c + 1 of segment r
+#pragma unroll
+    for (int t = 0; t < HT; ++t) {
+      const double2 b = *reinterpret_cast<const double2*>(s_aff + 8 * t + 2 * (lane & 3));
+#pragma unroll
+      for (int tl = 0; tl < NT; ++tl) { z[tl][t][0] = b.x; z[tl][t][1] = b.y; }
+#pragma unroll
+      for (int q = 0; q < MG::NX; ++q) {
+        const double2 w = *reinterpret_cast<const double2*>(s_aff + (q + 1) * 8 * HT + 8 * t + 2 * (lane & 3));
+#pragma unroll
+        for (int tl = 0; tl < NT; ++tl) { z[tl][t][0] = fma(X[tl][q], w.x, z[tl][t][0]); z[tl][t][1] = fma(X[tl][q], w.y, z[tl][t][1]); }
+      }
+    }
+  } else {
 #pragma unroll
   for (int tl = 0; tl < NT; ++tl)
 #pragma unroll
     for (int t = 0; t < HT; ++t) { z[tl][t][0] = 0.0; z[tl][t][1] = 0.0; }
+  }
 #pragma unroll
   for (int e = 0; e < KS; ++e) {
 #pragma unroll
     for (int t = 0; t < HT; ++t) {
-      const double bf = s_w[(t * KS + e) * 32 + lane];
+      const double bf = s_w[(t * MG::KS + e) * 32 + lane];
 #pragma unroll
       for (int tl = 0; tl < NT; ++tl) dmma(z[tl][t], xs[tl][e], bf);
     }
@@ -256,6 +278,7 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) ude_mma2_kernel(const Dev
   constexpr int D = D_, NX = NX_, HT = HT_, NT = NT_, KS = MG::KS, KSU = MG::KSU, NXA = MG::NXA, NA = MG::NA;
   __shared__ double s_tab[MG::TABN];
   __shared__ __align__(8) uint64_t s_bar[kBlockThreads / 32][2];
+  __shared__ __align__(16) double s_aff[MG::NAFF];
   extern __shared__ __align__(16) double s_dyn[];
   // [n_pm + 1 (block partial) padded even][weight fragments][per warp: 2 stage records (NT tiles each) | NT scratch tiles (+ park)]
   double* s_red = s_dyn;
@@ -284,6 +307,11 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) ude_mma2_kernel(const Dev
   for (long long k = threadIdx.x; k <= P.n_pm; k += blockDim.x) s_red[k] = 0.0;
   const double* __restrict__ pm = P.theta + (long long)D * P.model_col0[1];        // single model: [uhat | pm]
   build_frags<typename MG::Base>(P, pm, s_w);
+  if constexpr (MG::AFF)
+    for (int k = threadIdx.x; k < MG::NAFF; k += blockDim.x) {
+      const int q = k / (8 * HT), j = k % (8 * HT);             // q = 0: b1 (slot D + NX), q >= 1: covariate q - 1 (slot D + q - 1)
+      s_aff[k] = w1_slot<typename MG::Base>(P, pm, j, q == 0 ? D + NX : D + q - 1);
+    }
   if (GRAD && lane == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); }
   uint32_t bar_phase = 0;
   __syncthreads();
@@ -502,7 +530,7 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) ude_mma2_kernel(const Dev
             }
             make_xs(U, X[tl], xs[tl]);
           }
-          mma2_stage_forward<MG>(s_w, s_tab, lane, xs, b2own, h, y);
+          mma2_stage_forward<MG>(s_w, s_tab, lane, xs, b2own, h, y, s_aff, X);
           if (GRAD && (OPT & MMA2_DIRECT_ST)) {
             // stage record straight from the registers to the stash, in the layout the reverse sweep bulk-loads
             double* __restrict__ grec = stash + (long long)(k * T::S + st) * MG::RECW;
