@@ -206,14 +206,18 @@ int ude_adam_used_graph(const ude_handle* h);
  *   loss = - sum_series sum_t loglik_t + reg * (|W1|^2 + |W2|^2),  P_nu = F F' with F = pnu_factor (d x d, column-major),
  * identity observation model, P_eta fixed, first state = first observation (as the reference).  uhat does not enter the
  * loss (its gradient is returned as zeros).  The 2d+1 sigma-point predicts of every step run through the same fused RK
- * kernels as the other losses.  One model per handle, no per-series parameter vector. */
+ * kernels as the other losses.  Many-model handles (folds x ensemble members, ude_set_data's
+ * model_of_series) are filtered in the same launches: `loss` then holds n_models values, `pnu_factor` / `grad_pnu_factor`
+ * n_models blocks of d*d (one process-noise factor per model), alpha / beta / kappa / reg / Peta are shared.  MultiUDE's
+ * diagonal form P_nu = I .* p.^2 (src/UnscentedKalmanFilter.jl:123) is F = diag(p).  No per-series parameter vector. */
 typedef struct ude_ukf_opts {
   double alpha, beta, kappa;                 /* reference defaults 1e-3, 2, 0 (src/Optimizers.jl:408) */
   double reg;                                /* total weight of (|W1|^2 + |W2|^2) */
   double Peta[UDE_MAX_D * UDE_MAX_D];        /* observation covariance, d x d column-major */
 } ude_ukf_opts;
 int ude_ukf_loss_grad(ude_handle* h, const ude_ukf_opts* opts, const double* theta, int64_t n_theta, const double* pnu_factor,
-                      double* loss, double* grad_theta /* n_theta or NULL */, double* grad_pnu_factor /* d*d or NULL */);
+                      double* loss /* n_models */, double* grad_theta /* n_theta or NULL */,
+                      double* grad_pnu_factor /* n_models * d*d or NULL */);
 /* ukf_smoothing: filtered means (d x n_cols) and covariances (d x d x n_cols, may be NULL; zero at a series' first column) */
 int ude_ukf_filter(ude_handle* h, const ude_ukf_opts* opts, const double* theta, int64_t n_theta, const double* pnu_factor,
                    double* states, double* covariances);

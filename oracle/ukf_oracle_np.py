@@ -107,19 +107,29 @@ def filter_series(p, pm, s, Pnu, Peta, alpha, beta, kappa, dtype=float, causal=F
     return ll, xs, Ps
 
 
-def loss(p, theta, pnu, Peta, alpha=1e-3, beta=2.0, kappa=0.0, reg_weight=0.0, reg_mult=1.0, causal=False):
+def _model_range(p, model):
+    """(offset of the process model inside theta, first series, end series) of `model` (None: single-model problem)"""
+    if model is None:
+        return p.d * p.n_cols, 0, p.n_series
+    return (int(p.theta_base[model]) + p.d * int(p.model_col0[model + 1] - p.model_col0[model]),
+            int(p.model_series0[model]), int(p.model_series0[model + 1]))
+
+
+def loss(p, theta, pnu, Peta, alpha=1e-3, beta=2.0, kappa=0.0, reg_weight=0.0, reg_mult=1.0, causal=False, model=None):
     """-sum_series loglik + reg_mult * reg_weight * (|W1|^2 + |W2|^2).  theta = [uhat | process_model] of a single-model
-    problem (uhat does not enter); pnu = d x d factor with P_nu = pnu pnu^T.  reg_mult = 1 (UDE) or n_series + 1 (MultiUDE)."""
+    problem (uhat does not enter); pnu = d x d factor with P_nu = pnu pnu^T.  reg_mult = 1 (UDE) or n_series + 1 (MultiUDE).
+    model = m: the loss of model m of a many-model problem (its own series, its own theta block; pnu is that model's factor)."""
     theta = np.asarray(theta); pnu = np.asarray(pnu)
     dtype = complex if (np.iscomplexobj(theta) or np.iscomplexobj(pnu)) else (np.longdouble if theta.dtype == np.longdouble else float)
     if dtype is np.longdouble:
         Peta = np.asarray(Peta, dtype=np.longdouble); pnu = pnu.astype(np.longdouble)
     d = p.d
-    pm = theta[d * p.n_cols: d * p.n_cols + p.n_pm]
+    off, s0, s1 = _model_range(p, model)
+    pm = theta[off: off + p.n_pm]
     Lf = pnu.reshape(d, d, order="F")
     Pnu = Lf @ Lf.T
     tot = 0
-    for s in range(p.n_series):
+    for s in range(s0, s1):
         tot = tot - filter_series(p, pm, s, Pnu, Peta, alpha, beta, kappa, dtype, causal=causal)[0]
     w1 = pm[p.off_w1:p.off_w1 + p.nn_hidden * p.nn_in]; w2 = pm[p.off_w2:p.off_w2 + p.nn_out * p.nn_hidden]
     return tot + reg_mult * reg_weight * (np.sum(w1 * w1) + np.sum(w2 * w2))
@@ -128,7 +138,7 @@ def loss(p, theta, pnu, Peta, alpha=1e-3, beta=2.0, kappa=0.0, reg_weight=0.0, r
 def complex_step_grad(p, theta, pnu, Peta, eps=1e-30, **kw):
     """(d loss / d process_model, d loss / d pnu) by complex step."""
     d = p.d
-    n_u = d * p.n_cols
+    n_u = _model_range(p, kw.get("model"))[0]
     g_pm = np.zeros(p.n_pm); g_nu = np.zeros(d * d)
     th = np.asarray(theta, dtype=complex); pv = np.asarray(pnu, dtype=complex).reshape(-1, order="F")
     for k in range(p.n_pm):

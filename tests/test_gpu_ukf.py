@@ -190,3 +190,59 @@ def test_ukf_against_committed_fixtures(ude):
         assert abs(L - gold[key + "|loss"][0]) < tl * abs(L)
         assert cases.relerr(g[prob.d * prob.n_cols:], gold[key + "|g_pm"]) < tg
         assert cases.relerr(gF.reshape(-1, order="F"), gold[key + "|g_F"]) < tg
+
+
+@pytest.mark.parametrize("rhs,hidden,lengths,n_models", [("node_d2", 5, (7, 4, 3, 2, 6, 5), 3), ("node_time_d3", 4, (5, 3, 4), 3),
+                                                         ("node_d4x1", 6, (4, 6, 5, 2), 2), ("lv_ude_abs", 4, (3, 1, 6, 6), 2)])
+@pytest.mark.parametrize("solver", [0, 1])
+def test_ukf_many_models(ude, rhs, hidden, lengths, n_models, solver):
+    """Many-model handle (folds x ensemble members): every model is filtered in the same launches, with its own process model
+    and its own process-noise factor; a model whose series are shorter drops out of the later filter steps.  Each model
+    against the single-model twin (loss, complex-step gradients), and against the same model in a handle of its own."""
+    prob, theta = cases.make_case(rhs, "cond_lik", solver, hidden=hidden, lengths=lengths, n_models=n_models, seed=3)
+    d = prob.d
+    rng = np.random.default_rng(11)
+    Fs = np.stack([0.3 * np.eye(d) + 0.05 * rng.normal(size=(d, d)) for _ in range(n_models)])
+    Peta = 0.1 * np.eye(d) + 0.02 * np.ones((d, d))
+    with ude.Engine(prob) as eng:
+        L, g, gF = eng.ukf_loss_grad(theta, Fs, Peta, alpha=1.0, reg=2e-3)
+        L0, _, _ = eng.ukf_loss_grad(theta, Fs, Peta, alpha=1.0, reg=2e-3, want_grad=False)
+        xs, Ps = eng.ukf_filter(theta, Fs, Peta, alpha=1.0)
+    assert L.shape == (n_models,) and gF.shape == (n_models, d, d) and np.array_equal(L0, L)
+    touched = np.zeros(prob.n_theta, dtype=bool)
+    for m in range(n_models):
+        ref = ukf.loss(prob, theta, Fs[m], Peta, alpha=1.0, reg_weight=1e-3, reg_mult=2.0, model=m)
+        g_pm, g_F = ukf.complex_step_grad(prob, theta, Fs[m], Peta, alpha=1.0, reg_weight=1e-3, reg_mult=2.0, model=m)
+        off = ukf._model_range(prob, m)[0]
+        assert abs(L[m] - ref) < 1e-10 * abs(ref), m
+        assert cases.relerr(g[off:off + prob.n_pm], g_pm) < 1e-10, m
+        assert cases.relerr(gF[m].reshape(-1, order="F"), g_F) < 1e-10, m
+        touched[off:off + prob.n_pm] = True
+        for s in range(int(prob.model_series0[m]), int(prob.model_series0[m + 1])):
+            pm = theta[off:off + prob.n_pm]
+            _, xr, Pr = ukf.filter_series(prob, pm, s, Fs[m] @ Fs[m].T, Peta, 1.0, 2.0, 0.0)
+            c0, n = int(prob.starts[s]), int(prob.lengths[s])
+            assert cases.relerr(xs[:, c0:c0 + n], xr) < 1e-10
+            if n > 1:
+                assert cases.relerr(Ps[:, :, c0:c0 + n], Pr) < 1e-10
+    assert np.all(g[~touched] == 0.0)
+
+
+def test_ukf_many_models_shared_factor_equals_single_handles(ude):
+    """one (d, d) factor broadcast to every model; each model equals the same data in a handle of its own to round-off"""
+    prob, theta = cases.make_case("node_d2", "cond_lik", 0, hidden=5, lengths=(6, 4, 5, 7), n_models=2, seed=5)
+    d = prob.d
+    F = 0.25 * np.eye(d); Peta = 0.1 * np.eye(d)
+    with ude.Engine(prob) as eng:
+        L, g, gF = eng.ukf_loss_grad(theta, F, Peta, alpha=1.0)
+    for m in range(2):
+        sub, th = cases.make_case("node_d2", "cond_lik", 0, hidden=5, lengths=(6, 4, 5, 7)[2 * m:2 * m + 2], seed=5)
+        s0, s1 = int(prob.model_series0[m]), int(prob.model_series0[m + 1])
+        c0, c1 = int(prob.model_col0[m]), int(prob.model_col0[m + 1])
+        sub.data = np.asfortranarray(np.asarray(prob.data)[:, c0:c1]); sub.times = np.asarray(prob.times)[c0:c1].copy()
+        sub.finalize()
+        lo = int(prob.theta_base[m]); hi = lo + d * (c1 - c0) + prob.n_pm
+        with ude.Engine(sub) as eng:
+            L1, g1, gF1 = eng.ukf_loss_grad(theta[lo:hi], F, Peta, alpha=1.0)
+        assert abs(L[m] - L1) <= 1e-12 * abs(L1)
+        assert cases.relerr(g[lo:hi], g1) < 1e-11 and cases.relerr(gF[m], gF1) < 1e-11

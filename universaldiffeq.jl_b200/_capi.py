@@ -352,30 +352,43 @@ class Engine:
                 o.Peta[i + d * j] = Pe[i, j]
         return o
 
+    def _ukf_factor(self, pnu_factor):
+        """(M, d, d) process-noise factors as column-major bytes per model; a single (d, d) factor is shared by every model"""
+        d, M = self.problem.d, self.problem.n_models
+        F = np.asarray(pnu_factor, dtype=np.float64)
+        F = np.broadcast_to(F.reshape(-1, d, d), (M, d, d)) if F.size == d * d else F.reshape(M, d, d)
+        return np.ascontiguousarray(F.transpose(0, 2, 1))
+
     def ukf_loss_grad(self, theta, pnu_factor, Peta, alpha=1e-3, beta=2.0, kappa=0.0, reg=0.0, want_grad=True, causal=False):
         """Unscented-Kalman-filter marginal likelihood (src/UnscentedKalmanFilter.jl:76-87): returns
         (loss, grad_theta, grad_pnu_factor) with P_nu = F F', F = pnu_factor (d x d).  causal=False (default) integrates the
-        sigma points over [times[t], times[t] + dt] as the reference does (:83, :93); causal=True over [times[t-1], times[t]]."""
+        sigma points over [times[t], times[t] + dt] as the reference does (:83, :93); causal=True over [times[t-1], times[t]].
+        Many-model handles: pnu_factor (n_models, d, d) (or one (d, d) for all), loss (n_models,), grad_pnu_factor
+        (n_models, d, d); single-model handles keep the scalar / (d, d) shapes."""
         self.set_option(OPT_UKF_CAUSAL_INTERVAL, int(bool(causal)))
-        d = self.problem.d
+        d, M = self.problem.d, self.problem.n_models
         th = np.ascontiguousarray(theta, dtype=np.float64)
-        F = np.ascontiguousarray(np.asarray(pnu_factor, dtype=np.float64).reshape(d, d).T)      # column-major bytes
+        F = self._ukf_factor(pnu_factor)
         o = self._ukf_opts(Peta, alpha, beta, kappa, reg)
-        loss = C.c_double(0.0)
+        loss = np.zeros(M)
         g = np.zeros_like(th) if want_grad else None
-        gF = np.zeros((d, d)) if want_grad else None
-        rc = self.lib.ude_ukf_loss_grad(self.handle, C.byref(o), th.ctypes.data, th.shape[0], F.ctypes.data, C.addressof(loss),
+        gF = np.zeros((M, d, d)) if want_grad else None
+        rc = self.lib.ude_ukf_loss_grad(self.handle, C.byref(o), th.ctypes.data, th.shape[0], F.ctypes.data, loss.ctypes.data,
                                         g.ctypes.data if want_grad else None, gF.ctypes.data if want_grad else None)
         if rc != UDE_OK and rc != UDE_NONFINITE:
             self._check(rc)
-        return float(loss.value), g, (gF.T.copy() if want_grad else None)
+        if want_grad:
+            gF = gF.transpose(0, 2, 1).copy()
+        if M == 1:
+            return float(loss[0]), g, (gF[0] if want_grad else None)
+        return loss, g, gF
 
     def ukf_filter(self, theta, pnu_factor, Peta, alpha=1e-3, beta=2.0, kappa=0.0, causal=False):
         """ukf_smoothing (src/UnscentedKalmanFilter.jl:59-72): filtered states (d x n_cols) and covariances (d x d x n_cols)."""
         self.set_option(OPT_UKF_CAUSAL_INTERVAL, int(bool(causal)))
         d = self.problem.d
         th = np.ascontiguousarray(theta, dtype=np.float64)
-        F = np.ascontiguousarray(np.asarray(pnu_factor, dtype=np.float64).reshape(d, d).T)
+        F = self._ukf_factor(pnu_factor)
         o = self._ukf_opts(Peta, alpha, beta, kappa, 0.0)
         xs = np.zeros((d, self.problem.n_cols), order="F")
         Ps = np.zeros((d, d, self.problem.n_cols), order="F")
