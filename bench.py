@@ -497,6 +497,23 @@ def main():
                                     "ms_per_eval": (time.perf_counter() - t0) / 20 * 1e3}
         except Exception as ex:
             others["ukf_c1"] = {"error": str(ex)[:200]}
+        try:       # the same loss on a many-model handle: 100 members x 10 leave-future-out folds of the coral UDE in one launch chain
+            p4, th4 = ude.synthetic.config_c4(n_members=100, n_folds=10)
+            with ude.Engine(p4, device=local) as e4:
+                F4, Pe4 = 0.3 * np.eye(p4.d), 0.1 * np.eye(p4.d)
+                for _ in range(3):
+                    e4.ukf_loss_grad(th4, F4, Pe4)
+                t0 = time.perf_counter()
+                for _ in range(10):
+                    e4.ukf_loss_grad(th4, F4, Pe4)
+                ms = (time.perf_counter() - t0) / 10 * 1e3
+                n_upd = int(np.sum(np.asarray(p4.lengths) - 1))
+                others["ukf_c4_ensemble"] = {"workload": "C4 coral UDE, UKF marginal likelihood, 100 members x 10 folds = 1000 models in one handle "
+                                                         "(per-model process model and P_nu factor), 7 sigma points",
+                                             "ms_per_eval": ms, "filter_updates_per_s": n_upd / (ms * 1e-3),
+                                             "rk_steps_per_s": 2 * n_upd * (2 * p4.d + 1) * p4.substeps / (ms * 1e-3)}
+        except Exception as ex:
+            others["ukf_c4_ensemble"] = {"error": str(ex)[:200]}
         try:       # the tutorial workflow itself: 500 Adam iterations of the C1 conditional-likelihood fit, device resident
             p4, th4 = ude.synthetic.config_c1()
             with ude.Engine(p4, device=local) as e4:

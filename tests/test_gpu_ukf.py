@@ -246,3 +246,19 @@ def test_ukf_many_models_shared_factor_equals_single_handles(ude):
             L1, g1, gF1 = eng.ukf_loss_grad(theta[lo:hi], F, Peta, alpha=1.0)
         assert abs(L[m] - L1) <= 1e-12 * abs(L1)
         assert cases.relerr(g[lo:hi], g1) < 1e-11 and cases.relerr(gF[m], gF1) < 1e-11
+
+
+def test_marginal_likelihood_folds_batched_equal_sequential(ude):
+    """leave-future-out folds trained on the UKF likelihood in ONE many-model handle (marginal_likelihood_many_, the
+    "marginal likelihood" branch of leave_future_out_batched) equal the folds trained one handle at a time."""
+    df = ude.LotkaVolterra(plot=False, datasize=16)
+    base = ude.NODE(df, hidden_units=5, seed=3)
+    lo = dict(observation_error=0.05, alpha=1.0); oo = dict(maxiter=6, step_size=0.02)
+    models, train, test, forecasts, trace = ude.leave_future_out_batched(base, 3, loss_function="marginal likelihood",
+                                                                         regularization_weight=1e-4, loss_options=lo, optim_options=oo)
+    assert len(models) == 3 and trace.shape == (6, 3) and np.all(np.isfinite(trace)) and len(forecasts) == 3
+    for mi, tr in enumerate(train):
+        one = base.constructor(tr)
+        Pnu, Px = ude.train_(one, "marginal likelihood", verbose=False, regularization_weight=1e-4, loss_options=lo, optim_options=oo)
+        assert cases.relerr(one.extra["loss_trace"], trace[:, mi]) < 1e-10
+        assert cases.relerr(models[mi].parameters, one.parameters) < 1e-8

@@ -140,6 +140,12 @@ def leave_future_out_batched(model: UDE, k: int, skip: int = 1, loss_function="c
         train = [tr for _ in seeds for tr in train]
     else:
         models = [model.constructor(tr) for tr in train]
+    if loss_function == "marginal likelihood":       # UKF loss: all folds x members filtered in one many-model handle
+        from .training import marginal_likelihood_many_
+        marginal_likelihood_many_(models, regularization_weight, loss_options, optim_options, device=device)
+        trace = np.stack([m.extra["loss_trace"] for m in models], axis=1)
+        forecasts = [_forecast_fold(m, te, device) for m, te in zip(models, test)] if do_forecast else []
+        return models, train, test, forecasts, trace
     opts = dict(default_options(loss_function)); opts.update(optim_options or {})
     big, theta = stack_models(models, loss_function, regularization_weight, loss_options)
     if devices is not None and len(devices) > 1 and big.n_models >= len(devices):

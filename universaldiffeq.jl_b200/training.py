@@ -461,6 +461,59 @@ def marginal_likelihood_(model: UDE, regularization_weight=0.0, loss_options=Non
     return F @ F.T, Ps
 
 
+def marginal_likelihood_many_(models, regularization_weight=0.0, loss_options=None, optim_options=None, verbose=False, device=0):
+    """train!(...; loss_function = "marginal likelihood") for a LIST of models of one architecture (leave-future-out folds,
+    ensemble members) in one many-model handle: every Adam iteration filters all of them in the same launches
+    (ude_ukf_loss_grad on a many-model handle, one process model and one P_nu factor per model).  Adam is element-wise, so
+    this equals len(models) separate marginal_likelihood_ runs.  Returns [(P_nu, Px), ...]; loss traces in model.extra."""
+    from .cross_validation import stack_models
+    o = dict(loss_options or {})
+    d = models[0].d
+    Pnu0 = errors_to_matrix(o.get("process_error", 0.1), d)
+    Peta = errors_to_matrix(o.get("observation_error", 0.1), d)
+    alpha, beta, kappa = o.get("alpha", 1e-3), o.get("beta", 2.0), o.get("kappa", 0.0)
+    opts = dict(default_options("marginal likelihood")); opts.update(optim_options or {})
+    regs = {regularization_weight * m.weights["regularization"] * (_n_series(m) + 1 if m.multi else 1) for m in models}
+    if len(regs) != 1:
+        raise ValueError("models filtered together share one regularisation weight")
+    reg = regs.pop()
+    big, theta = stack_models(models, "default")
+    M, n_pm = big.n_models, big.n_pm
+    col0 = np.asarray(big.model_col0, dtype=np.int64)
+    base = np.asarray(big.theta_base, dtype=np.int64)
+    pm_idx = (base + d * (col0[1:] - col0[:-1]))[:, None] + np.arange(n_pm)[None, :]           # (M, n_pm) into theta
+    F0 = np.linalg.cholesky(Pnu0)
+    x = np.concatenate([theta[pm_idx], np.tile(F0.reshape(-1, order="F"), (M, 1))], axis=1)    # (M, n_pm + d*d)
+    m1 = np.zeros_like(x); v1 = np.zeros_like(x)
+    trace = []
+    as_factors = lambda xx: xx[:, n_pm:].reshape(M, d, d).transpose(0, 2, 1)                   # noqa: E731  (column-major rows)
+    with Engine(big, device=device) as eng:
+        for it in range(1, int(opts["maxiter"]) + 1):
+            theta[pm_idx] = x[:, :n_pm]
+            L, g, gF = eng.ukf_loss_grad(theta, as_factors(x), Peta, alpha, beta, kappa, reg)
+            L, gF = np.atleast_1d(L), np.asarray(gF).reshape(M, d, d)
+            trace.append(L.copy())
+            if verbose:
+                print(round(float(L.sum()), 3), end=" ", flush=True)
+            gx = np.concatenate([g[pm_idx], gF.transpose(0, 2, 1).reshape(M, d * d)], axis=1)
+            m1 = 0.9 * m1 + 0.1 * gx
+            v1 = 0.999 * v1 + 0.001 * gx * gx
+            x = x - opts["step_size"] * (m1 / (1 - 0.9 ** it)) / (np.sqrt(v1 / (1 - 0.999 ** it)) + 1e-8)
+        theta[pm_idx] = x[:, :n_pm]
+        Fs = as_factors(x)
+        xs, Ps = eng.ukf_filter(theta, Fs, Peta, alpha, beta, kappa)
+    trace = np.array(trace).reshape(-1, M)
+    out = []
+    for mi, mdl in enumerate(models):
+        c0, c1 = int(col0[mi]), int(col0[mi + 1])
+        th = theta[int(base[mi]): int(base[mi]) + d * (c1 - c0) + n_pm].copy()
+        th[:d * (c1 - c0)] = xs[:, c0:c1].reshape(-1, order="F")
+        mdl.parameters = th
+        mdl.extra["loss_trace"] = trace[:, mi].copy()
+        out.append((Fs[mi] @ Fs[mi].T, Ps[:, :, c0:c1]))
+    return out
+
+
 def kalman_filter_(model: UDE, sigma2, Pnu=None, Peta=None, alpha=1e-3, beta=2.0, kappa=0.0, verbose=False, maxiter=500, step_size=0.05,
                    device=0):
     """kalman_filter!(UDE::MultiUDE, sigma2; ...) (src/UnscentedKalmanFilter.jl:181-235): Adam over (process_model, p) with
