@@ -110,7 +110,7 @@ def test_parity_mma2_dense_knots_and_forward(ude, kernel, monkeypatch):
         assert cases.relerr(out, ref) < TOL, loss
 
 
-@pytest.mark.parametrize("kernel", ["mma", "g32h4"])
+@pytest.mark.parametrize("kernel", ["mma_h128", "mma_h128_biasmma", "g32h4"])
 def test_parity_wide_node(ude, kernel, monkeypatch):
     """d = 8, hidden 128 (BASELINE config C5): the DMMA kernel with the hidden layer split over four warps, and the
     lane-per-hidden-unit kernel, against the oracle."""
@@ -429,15 +429,19 @@ def test_error_paths_of_the_wider_api(ude):
     assert ei.value.code == -2
     many, th_many = cases.make_case("node_d2", "cond_lik", 0, lengths=(5, 4, 6, 3), n_models=2)
     with ude.Engine(many) as eng:
-        with pytest.raises(ude.UdeError) as ei:
-            eng.ukf_loss_grad(th_many, 0.3 * np.eye(2), 0.1 * np.eye(2))
-        assert ei.value.code == -2
+        Lm, _, _ = eng.ukf_loss_grad(th_many, 0.3 * np.eye(2), 0.1 * np.eye(2), alpha=1.0)     # many-model UKF is supported (round 2)
+        assert Lm.shape == (2,) and np.all(np.isfinite(Lm))
         with pytest.raises(ude.UdeError):
             eng.forecast_chain(th_many, np.ones(2), np.ones(2), np.zeros(2), np.ones(2) * 0.5, 0.25, 0.1)
         with pytest.raises(ude.UdeError):
             eng.peer_attach([b"\0" * 128, b"\0" * 128], 2, 0)
         with pytest.raises(ude.UdeError):
             eng.peer_export(1)
+    sp, th_sp = cases.make_case("series_growth_d1", "cond_lik", 0, hidden=4, lengths=(5, 4))      # per-series parameter vector: no UKF path
+    with ude.Engine(sp) as eng:
+        with pytest.raises(ude.UdeError) as ei:
+            eng.ukf_loss_grad(th_sp, 0.3 * np.eye(1), 0.1 * np.eye(1))
+        assert ei.value.code == -2
     one, th_one = cases.make_case("node_d2", "cond_lik", 0, lengths=(1,))           # a single point: nothing to filter
     with ude.Engine(one) as eng:
         with pytest.raises(ude.UdeError):

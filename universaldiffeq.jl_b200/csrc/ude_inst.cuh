@@ -56,26 +56,26 @@ void register_combo_f32(const char* name, int priority) { register_combo_t<F32, 
 
 // tensor-core (FP64 DMMA) family: NODE right-hand sides, 8 segments per task, HW warps per task each owning HT hidden
 // tiles (hidden width padded to 8*HT*HW)
-template <int D, int NX, int HT, int HW, int MINB, int SOLVER, int LK, int TB = 4>
+template <int D, int NX, int HT, int HW, int MINB, int SOLVER, int LK, int TB = 4, int BX = 0>
 void register_mma_one(const char* name, int priority) {
-  using MG = MmaGeo<D, NX, HT, HW, TB>;
+  using MG = MmaGeo<D, NX, HT, HW, TB, BX>;
   // registry fields G / HPL are reused as "segments per warp-task = 32/G" and capacity G*HPL >= nn_hidden
   const int G = 4, HPLcap = 2 * HT * HW;
   kernel_registry().push_back(KernelEntry{UDE_RHS_NODE, D, NX, D + NX, D, UDE_F64, G, HPLcap, SOLVER, LK, 1, MG::REC / 32, 8, 0,
                                           MmaSmem<MG, LK, true>::BLOCK * 8, MmaSmem<MG, LK, true>::WARP * 8, 1, 8, HW, priority,
-                                          (const void*)ude_mma_kernel<D, NX, HT, HW, SOLVER, LK, true, MINB, TB>, name});
+                                          (const void*)ude_mma_kernel<D, NX, HT, HW, SOLVER, LK, true, MINB, TB, BX>, name});
   kernel_registry().push_back(KernelEntry{UDE_RHS_NODE, D, NX, D + NX, D, UDE_F64, G, HPLcap, SOLVER, LK, 0, MG::REC / 32, 8, 0,
                                           MmaSmem<MG, LK, false>::BLOCK * 8, MmaSmem<MG, LK, false>::WARP * 8, 1, 8, HW, priority,
-                                          (const void*)ude_mma_kernel<D, NX, HT, HW, SOLVER, LK, false, MINB, TB>, name});
+                                          (const void*)ude_mma_kernel<D, NX, HT, HW, SOLVER, LK, false, MINB, TB, BX>, name});
 }
-template <int D, int NX, int HT, int MINB, int HW = 1, int TB = 4>
+template <int D, int NX, int HT, int MINB, int HW = 1, int TB = 4, int BX = 0>
 void register_mma_combo(const char* name, int priority) {
-  register_mma_one<D, NX, HT, HW, MINB, 0, LK_STATE, TB>(name, priority);
-  register_mma_one<D, NX, HT, HW, MINB, 0, LK_TRAJ, TB>(name, priority);
-  register_mma_one<D, NX, HT, HW, MINB, 0, LK_DM, TB>(name, priority);
-  register_mma_one<D, NX, HT, HW, MINB, 1, LK_STATE, TB>(name, priority);
-  register_mma_one<D, NX, HT, HW, MINB, 1, LK_TRAJ, TB>(name, priority);
-  register_mma_one<D, NX, HT, HW, MINB, 1, LK_DM, TB>(name, priority);
+  register_mma_one<D, NX, HT, HW, MINB, 0, LK_STATE, TB, BX>(name, priority);
+  register_mma_one<D, NX, HT, HW, MINB, 0, LK_TRAJ, TB, BX>(name, priority);
+  register_mma_one<D, NX, HT, HW, MINB, 0, LK_DM, TB, BX>(name, priority);
+  register_mma_one<D, NX, HT, HW, MINB, 1, LK_STATE, TB, BX>(name, priority);
+  register_mma_one<D, NX, HT, HW, MINB, 1, LK_TRAJ, TB, BX>(name, priority);
+  register_mma_one<D, NX, HT, HW, MINB, 1, LK_DM, TB, BX>(name, priority);
 }
 
 // round-2 tensor-core family (ude_kernel_mma2.cuh): NT M-tiles (8 segments each) per warp, state-space and trajectory

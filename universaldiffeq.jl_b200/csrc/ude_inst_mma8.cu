@@ -4,7 +4,9 @@
 namespace {
 using namespace ude;
 RegisterKernels reg([] {
-  register_mma_combo<8, 0, 4, 2, 4>("node_d8_mma_h128", 0);
-  register_mma_combo<8, 0, 4, 3, 1>("node_d8_mma_h32", 0);
+  // BX = 1: b1 stays out of the MMAs (d = 8 fills the input slots exactly; ude_kernel_mma.cuh MmaGeo::BX): 16.0 -> 14.5 ms on C5
+  register_mma_combo<8, 0, 4, 2, 4, 4, 1>("node_d8_mma_h128", 0);
+  register_mma_combo<8, 0, 4, 3, 1, 4, 1>("node_d8_mma_h32", 0);
+  register_mma_combo<8, 0, 4, 2, 4, 4, 0>("node_d8_mma_h128_biasmma", 9);       // A/B: the bias as a constant-1 input slot
 });
 }  // namespace

@@ -5,7 +5,7 @@ namespace {
 using namespace ude;
 RegisterKernels reg([] {
   register_mma_combo<4, 1, 4, 2, 4>("node_d4x1_mma_h128", 4);
-  register_mma_combo<4, 0, 4, 2, 4>("node_d4_mma_h128", 4);
+  register_mma_combo<4, 0, 4, 2, 4, 4, 1>("node_d4_mma_h128", 4);
   register_mma_combo<2, 0, 4, 2, 4>("node_d2_mma_h128", 4);
 });
 }  // namespace

@@ -29,14 +29,19 @@ __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
                : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
 
-template <int D_, int NX_, int HT_, int HW_ = 1, int TB_ = 4>
+template <int D_, int NX_, int HT_, int HW_ = 1, int TB_ = 4, int BX_ = 0>
 struct MmaGeo {
   static constexpr int TB = TB_;                         // tanh evaluations interleaved per batch (4 or 8)
+  // BX: the bias b1 stays OUT of the MMAs.  When D + NX is a multiple of 4 the constant-1 input slot would be alone in an
+  // extra layer-1 k-step (and, for a multiple of 8, alone in an extra M tile of the W1 gradient): d = 8 spends 12 instead
+  // of 8 DMMAs per warp and stage on layer 1 and 16 instead of 8 on the W1 gradient for it.  With BX the layer-1
+  // accumulators start at b1 and the b1 gradient is the column sum of the z-bar fragments the W1-gradient MMAs load anyway.
+  static constexpr bool BX = BX_ != 0;
   static constexpr int D = D_, NX = NX_, HT = HT_;
   static constexpr int HW = HW_;                         // warps that share one 8-segment task, each owning HT hidden tiles
   static constexpr int HTT = HT_ * HW_;                  // hidden tiles of the whole network (8 units each)
   static constexpr int NXA = NX > 0 ? NX : 1;
-  static constexpr int KS = (D + NX + 1 + 3) / 4;        // input k-steps (state, covariates, constant-1 bias slot)
+  static constexpr int KS = (D + NX + (BX ? 0 : 1) + 3) / 4;   // input k-steps (state, covariates, constant-1 bias slot unless BX)
   static constexpr int NSLOT = 4 * KS;
   static constexpr int KO = (D + 3) / 4;                 // output k-steps (h-bar = W2^T k-bar)
   static constexpr int MT = (NSLOT + 7) / 8;             // M tiles of the W1 gradient (slots)
@@ -128,11 +133,16 @@ template <class MG>
 __device__ __forceinline__ void mma_stage_forward(const double* __restrict__ s_w, const double* s_tab, int lane, int wl,
                                                   double* s_xch, int& xpar,
                                                   const double (&xs)[MG::KS], const double (&b2own)[2],
-                                                  double (&h)[MG::HT][2], double (&y)[2]) {
+                                                  double (&h)[MG::HT][2], double (&y)[2], const double* s_b1) {
   const int tb = wl * MG::HT;                 // first hidden tile of this warp
   double z[MG::HT][2];
 #pragma unroll
-  for (int t = 0; t < MG::HT; ++t) { z[t][0] = 0.0; z[t][1] = 0.0; }
+  for (int t = 0; t < MG::HT; ++t) {
+    if constexpr (MG::BX) {                   // lane (r, c) accumulates hidden units 8 (tb + t) + 2c, + 1
+      const double2 b = *reinterpret_cast<const double2*>(s_b1 + 8 * (tb + t) + 2 * (lane & 3));
+      z[t][0] = b.x; z[t][1] = b.y;
+    } else { z[t][0] = 0.0; z[t][1] = 0.0; }
+  }
 #pragma unroll
   for (int e = 0; e < MG::KS; ++e) {
 #pragma unroll
@@ -175,15 +185,16 @@ __device__ __forceinline__ void mma_stage_forward(const double* __restrict__ s_w
   y[1] += b2own[1];
 }
 
-template <int D_, int NX_, int HT_, int HW_, int SOLVER, int LK, bool GRAD, int MINB, int TB_ = 4>
+template <int D_, int NX_, int HT_, int HW_, int SOLVER, int LK, bool GRAD, int MINB, int TB_ = 4, int BX_ = 0>
 __global__ void __launch_bounds__(kBlockThreads, MINB) ude_mma_kernel(const DevProblem P) {
-  using MG = MmaGeo<D_, NX_, HT_, HW_, TB_>;
+  using MG = MmaGeo<D_, NX_, HT_, HW_, TB_, BX_>;
   constexpr int HW = HW_;
   static_assert(HW == 1 || HW == kBlockThreads / 32, "a task is shared by one warp or by the whole block");
   using T = Tab<SOLVER>;
   constexpr int D = D_, NX = NX_, HT = HT_, KS = MG::KS;
   __shared__ double s_tab[64];
   __shared__ __align__(8) uint64_t s_bar[kBlockThreads / 32][2];
+  __shared__ __align__(16) double s_b1[MG::BX ? 8 * MG::HTT : 2];
   extern __shared__ __align__(16) double s_dyn[];
   // [n_pm + 1 (block partial) padded even][weight fragments][per warp: 2 stage records | z-bar/k-bar scratch]
   double* s_red = s_dyn;
@@ -216,6 +227,8 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) ude_mma_kernel(const DevP
   for (long long k = threadIdx.x; k <= P.n_pm; k += blockDim.x) s_red[k] = 0.0;
   const double* __restrict__ pm = P.theta + (long long)D * P.model_col0[1];        // single model: [uhat | pm]
   build_frags<MG>(P, pm, s_w);
+  if constexpr (MG::BX)
+    for (int j = threadIdx.x; j < 8 * MG::HTT; j += blockDim.x) s_b1[j] = j < P.H ? pm[P.off_b1 + j] : 0.0;
   if (GRAD && LK != LK_DM && lane == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); }
   uint32_t bar_phase = 0;
   __syncthreads();
@@ -231,9 +244,10 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) ude_mma_kernel(const DevP
 
   // gradient accumulators (C fragments) -- summed over the warp's 8 segments by the MMA itself
   double GW1[MG::MT][HT][2], GW2[HT][2], gb2[2] = {0.0, 0.0};
+  double gb1[HT];                              // BX: column sums of the z-bar B fragments this lane loads (tile column r)
 #pragma unroll
   for (int t = 0; t < HT; ++t) {
-    GW2[t][0] = GW2[t][1] = 0.0;
+    GW2[t][0] = GW2[t][1] = 0.0; gb1[t] = 0.0;
 #pragma unroll
     for (int m = 0; m < MG::MT; ++m) GW1[m][t][0] = GW1[m][t][1] = 0.0;
   }
@@ -272,7 +286,7 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) ude_mma_kernel(const DevP
       const double ts = P.times[col];
       if (NX > 0) cov_eval<NX>(P, series, ts, cur, X);
       make_xs(U, X, xs);
-      mma_stage_forward<MG>(s_w, s_tab, lane, wl, s_xch, xpar, xs, b2own, h, y);
+      mma_stage_forward<MG>(s_w, s_tab, lane, wl, s_xch, xpar, xs, b2own, h, y, s_b1);
       const double w = is_null ? 0.0 : 1.0;
       double kb[2];
 #pragma unroll
@@ -323,6 +337,7 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) ude_mma_kernel(const DevP
 #pragma unroll
             for (int m = 0; m < MG::MT; ++m) dmma(GW1[m][t], aX[m], bZ);
             dmma(GW2[t], aK, bH);
+            if constexpr (MG::BX) gb1[t] += bZ;
           }
         }
         __syncwarp();
@@ -400,7 +415,7 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) ude_mma_kernel(const DevP
             const double ts = t + T::c(st) * hs;
             if (NX > 0) cov_eval<NX>(P, series, ts, cur, X);
             make_xs(U, X, xs);
-            mma_stage_forward<MG>(s_w, s_tab, lane, wl, s_xch, xpar, xs, b2own, h, y);
+            mma_stage_forward<MG>(s_w, s_tab, lane, wl, s_xch, xpar, xs, b2own, h, y, s_b1);
             if (GRAD) {
               // stage record -> shared memory -> TMA bulk store to the stash (two-buffer ring, one record per stage)
               const int rec = k * T::S + st;
@@ -589,6 +604,7 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) ude_mma_kernel(const DevP
 #pragma unroll
                 for (int m = 0; m < MG::MT; ++m) dmma(GW1[m][t], aX[m], bZ);
                 dmma(GW2[t], aK, bH);
+                if constexpr (MG::BX) gb1[t] += bZ;
               }
             }
             __syncwarp();                       // everyone is done with buffer b and the scratch tiles
@@ -633,6 +649,10 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) ude_mma_kernel(const DevP
     for (int off = 1; off < 32; off <<= 1) l += __shfl_xor_sync(0xffffffffu, l, off);
 #pragma unroll
     for (int off = 4; off < 32; off <<= 1) { gb2[0] += __shfl_xor_sync(0xffffffffu, gb2[0], off); gb2[1] += __shfl_xor_sync(0xffffffffu, gb2[1], off); }
+    if constexpr (MG::BX && GRAD) {        // lanes (r, 0..3) loaded the 8 segments of tile column r between them
+#pragma unroll
+      for (int t = 0; t < HT; ++t) { gb1[t] += __shfl_xor_sync(0xffffffffu, gb1[t], 1); gb1[t] += __shfl_xor_sync(0xffffffffu, gb1[t], 2); }
+    }
     const int nw = blockDim.x >> 5, wib = threadIdx.x >> 5;
     for (int w = 0; w < nw; ++w) {
       if (wib == w) {
@@ -648,7 +668,7 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) ude_mma_kernel(const DevP
                 for (int m = 0; m < MG::MT; ++m) {
                   const int s = r + 8 * m;            // slot: input column, or the bias
                   if (s < D + NX) s_red[P.off_w1 + hid + (long long)P.H * s] += GW1[m][t][j];
-                  else if (s == D + NX) s_red[P.off_b1 + hid] += GW1[m][t][j];
+                  else if (!MG::BX && s == D + NX) s_red[P.off_b1 + hid] += GW1[m][t][j];   // BX: rows >= 4 KS of the x tile are never written
                 }
                 if (r < D) s_red[P.off_w2 + r + (long long)P.nn_out * hid] += GW2[t][j];
               }
@@ -657,6 +677,15 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) ude_mma_kernel(const DevP
           if (r == 0) {
 #pragma unroll
             for (int j = 0; j < 2; ++j) if (c + 4 * j < D) s_red[P.off_b2 + c + 4 * j] += gb2[j];
+          }
+          if constexpr (MG::BX) {
+            if (c == 0) {
+#pragma unroll
+              for (int t = 0; t < HT; ++t) {         // tile column r holds hidden unit 2 (r & 3) + (r >> 2) of the tile
+                const int hid = 8 * (wl * HT + t) + 2 * (r & 3) + (r >> 2);
+                if (hid < P.H) s_red[P.off_b1 + hid] += gb1[t];
+              }
+            }
           }
         }
         if (lane == 0) s_red[P.n_pm] += l;
