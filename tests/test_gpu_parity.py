@@ -110,7 +110,7 @@ def test_parity_mma2_dense_knots_and_forward(ude, kernel, monkeypatch):
         assert cases.relerr(out, ref) < TOL, loss
 
 
-@pytest.mark.parametrize("kernel", ["mma_h128", "mma_h128_biasmma", "g32h4"])
+@pytest.mark.parametrize("kernel", ["mma_h128", "mma_h128_biasmma", "mma_h128_b2", "g32h4"])
 def test_parity_wide_node(ude, kernel, monkeypatch):
     """d = 8, hidden 128 (BASELINE config C5): the DMMA kernel with the hidden layer split over four warps, and the
     lane-per-hidden-unit kernel, against the oracle."""

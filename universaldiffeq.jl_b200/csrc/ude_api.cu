@@ -491,7 +491,9 @@ int build_plan(ude_handle* h) {
   // dynamic smem: block partial row (single model) padded to 16 B + per-warp two-step TMA staging ring of the stash
   const size_t red_doubles = (size_t)(((h->n_models == 1 ? D.n_pm + 1 : 0) + 1) / 2 * 2);
   auto smem_for = [&](const KernelEntry* k) {
-    return red_doubles * sizeof(double) + (size_t)k->block_bytes + (size_t)(ude::kBlockThreads / 32) * (size_t)k->warp_bytes;
+    const size_t warps = (size_t)(ude::kBlockThreads / 32) * (size_t)k->warp_bytes, red = red_doubles * sizeof(double);
+    if (k->red_alias) return (size_t)k->block_bytes + std::max(warps, red);      // the partial row lives in the per-warp region
+    return red + (size_t)k->block_bytes + warps;
   };
   h->smem_bytes = smem_for(h->k_grad);
   h->smem_bytes_fwd = smem_for(h->k_fwd);

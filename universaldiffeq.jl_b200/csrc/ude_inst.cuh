@@ -63,7 +63,7 @@ void register_mma_one(const char* name, int priority) {
   const int G = 4, HPLcap = 2 * HT * HW;
   kernel_registry().push_back(KernelEntry{UDE_RHS_NODE, D, NX, D + NX, D, UDE_F64, G, HPLcap, SOLVER, LK, 1, MG::REC / 32, 8, 0,
                                           MmaSmem<MG, LK, true>::BLOCK * 8, MmaSmem<MG, LK, true>::WARP * 8, 1, 8, HW, priority,
-                                          (const void*)ude_mma_kernel<D, NX, HT, HW, SOLVER, LK, true, MINB, TB, BX>, name});
+                                          (const void*)ude_mma_kernel<D, NX, HT, HW, SOLVER, LK, true, MINB, TB, BX>, name, MG::RA ? 1 : 0});
   kernel_registry().push_back(KernelEntry{UDE_RHS_NODE, D, NX, D + NX, D, UDE_F64, G, HPLcap, SOLVER, LK, 0, MG::REC / 32, 8, 0,
                                           MmaSmem<MG, LK, false>::BLOCK * 8, MmaSmem<MG, LK, false>::WARP * 8, 1, 8, HW, priority,
                                           (const void*)ude_mma_kernel<D, NX, HT, HW, SOLVER, LK, false, MINB, TB, BX>, name});

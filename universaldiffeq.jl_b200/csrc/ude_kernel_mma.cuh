@@ -36,7 +36,11 @@ struct MmaGeo {
   // extra layer-1 k-step (and, for a multiple of 8, alone in an extra M tile of the W1 gradient): d = 8 spends 12 instead
   // of 8 DMMAs per warp and stage on layer 1 and 16 instead of 8 on the W1 gradient for it.  With BX the layer-1
   // accumulators start at b1 and the b1 gradient is the column sum of the z-bar fragments the W1-gradient MMAs load anyway.
-  static constexpr bool BX = BX_ != 0;
+  static constexpr bool BX = (BX_ & 1) != 0;
+  // RA (bit 1 of BX_): the block's partial row [n_pm + 1] aliases the per-warp stage rings instead of owning shared memory
+  // of its own -- it is only written by the flush, after the last task (C5: 17.5 of 86 KB, the difference between 2 and 3
+  // blocks per SM)
+  static constexpr bool RA = (BX_ & 2) != 0;
   static constexpr int D = D_, NX = NX_, HT = HT_;
   static constexpr int HW = HW_;                         // warps that share one 8-segment task, each owning HT hidden tiles
   static constexpr int HTT = HT_ * HW_;                  // hidden tiles of the whole network (8 units each)
@@ -197,10 +201,11 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) ude_mma_kernel(const DevP
   __shared__ __align__(16) double s_b1[MG::BX ? 8 * MG::HTT : 2];
   extern __shared__ __align__(16) double s_dyn[];
   // [n_pm + 1 (block partial) padded even][weight fragments][per warp: 2 stage records | z-bar/k-bar scratch]
-  double* s_red = s_dyn;
-  double* s_w = s_dyn + (P.n_pm + 1 + 1) / 2 * 2;
+  constexpr bool RA = MG::RA && GRAD;          // forward-only kernels have no per-warp region to alias
+  double* s_w = RA ? s_dyn : s_dyn + (P.n_pm + 1 + 1) / 2 * 2;
   constexpr int kPerWarp = MmaSmem<MG, LK, GRAD>::WARP;
   double* s_xch = s_w + MG::NFRAG * 32;
+  double* s_red = RA ? s_xch + MmaSmem<MG, LK, GRAD>::XCH : s_dyn;
   double* s_warp = s_xch + MmaSmem<MG, LK, GRAD>::XCH + (size_t)(threadIdx.x >> 5) * kPerWarp;
   double* s_stage = s_warp;
   // ring first (LK_DM: nothing), then the scratch tiles; LK_DM puts its h/x tiles behind the k-bar tile
@@ -224,7 +229,7 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) ude_mma_kernel(const DevP
   double* __restrict__ stash = GRAD ? reinterpret_cast<double*>(P.stash) + warp_global * P.stash_rows_per_warp * 32 : nullptr;
 
   ude_load_exp2_tab(s_tab);
-  for (long long k = threadIdx.x; k <= P.n_pm; k += blockDim.x) s_red[k] = 0.0;
+  if constexpr (!RA) for (long long k = threadIdx.x; k <= P.n_pm; k += blockDim.x) s_red[k] = 0.0;
   const double* __restrict__ pm = P.theta + (long long)D * P.model_col0[1];        // single model: [uhat | pm]
   build_frags<MG>(P, pm, s_w);
   if constexpr (MG::BX)
@@ -654,6 +659,11 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) ude_mma_kernel(const DevP
       for (int t = 0; t < HT; ++t) { gb1[t] += __shfl_xor_sync(0xffffffffu, gb1[t], 1); gb1[t] += __shfl_xor_sync(0xffffffffu, gb1[t], 2); }
     }
     const int nw = blockDim.x >> 5, wib = threadIdx.x >> 5;
+    if constexpr (RA) {                     // every warp is done with its rings (bulk stores drained, loads consumed)
+      __syncthreads();
+      for (long long k = threadIdx.x; k <= P.n_pm; k += blockDim.x) s_red[k] = 0.0;
+      __syncthreads();
+    }
     for (int w = 0; w < nw; ++w) {
       if (wib == w) {
         if (GRAD) {

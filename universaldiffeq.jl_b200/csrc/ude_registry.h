@@ -21,6 +21,7 @@ struct KernelEntry {
   int priority;            // lower = preferred when several (G, HPL) fit
   const void* fn;
   const char* name;
+  int red_alias;           // 1: the block-partial row aliases the per-warp region (no shared memory of its own)
 };
 
 std::vector<KernelEntry>& kernel_registry();
