@@ -202,3 +202,33 @@ def test_alpha_conditioning_extended_precision():
         gld = float(np.imag(ukf.loss(prob, tld, Lf.astype(np.clongdouble), np.asarray(Peta, dtype=np.clongdouble), alpha=1e-3)) / eps)
         assert abs(g64 - gld) < 1e-7 * max(abs(gld), 1e-3)
 
+
+
+def test_model_argument_selects_one_model_of_a_stacked_problem():
+    """loss(..., model=m) on a many-model problem = the same series and process model as a single-model problem of their own
+    (what tests/test_gpu_ukf.py::test_ukf_many_models checks the CUDA many-model filter against)."""
+    many, th = cases.make_case("node_time_d3", "cond_lik", 0, hidden=4, lengths=(5, 3, 4, 6), n_models=2, seed=4)
+    d = many.d
+    rng = np.random.default_rng(2)
+    Peta = 0.1 * np.eye(d)
+    for m in range(2):
+        Lf = 0.3 * np.eye(d) + 0.05 * rng.normal(size=(d, d))
+        got = ukf.loss(many, th, Lf, Peta, alpha=1.0, reg_weight=1e-3, model=m)
+        off, s0, s1 = ukf._model_range(many, m)
+        pm = th[off:off + many.n_pm]
+        tot = 0.0
+        for s in range(s0, s1):
+            tot -= ukf.filter_series(many, pm, s, Lf @ Lf.T, Peta, 1.0, 2.0, 0.0)[0]
+        w1 = pm[many.off_w1:many.off_w1 + many.nn_hidden * many.nn_in]; w2 = pm[many.off_w2:many.off_w2 + many.nn_out * many.nn_hidden]
+        assert abs(got - (tot + 1e-3 * (w1 @ w1 + w2 @ w2))) < 1e-13 * abs(got)
+        g_pm, g_F = ukf.complex_step_grad(many, th, Lf, Peta, alpha=1.0, model=m)
+        # finite-difference spot check of two entries of each gradient (the complex step perturbs the right theta block)
+        for k in (0, many.n_pm - 1):
+            t2 = th.copy(); t2[off + k] += 1e-6
+            t3 = th.copy(); t3[off + k] -= 1e-6
+            fd = (ukf.loss(many, t2, Lf, Peta, alpha=1.0, model=m) - ukf.loss(many, t3, Lf, Peta, alpha=1.0, model=m)) / 2e-6
+            assert abs(fd - g_pm[k]) < 1e-5 * max(1.0, abs(g_pm[k]))
+        other = 1 - m
+        off_o = ukf._model_range(many, other)[0]
+        t4 = th.copy(); t4[off_o:off_o + many.n_pm] += 0.1               # the other model's parameters do not enter
+        assert ukf.loss(many, t4, Lf, Peta, alpha=1.0, reg_weight=1e-3, model=m) == got
