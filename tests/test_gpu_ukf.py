@@ -28,6 +28,7 @@ def _setup(rhs, hidden, lengths, solver, seed=0):
 
 
 @pytest.mark.parametrize("rhs,hidden,lengths", [("node_d2", 5, (7,)), ("node_d2", 5, (6, 3, 1, 4)), ("lv_ude_abs", 4, (6,)),
+                                                ("node_d2", 5, (2,)), ("node_d4x1", 6, (2, 2, 1)),      # ONE filter step
                                                 ("node_d4x1", 6, (4, 3)), ("node_time_d3", 5, (5, 2)), ("nn_decay_d1", 3, (9,))])
 @pytest.mark.parametrize("solver", [0, 1])
 def test_ukf_parity_alpha_one(ude, rhs, hidden, lengths, solver):

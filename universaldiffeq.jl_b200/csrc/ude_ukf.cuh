@@ -734,6 +734,12 @@ int ukf_enqueue(ude_handle* h, ude_ukf_plan* pl, bool want_grad, double* d_state
       const UkfStep& sk = pl->steps[(size_t)k];
       int rc = launch_segments(ax, pl->d_theta_aux.p, pl->d_grad_aux.p, nullptr, task0(sk), task1(sk), 0, s);
       if (rc != UDE_OK) return fail(h, rc, std::string("UKF adjoint: ") + ude_last_error(ax));
+      if (ax->n_models == 1) {
+        // a single auxiliary model (one filter step, one model): the single-model kernels leave the process-model gradient in
+        // per-block partial rows, which only the finalize kernel folds into the gradient vector
+        rc = finalize_eval(ax, pl->d_theta_aux.p, ax->d_loss.p, pl->d_grad_aux.p, ax->grid_grad, s);
+        if (rc != UDE_OK) return fail(h, rc, std::string("UKF adjoint: ") + ude_last_error(ax));
+      }
       if (k > 0) {
         const UkfStep& st = pl->steps[(size_t)k - 1]; const UkfStep& nx = pl->steps[(size_t)k];
         UKF_DISPATCH(d, ukf_bwd_fused, <<<(st.n_act + TB - 1) / TB, TB, 0, s>>>(st, nx, pl->d_next.p, C, act, smod, pnu, thoff, pl->d_U.p, pl->d_grad_aux.p,
