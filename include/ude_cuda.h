@@ -63,7 +63,13 @@ enum {
   UDE_RHS_LV_UDE_ABS = 3,    /* README.md:52-62 (abs on NN and parameters, logistic prey growth) */
   UDE_RHS_FISHERY = 4,       /* docs/src/examples.md:163-166 */
   UDE_RHS_NN_DECAY = 5,      /* du = NN(u) - m u                         test/MultiUDE.jl:17-19 */
-  UDE_RHS_SERIES_GROWTH = 6  /* du = r[series] u NN(u)[1]                docs/src/MultipleTimeSeries.md:51-55 */
+  UDE_RHS_SERIES_GROWTH = 6, /* du = r[series] u NN(u)[1]                docs/src/MultipleTimeSeries.md:51-55 */
+  /* >= 1000: a user-written right-hand side (the reference's `derivs!` closure, src/Models.jl:115-116).  Its kernels are not in
+   * this library: the host side writes the parametric part as expressions, generates the input / combine / combine_vjp trait
+   * of csrc/ude_kernel_body.inc from them, compiles it with nvcc into a PLUGIN shared library linked against libude_cuda.so
+   * and dlopens it (RTLD_GLOBAL) -- the plugin's static initialiser registers its kernels under this rhs_kind, after which
+   * every entry point below accepts it (universaldiffeq.jl_b200/user_rhs.py).  FP64 only. */
+  UDE_RHS_USER0 = 1000
 };
 
 typedef struct ude_handle ude_handle;

@@ -58,6 +58,11 @@ def rhs(p, pm, series_local, series_global, u, t):
     b2 = pm[p.off_b2:p.off_b2 + dout]
     X = covariates_at(p, series_global, t) if p.n_cov else np.zeros(0)
     k = p.rhs_kind
+    if k >= 1000:      # expression right-hand side (universaldiffeq.jl_b200/user_rhs.py): NN([u; X (; a t + b)]), then the user's du
+        ur = p.user_rhs
+        x = np.concatenate([u, X, [p.time_scale * t + p.time_shift]]) if ur.has_time_input else np.concatenate([u, X])
+        y = W2 @ np.tanh(W1 @ x + b1) + b2
+        return ur.du_numpy(u, X, y, [pm[o] for o in p.off_scalar])
     if k in (0, 4):
         x = np.concatenate([u, X])
     elif k == 1:

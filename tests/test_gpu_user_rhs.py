@@ -1,0 +1,80 @@
+"""User-written right-hand sides (expressions -> generated trait -> nvcc plugin) on the GPU, through the C ABI.
+
+Bars: 1e-10 against the NumPy twin (loss; complex-step gradient, element-wise per gradient leaf as in test_gpu_parity.py), and
+against the hand-written catalog kernel where the expressions restate a catalog entry."""
+import numpy as np
+import pytest
+
+import cases
+import user_rhs_cases as urc
+from oracle import oracle, ukf_oracle_np as ukf
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def _check_np(prob, theta, ude):
+    L_ref, g_ref = urc.numpy_loss_grad(prob, theta)
+    with ude.Engine(prob) as eng:
+        assert f"user{prob.rhs_kind}" in eng.kernel_name()
+        L, g = eng.loss_grad(theta)
+        L2, _ = eng.loss_grad(theta, want_grad=False)
+    assert np.all(np.isfinite(g))
+    assert abs(L[0] - L_ref[0]) < TOL * abs(L_ref[0]) and abs(L2[0] - L_ref[0]) < TOL * abs(L_ref[0])
+    worst = cases.grad_mismatch(prob, g, g_ref, TOL)
+    assert worst[0] <= 1.0, worst
+
+
+@pytest.mark.parametrize("loss", ["cond_lik", "mse", "multi_shoot", "multi_shoot_preroll", "shoot_theta", "shoot_data", "deriv_match"])
+@pytest.mark.parametrize("solver", [0, 1])
+def test_expressions_restating_a_catalog_entry_equal_the_catalog_kernel(ude, loss, solver):
+    rhs = urc.lv_twin(ude)
+    kw = dict(hidden=10, lengths=(9, 1, 14, 2, 6), skip=(loss in ("cond_lik", "mse")))
+    prob_u, theta = urc.make(ude, "user_lv", rhs, (1.0, 0.5, 0.5), loss, solver, **kw)
+    prob_c, theta_c = cases.make_case("lv_ude", loss, solver, **kw)
+    assert np.array_equal(theta, theta_c)
+    L_ref, g_ref = oracle.loss_grad(prob_c, theta)
+    with ude.Engine(prob_u) as eng:
+        assert f"user{rhs.kind}" in eng.kernel_name()
+        Lu, gu = eng.loss_grad(theta)
+    with ude.Engine(prob_c) as eng:
+        Lc, gc = eng.loss_grad(theta)
+    assert abs(Lu[0] - Lc[0]) <= 1e-13 * abs(Lc[0]) and cases.relerr(gu, gc) < 1e-12
+    assert abs(Lu[0] - L_ref[0]) < TOL * abs(L_ref[0])
+    worst = cases.grad_mismatch(prob_c, gu, g_ref, TOL)
+    assert worst[0] <= 1.0, worst
+
+
+@pytest.mark.parametrize("loss,solver,hidden", [("cond_lik", 0, 6), ("multi_shoot", 1, 6), ("deriv_match", 0, 5), ("shoot_theta", 0, 12),
+                                                ("mse", 1, 20)])
+def test_right_hand_side_outside_the_catalog(ude, loss, solver, hidden):
+    """three states, covariate, time input, two network outputs, abs / exp / rational terms: against the NumPy twin"""
+    rhs = urc.epidemic(ude)
+    prob, theta = urc.make(ude, "user_epi", rhs, (0.9, 0.4, 2.0), loss, solver, hidden=hidden, lengths=(5, 3, 1, 4), substeps=2)
+    _check_np(prob, theta, ude)
+
+
+def test_user_rhs_through_the_host_api_and_the_filter(ude):
+    """CustomDerivatives(data, expression_rhs, parameters) trains; forward predictions and the UKF run on the generated kernels"""
+    df = ude.LotkaVolterra(plot=False, datasize=15)
+    rhs = urc.lv_twin(ude)
+    _, nn = ude.SimpleNeuralNetwork(2, 1, hidden=6, seed=4)
+    m = ude.CustomDerivatives(df, rhs, {"NN": nn, "r": 0.5, "m": 0.4, "theta": 0.6})
+    ude.train_(m, "conditional likelihood", verbose=False, optim_options=dict(maxiter=30, step_size=0.02))
+    tr = m.extra["loss_trace"] if "loss_trace" in m.extra else None
+    assert tr is None or tr[-1] < tr[0]
+    inits, obs, preds = ude.predictions(m, df.iloc[3:9])
+    assert preds.shape == obs.shape and np.all(np.isfinite(preds))
+    # same model through the catalog entry: identical parameters after the same number of iterations
+    mc = ude.CustomDerivatives(df, ude.LV_UDE, {"NN": nn, "r": 0.5, "m": 0.4, "theta": 0.6})
+    ude.train_(mc, "conditional likelihood", verbose=False, optim_options=dict(maxiter=30, step_size=0.02))
+    assert cases.relerr(m.parameters, mc.parameters) < 1e-9
+    # UKF marginal likelihood on the generated kernels against the NumPy twin
+    prob, theta = urc.make(ude, "user_lv", rhs, (1.0, 0.5, 0.5), "cond_lik", 0, hidden=5, lengths=(6, 3))
+    F, Peta = 0.3 * np.eye(2), 0.1 * np.eye(2)
+    ref = ukf.loss(prob, theta, F, Peta, alpha=1.0)
+    g_pm, g_F = ukf.complex_step_grad(prob, theta, F, Peta, alpha=1.0)
+    with ude.Engine(prob) as eng:
+        L, g, gF = eng.ukf_loss_grad(theta, F, Peta, alpha=1.0)
+    n_u = prob.d * prob.n_cols
+    assert abs(L - ref) < TOL * abs(ref) and cases.relerr(g[n_u:], g_pm) < TOL and cases.relerr(gF.reshape(-1, order="F"), g_F) < TOL

@@ -1,0 +1,39 @@
+"""Expression right-hand sides used by tests/test_user_rhs.py (CPU) and tests/test_gpu_user_rhs.py (GPU)."""
+import numpy as np
+
+import cases
+
+
+def lv_twin(ude):
+    """the catalog's LV UDE (test/UDETests.jl:20-28; csrc RhsLvUde<0>) written as expressions"""
+    return ude.expression_rhs(d=2, nn_out=1, scalars=("r", "m", "theta"), du=["r*u1 - y1", "theta*y1 - m*u2"], name="LV_TWIN")
+
+
+def epidemic(ude):
+    """not in the catalog: three states, one covariate, a time input, two network outputs, nonlinear in states, parameters AND
+    network outputs (so the VJP needs the stashed y), with abs / exp / a rational term"""
+    return ude.expression_rhs(
+        d=3, n_cov=1, nn_out=2, scalars=("beta", "gamma", "K"), time_input=(0.5, -0.25),
+        du=["-beta*u1*u2/(1 + u1**2) + y1*x1",
+            "beta*u1*u2/(1 + u1**2) - gamma*u2*abs(y2) + 0.1*exp(-u3)",
+            "gamma*u2*abs(y2) - u3*y1**2/K"], name="EPIDEMIC")
+
+
+def register(ude, name, rhs, sc0):
+    """make the right-hand side reachable through cases.make_case(name, ...)"""
+    cases.RHS_SPECS[name] = (rhs.kind, rhs.d, rhs.n_cov, rhs.nn_in, rhs.nn_out, len(rhs.scalar_names), False, tuple(sc0))
+
+
+def make(ude, name, rhs, sc0, loss, solver, **kw):
+    register(ude, name, rhs, sc0)
+    prob, theta = cases.make_case(name, loss, solver, **kw)
+    prob.user_rhs = rhs
+    return prob, theta
+
+
+def numpy_loss_grad(prob, theta):
+    """loss and complex-step gradient of model 0 from the NumPy twin (oracle/ude_oracle_np.py)"""
+    from oracle import ude_oracle_np as onp
+    L = onp.loss(prob, np.asarray(theta, dtype=np.float64))
+    g = onp.complex_step_grad(prob, theta)
+    return L, np.array([g[k] for k in range(len(theta))])

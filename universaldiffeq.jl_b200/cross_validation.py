@@ -94,6 +94,7 @@ def stack_models(models: List[UDE], loss_function, regularization_weight=0.0, lo
                     time_scale=p0.time_scale, time_shift=p0.time_shift, loss_kind=p0.loss_kind, pred_length=p0.pred_length,
                     proc_inv_dt=p0.proc_inv_dt, shoot_from_theta=p0.shoot_from_theta, shoot_first_scored=p0.shoot_first_scored,
                     remove_ends=p0.remove_ends, preroll_eps=p0.preroll_eps, A=p0.A, B=p0.B)
+    big.user_rhs = p0.user_rhs
     big.off_w1, big.off_b1, big.off_w2, big.off_b2 = p0.off_w1, p0.off_b1, p0.off_w2, p0.off_b2
     big.off_scalar, big.off_series_param, big.n_pm = list(p0.off_scalar), p0.off_series_param, p0.n_pm
     col, ser = 0, 0

@@ -203,6 +203,8 @@ class UDE:
                       n_cov=self.n_cov, n_scalars=len(self.rhs.scalar_names), has_series_param=self.rhs.series_param is not None,
                       solver=self.solvers.kind, substeps=self.solvers.substeps, time_scale=self.rhs.time_scale,
                       time_shift=self.rhs.time_shift)
+        if self.rhs.kind >= 1000:           # expression right-hand side (user_rhs.expression_rhs)
+            p.user_rhs = self.rhs
         p.default_layout(n_series_param=n_series)
         p.data, p.times = self.data, self.times
         if self.multi:

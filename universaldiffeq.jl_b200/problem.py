@@ -52,6 +52,7 @@ class Problem:
     substeps: int = 4
     time_scale: float = 1.0
     time_shift: float = 0.0
+    user_rhs: object = None          # rhs_kind >= 1000: the expression right-hand side (user_rhs.UserRhs) the kind stands for
     # process_model layout (offsets inside process_model); filled by ``default_layout``
     off_w1: int = 0
     off_b1: int = 0
