@@ -242,22 +242,23 @@ def ensure_kernels(rhs: UserRhs, hidden: int, solver: int, verbose: bool = False
     if not os.path.exists(so):
         os.makedirs(_CACHE, exist_ok=True)
         src = os.path.join(_CACHE, f"ude_user_{tag}.cu")
+        tmp = f".{os.getpid()}.tmp"                   # several ranks may build the same plugin at once: private files, atomic renames
         label = f"user{rhs.kind}_g{G}h{HPL}"
         regs = "\n".join(f'  register_one<F64, RhsUser, {G}, {HPL}, {minb}, {solver}, {lk}, false>("{label}", 0);'
                          for lk in (("LK_STATE",) if solver == P.EULER else ("LK_STATE", "LK_TRAJ", "LK_DM")))
-        with open(src, "w") as fh:
+        with open(src + tmp, "w") as fh:
             fh.write("// generated by universaldiffeq.jl_b200/user_rhs.py from the expressions of a user right-hand side -- do not edit\n"
                      '#include "ude_inst.cuh"\nnamespace ude {\nnamespace f64 {\n' + rhs.cuda_trait + "}  // namespace f64\n}  // namespace ude\n"
                      "namespace {\nusing namespace ude;\nusing ude::f64::RhsUser;\nRegisterKernels reg([] {\n" + regs + "\n});\n}  // namespace\n")
-        lib = _build.build()
-        cmd = [_build.NVCC, *_build.FLAGS, "-I", _build.CSRC, "-shared", "-o", so + ".tmp", src, "-L", _build.CSRC, "-lude_cuda", "-lcudart",
+        os.replace(src + tmp, src)
+        _build.build()
+        cmd = [_build.NVCC, *_build.FLAGS, "-I", _build.CSRC, "-shared", "-o", so + tmp, src, "-L", _build.CSRC, "-lude_cuda", "-lcudart",
                "-Xlinker", "-rpath", "-Xlinker", _build.CSRC]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for the generated right-hand side ({src}):\n{r.stdout}\n{r.stderr}")
         if verbose and r.stderr:
             print(r.stderr)
-        os.replace(so + ".tmp", so)
-        del lib
+        os.replace(so + tmp, so)
     _loaded[so] = ctypes.CDLL(so, mode=ctypes.RTLD_GLOBAL)
     return so
