@@ -62,7 +62,7 @@ def rhs(p, pm, series_local, series_global, u, t):
         ur = p.user_rhs
         x = np.concatenate([u, X, [p.time_scale * t + p.time_shift]]) if ur.has_time_input else np.concatenate([u, X])
         y = W2 @ np.tanh(W1 @ x + b1) + b2
-        return ur.du_numpy(u, X, y, [pm[o] for o in p.off_scalar])
+        return ur.du_numpy(u, X, y, [pm[o] for o in p.off_scalar], pm[p.off_series_param + series_local] if p.has_series_param else None)
     if k in (0, 4):
         x = np.concatenate([u, X])
     elif k == 1:

@@ -45,6 +45,27 @@ def test_expressions_restating_a_catalog_entry_equal_the_catalog_kernel(ude, los
     assert worst[0] <= 1.0, worst
 
 
+@pytest.mark.parametrize("loss,solver,n_models", [("cond_lik", 0, 1), ("multi_shoot", 1, 1), ("shoot_theta", 0, 1), ("mse", 0, 2)])
+def test_per_series_parameter(ude, loss, solver, n_models):
+    """`series_param="r"`: one trainable parameter per series (MultiCustomDerivatives' p.r[i]); the expression form of the
+    catalog's per-series growth model against the hand-written kernel and the C oracle, also on a many-model handle"""
+    rhs = urc.growth_twin(ude)
+    kw = dict(hidden=4, lengths=(5, 3, 4, 6), n_models=n_models)
+    prob_u, theta = urc.make(ude, "user_growth", rhs, (), loss, solver, **kw)
+    prob_c, theta_c = cases.make_case("series_growth_d1", loss, solver, **kw)
+    assert np.array_equal(theta, theta_c)
+    L_ref, g_ref = oracle.loss_grad(prob_c, theta)
+    with ude.Engine(prob_u) as eng:
+        assert f"user{rhs.kind}" in eng.kernel_name()
+        Lu, gu = eng.loss_grad(theta)
+    with ude.Engine(prob_c) as eng:
+        Lc, gc = eng.loss_grad(theta)
+    assert np.max(np.abs(Lu - Lc) / np.abs(Lc)) <= 1e-13 and cases.relerr(gu, gc) < 1e-12
+    assert np.max(np.abs(Lu - L_ref) / np.abs(L_ref)) < TOL
+    worst = cases.grad_mismatch(prob_c, gu, g_ref, TOL)
+    assert worst[0] <= 1.0, worst
+
+
 @pytest.mark.parametrize("loss,solver,hidden", [("cond_lik", 0, 6), ("multi_shoot", 1, 6), ("deriv_match", 0, 5), ("shoot_theta", 0, 12),
                                                 ("mse", 1, 20)])
 def test_right_hand_side_outside_the_catalog(ude, loss, solver, hidden):

@@ -20,6 +20,9 @@ def test_generated_trait_and_twin(ude):
     assert np.allclose(rhs.du_numpy(u, [], y, sc), [0.1 * 0.7 - 0.4, 0.3 * 0.4 - 0.2 * 1.3])
     ep = urc.epidemic(ude)
     assert ep.nn_in == 3 + 1 + 1 and ep.has_time_input and "sgn1(" in ep.cuda_trait and "fabs(" in ep.cuda_trait
+    gr = urc.growth_twin(ude)
+    assert gr.series_param == "r" and "SERIES = true" in gr.cuda_trait and "gseries += kb0*u1*y1;" in gr.cuda_trait
+    assert np.allclose(gr.du_numpy([2.0], [], [0.5], [], 0.3), [0.3 * 2.0 * 0.5])
     with pytest.raises(ValueError):
         ude.expression_rhs(d=1, nn_out=1, du=["q*u1"])                        # unknown symbol
     with pytest.raises(ValueError):

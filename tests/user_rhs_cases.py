@@ -19,9 +19,16 @@ def epidemic(ude):
             "gamma*u2*abs(y2) - u3*y1**2/K"], name="EPIDEMIC")
 
 
+def growth_twin(ude):
+    """the catalog's per-series growth model (docs/src/MultipleTimeSeries.md:51-55; csrc RhsSeriesGrowth<1>) as an expression
+    with one trainable parameter per series"""
+    return ude.expression_rhs(d=1, nn_out=1, series_param="r", du=["r*u1*y1"], name="GROWTH_TWIN")
+
+
 def register(ude, name, rhs, sc0):
     """make the right-hand side reachable through cases.make_case(name, ...)"""
-    cases.RHS_SPECS[name] = (rhs.kind, rhs.d, rhs.n_cov, rhs.nn_in, rhs.nn_out, len(rhs.scalar_names), False, tuple(sc0))
+    cases.RHS_SPECS[name] = (rhs.kind, rhs.d, rhs.n_cov, rhs.nn_in, rhs.nn_out, len(rhs.scalar_names), rhs.series_param is not None,
+                             tuple(sc0))
 
 
 def make(ude, name, rhs, sc0, loss, solver, **kw):

@@ -93,8 +93,10 @@ def _printer():
 
 
 def expression_rhs(d: int, nn_out: int, du: Sequence[str], scalars: Sequence[str] = (), n_cov: int = 0,
-                   time_input: Optional[tuple] = None, name: str = "USER") -> UserRhs:
-    """Build a right-hand side from expressions (module docstring).  `du[i]` is d u_{i+1} / dt."""
+                   time_input: Optional[tuple] = None, series_param: Optional[str] = None, name: str = "USER") -> UserRhs:
+    """Build a right-hand side from expressions (module docstring).  `du[i]` is d u_{i+1} / dt.  `series_param="r"` adds one
+    trainable parameter PER SERIES (MultiCustomDerivatives' `p.r[i]`, docs/src/MultipleTimeSeries.md:51-55), visible in the
+    expressions under that name."""
     sp = _sympy()
     if len(du) != d:
         raise ValueError("one expression per state")
@@ -111,11 +113,17 @@ def expression_rhs(d: int, nn_out: int, du: Sequence[str], scalars: Sequence[str
         if str(n) in table or not str(n).isidentifier():
             raise ValueError(f"scalar parameter name {n!r} is not an identifier or shadows a state / covariate / network output")
         table[str(n)] = s
+    sps = []
+    if series_param is not None:
+        if str(series_param) in table or not str(series_param).isidentifier():
+            raise ValueError(f"per-series parameter name {series_param!r} is not an identifier or is already taken")
+        sps = [sp.Symbol("ps_" + str(series_param), real=True)]
+        table[str(series_param)] = sps[0]
     table.update(abs=sp.Abs, exp=sp.exp, log=sp.log, sqrt=sp.sqrt, tanh=sp.tanh)
     exprs = []
     for e in du:
         ex = sp.sympify(e, locals=table)
-        unknown = ex.free_symbols - set(us + xs + ys + ps)
+        unknown = ex.free_symbols - set(us + xs + ys + ps + sps)
         if unknown:
             raise ValueError(f"unknown symbols {sorted(map(str, unknown))} in {e!r}: use u1..u{d}, x1..x{n_cov}, y1..y{nn_out} and {list(scalars)}")
         exprs.append(ex)
@@ -124,7 +132,8 @@ def expression_rhs(d: int, nn_out: int, du: Sequence[str], scalars: Sequence[str
     yb = [sp.diff(seed, y) for y in ys]
     ub = [sp.diff(seed, u) for u in us]
     gp = [sp.diff(seed, p) for p in ps]
-    need_y = any(y in ex.free_symbols for ex in yb + ub + gp for y in ys)
+    gs = [sp.diff(seed, q) for q in sps]
+    need_y = any(y in ex.free_symbols for ex in yb + ub + gp + gs for y in ys)
     pr = _printer()
 
     def block(targets, values, op):
@@ -148,16 +157,19 @@ def expression_rhs(d: int, nn_out: int, du: Sequence[str], scalars: Sequence[str
         for i, s in enumerate(ps):
             if s in used:
                 out.append(f"    const real {s.name} = c.sc[{i}];")
+        for s in sps:
+            if s in used:
+                out.append(f"    const real {s.name} = c.series_param;")
         return "\n".join(out)
 
     free_f = set().union(*[e.free_symbols for e in exprs])
-    free_b = set().union(*[e.free_symbols for e in yb + ub + gp]) if (yb or ub or gp) else set()
+    free_b = set().union(*[e.free_symbols for e in yb + ub + gp + gs]) if (yb or ub or gp or gs) else set()
     din = d + n_cov + (1 if time_input is not None else 0)
     tin = f"    x[{d + n_cov}] = (real)(c.time_scale * t + c.time_shift);\n" if time_input is not None else ""
     kb_binds = "\n".join(f"    const real kb{i} = kb[{i}];" for i in range(d))
     trait = f"""struct RhsUser {{
   static constexpr int KIND = @KIND@, D = {d}, NX = {n_cov}, DIN = {din}, DOUT = {nn_out}, NS = {len(ps)};
-  static constexpr bool NEED_Y = {"true" if need_y else "false"}, SERIES = false;
+  static constexpr bool NEED_Y = {"true" if need_y else "false"}, SERIES = {"true" if sps else "false"};
   __device__ __forceinline__ static void input(const real (&U)[D], const real* X, double t, const RhsCtx& c, real (&x)[DIN]) {{
 #pragma unroll
     for (int j = 0; j < D; ++j) x[j] = U[j];
@@ -169,11 +181,11 @@ def expression_rhs(d: int, nn_out: int, du: Sequence[str], scalars: Sequence[str
 {block([f"du[{i}]" for i in range(d)], exprs, "=")}
   }}
   __device__ __forceinline__ static void combine_vjp(const real (&U)[D], const real* X, const real (&y)[DOUT], const RhsCtx& c,
-                                                     const real (&kb)[D], real (&yb)[DOUT], real (&ub)[D], real* gsc, real&) {{
+                                                     const real (&kb)[D], real (&yb)[DOUT], real (&ub)[D], real* gsc, real& gseries) {{
 {kb_binds}
 {binds(free_b)}
-{block([f"yb[{i}]" for i in range(nn_out)] + [f"ub[{i}]" for i in range(d)] + [f"gsc[{i}]" for i in range(len(ps))],
-       yb + ub + gp, "@OP@")}
+{block([f"yb[{i}]" for i in range(nn_out)] + [f"ub[{i}]" for i in range(d)] + [f"gsc[{i}]" for i in range(len(ps))] + ["gseries"] * len(sps),
+       yb + ub + gp + gs, "@OP@")}
   }}
 }};
 """
@@ -190,13 +202,14 @@ def expression_rhs(d: int, nn_out: int, du: Sequence[str], scalars: Sequence[str
     def _abs_cs(z):
         return z * (-1.0 if np.real(z) < 0 else 1.0)
 
-    f_np = sp.lambdify([us, xs, ys, ps], exprs, modules=[{"Abs": _abs_cs, "sign": lambda z: -1.0 if np.real(z) < 0 else 1.0}, "numpy"])
+    f_np = sp.lambdify([us, xs, ys, ps, sps], exprs, modules=[{"Abs": _abs_cs, "sign": lambda z: -1.0 if np.real(z) < 0 else 1.0}, "numpy"])
 
-    def du_numpy(u, X, y, sc):
-        return np.array(f_np(list(u), list(X), list(y), list(sc)))
+    def du_numpy(u, X, y, sc, series_value=None):
+        return np.array(f_np(list(u), list(X), list(y), list(sc), [series_value] if sps else []))
 
     ts, tsh = (float(time_input[0]), float(time_input[1])) if time_input is not None else (1.0, 0.0)
-    rhs = UserRhs(kind, d, n_cov, din, nn_out, tuple(str(s) for s in scalars), ts, tsh, time_input is not None, trait, du_numpy, None, name)
+    rhs = UserRhs(kind, d, n_cov, din, nn_out, tuple(str(s) for s in scalars), ts, tsh, time_input is not None, trait, du_numpy,
+                  str(series_param) if series_param is not None else None, name)
     _by_kind[kind] = rhs
     return rhs
 
