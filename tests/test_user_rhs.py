@@ -29,6 +29,8 @@ def test_generated_trait_and_twin(ude):
         ude.expression_rhs(d=1, nn_out=1, scalars=("u1",), du=["u1"])         # shadows a state
     with pytest.raises(ValueError):
         ude.expression_rhs(d=2, nn_out=1, du=["u1"])                          # one expression per state
+    with pytest.raises(ValueError):
+        ude.expression_rhs(d=9, nn_out=1, du=["y1"] * 9)                      # UDE_MAX_D
 
 
 @pytest.mark.parametrize("loss", ["cond_lik", "multi_shoot", "deriv_match"])
@@ -54,4 +56,4 @@ def test_plugin_compiles_and_registers(ude):
     assert os.path.exists(so) and so in ude.user_rhs._loaded
     assert ude.user_rhs.ensure_kernels(rhs, 6, 0) == so
     src = open(so[:-3] + ".cu").read()
-    assert "register_one<F64, RhsUser, 2, 3, 2, 0, LK_TRAJ, false>" in src and f"KIND = {rhs.kind}" in src
+    assert f"register_one<F64, RhsUser{rhs.kind}, 2, 3, 2, 0, LK_TRAJ, false>" in src and f"KIND = {rhs.kind}" in src

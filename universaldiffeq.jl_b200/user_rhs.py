@@ -100,7 +100,7 @@ def expression_rhs(d: int, nn_out: int, du: Sequence[str], scalars: Sequence[str
     sp = _sympy()
     if len(du) != d:
         raise ValueError("one expression per state")
-    if not (1 <= d <= P.MAX_D if hasattr(P, "MAX_D") else 8) or nn_out < 1:
+    if not (1 <= d <= 8) or nn_out < 1:                               # UDE_MAX_D
         raise ValueError("d must be 1..8 and nn_out >= 1")
     if len(scalars) > 8:
         raise ValueError("at most 8 scalar parameters (UDE_MAX_SCALARS)")
@@ -197,7 +197,7 @@ def expression_rhs(d: int, nn_out: int, du: Sequence[str], scalars: Sequence[str
         fixed.append(ln)
     trait = "\n".join(fixed)
     kind = USER_KIND0 + int(hashlib.sha1(trait.encode()).hexdigest()[:6], 16)
-    trait = trait.replace("@KIND@", str(kind))
+    trait = trait.replace("@KIND@", str(kind)).replace("struct RhsUser {", f"struct RhsUser{kind} {{")      # one type name per right-hand side
 
     def _abs_cs(z):
         return z * (-1.0 if np.real(z) < 0 else 1.0)
@@ -257,12 +257,12 @@ def ensure_kernels(rhs: UserRhs, hidden: int, solver: int, verbose: bool = False
         src = os.path.join(_CACHE, f"ude_user_{tag}.cu")
         tmp = f".{os.getpid()}.tmp"                   # several ranks may build the same plugin at once: private files, atomic renames
         label = f"user{rhs.kind}_g{G}h{HPL}"
-        regs = "\n".join(f'  register_one<F64, RhsUser, {G}, {HPL}, {minb}, {solver}, {lk}, false>("{label}", 0);'
+        regs = "\n".join(f'  register_one<F64, RhsUser{rhs.kind}, {G}, {HPL}, {minb}, {solver}, {lk}, false>("{label}", 0);'
                          for lk in (("LK_STATE",) if solver == P.EULER else ("LK_STATE", "LK_TRAJ", "LK_DM")))
         with open(src + tmp, "w") as fh:
             fh.write("// generated by universaldiffeq.jl_b200/user_rhs.py from the expressions of a user right-hand side -- do not edit\n"
                      '#include "ude_inst.cuh"\nnamespace ude {\nnamespace f64 {\n' + rhs.cuda_trait + "}  // namespace f64\n}  // namespace ude\n"
-                     "namespace {\nusing namespace ude;\nusing ude::f64::RhsUser;\nRegisterKernels reg([] {\n" + regs + "\n});\n}  // namespace\n")
+                     f"namespace {{\nusing namespace ude;\nusing ude::f64::RhsUser{rhs.kind};\nRegisterKernels reg([] {{\n" + regs + "\n});\n}  // namespace\n")
         os.replace(src + tmp, src)
         _build.build()
         cmd = [_build.NVCC, *_build.FLAGS, "-I", _build.CSRC, "-shared", "-o", so + tmp, src, "-L", _build.CSRC, "-lude_cuda", "-lcudart",
