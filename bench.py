@@ -497,6 +497,31 @@ def main():
                                     "ms_per_eval": (time.perf_counter() - t0) / 20 * 1e3}
         except Exception as ex:
             others["ukf_c1"] = {"error": str(ex)[:200]}
+        try:       # a right-hand side written as expressions (generated trait -> nvcc plugin) against the hand-written kernel of the same model
+            P = ude.problem
+            rngu = np.random.default_rng(0)
+            Yu, tsu = ude.synthetic.lotka_volterra_data(rngu, 20000, 30, random_u0=True)
+            t0 = time.perf_counter()
+            urhs = ude.expression_rhs(d=2, nn_out=1, scalars=("r", "m", "theta"), du=["r*u1 - y1", "theta*y1 - m*u2"])
+            ude.user_rhs.ensure_kernels(urhs, 10, 0)
+            ures = {"workload": "LV UDE (test/UDETests.jl:20-28) NN 2->10->1, multiple shooting pl=5, 20000 series x 30 pts",
+                   "generate_and_load_s": time.perf_counter() - t0}
+            for label, kind, ur in (("hand_written", P.RHS_LV_UDE, None), ("generated", urhs.kind, urhs)):
+                pu = P.Problem(d=2, nn_in=2, nn_hidden=10, nn_out=1, rhs_kind=kind, n_scalars=3, solver=P.RK4, substeps=4,
+                               loss_kind=P.LOSS_MULTI_SHOOT, pred_length=5).default_layout()
+                pu.user_rhs = ur
+                ude.synthetic._tile_series(pu, Yu, tsu)
+                pu.finalize()
+                thu = ude.synthetic.theta_from(pu, ude.synthetic.init_pm(pu, np.random.default_rng(1), scalars=(1.0, 0.5, 0.5)), np.asarray(pu.data))
+                eu, _ = cx.engine(pu)
+                try:
+                    ru = time_resident(cx, eu, pu, thu, 10, 3)
+                    ures[label] = {"kernel": eu.kernel_name(), "steps_per_s": eu.steps_per_eval() / (ru["ms_step"] * 1e-3), "ms_per_step": ru["ms_step"]}
+                finally:
+                    eu.close()
+            others["user_rhs_lv"] = ures
+        except Exception as ex:
+            others["user_rhs_lv"] = {"error": str(ex)[:200]}
         try:       # the same loss on a many-model handle: 100 members x 10 leave-future-out folds of the coral UDE in one launch chain
             p4, th4 = ude.synthetic.config_c4(n_members=100, n_folds=10)
             with ude.Engine(p4, device=local) as e4:
