@@ -99,3 +99,20 @@ def test_user_rhs_through_the_host_api_and_the_filter(ude):
         L, g, gF = eng.ukf_loss_grad(theta, F, Peta, alpha=1.0)
     n_u = prob.d * prob.n_cols
     assert abs(L - ref) < TOL * abs(ref) and cases.relerr(g[n_u:], g_pm) < TOL and cases.relerr(gF.reshape(-1, order="F"), g_F) < TOL
+
+
+@pytest.mark.parametrize("m,hidden", [(3, 6), (10, 10)])
+def test_one_hot_series_network_on_the_gpu(ude, m, hidden):
+    """docs/src/MultipleTimeSeries.md:72-92 (m = 10 series, hidden 10 in the docs): one-hot series input through generated kernels
+    with n_cov = m constant covariates; loss and gradient against the NumPy twin, then a short training run"""
+    model, nn, df = urc.one_hot_model(ude, m=m, n_pts=6, hidden=hidden)
+    prob = ude.build_problem(model, "conditional likelihood")
+    theta = model.parameters + 0.01 * np.random.default_rng(1).normal(size=model.parameters.shape)
+    L_ref, g_ref = urc.numpy_loss_grad(prob, theta)
+    with ude.Engine(prob) as eng:
+        L, g = eng.loss_grad(theta)
+    assert abs(L[0] - L_ref[0]) < TOL * abs(L_ref[0])
+    worst = cases.grad_mismatch(prob, g, g_ref, TOL)
+    assert worst[0] <= 1.0, worst
+    ude.train_(model, "conditional likelihood", verbose=False, optim_options=dict(maxiter=40, step_size=0.02))
+    assert np.all(np.isfinite(model.parameters))

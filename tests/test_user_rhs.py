@@ -57,3 +57,20 @@ def test_plugin_compiles_and_registers(ude):
     assert ude.user_rhs.ensure_kernels(rhs, 6, 0) == so
     src = open(so[:-3] + ".cu").read()
     assert f"register_one<F64, RhsUser{rhs.kind}, 2, 3, 2, 0, LK_TRAJ, false>" in src and f"KIND = {rhs.kind}" in src
+
+
+def test_one_hot_series_input(ude):
+    """MultiTimeSeriesNetwork semantics (src/NeuralNetworkConstructors.jl:69-82): NN(vcat(x, distance * onehot(i))) -- here as
+    constant covariates, one per series; the right-hand side the oracle evaluates must be exactly that"""
+    model, nn, df = urc.one_hot_model(ude, m=3, distance=0.5)
+    X = model.X_data_frame
+    assert list(X.columns[2:]) == ["series_is_s00", "series_is_s01", "series_is_s02"] and X.shape == (3, 5)
+    p = ude.build_problem(model, "conditional likelihood")
+    assert p.n_cov == 3 and p.nn_in == 5
+    W1, b1, W2, b2 = (np.asarray(nn[k]) for k in ("layer_1.weight", "layer_1.bias", "layer_2.weight", "layer_2.bias"))
+    u = np.array([0.7, 1.1])
+    for i in range(3):
+        oh = np.zeros(3); oh[i] = 0.5
+        ref = W2 @ np.tanh(W1 @ np.concatenate([u, oh]) + b1) + b2
+        for t in (-3.0, 0.4, 50.0):                   # constant in time, before and after the single knot
+            assert np.allclose(onp.rhs(p, model.process_model, i, i, u, t), ref, rtol=1e-14, atol=0)

@@ -44,3 +44,15 @@ def numpy_loss_grad(prob, theta):
     L = onp.loss(prob, np.asarray(theta, dtype=np.float64))
     g = onp.complex_step_grad(prob, theta)
     return L, np.array([g[k] for k in range(len(theta))])
+
+
+def one_hot_model(ude, m=3, n_pts=8, hidden=6, distance=0.5, seed=3):
+    """docs/src/MultipleTimeSeries.md:72-92: one network for m series, each told which series it is through a one-hot input"""
+    import pandas as pd
+    Y, ts = ude.synthetic.lotka_volterra_data(np.random.default_rng(0), m, n_pts, random_u0=True)
+    df = pd.concat([pd.DataFrame({"time": ts + 0.1 * s, "series": f"s{s:02d}", "x1": Y[s, 0], "x2": Y[s, 1]}) for s in range(m)],
+                   ignore_index=True)
+    X = ude.one_hot_series_covariates(df, distance=distance)
+    rhs = ude.expression_rhs(d=2, n_cov=m, nn_out=2, du=["y1", "y2"], name="ONE_HOT_NODE")
+    _, nn = ude.SimpleNeuralNetwork(2 + m, 2, hidden=hidden, seed=seed)
+    return ude.MultiCustomDerivatives(df, rhs, {"NN": nn}, X=X), nn, df

@@ -11,7 +11,7 @@ from ._capi import (Engine, UdeError, device_count, measure_fp64_peak, get_uniqu
                     OPT_SPARSE_UHAT_IO, OPT_UKF_CAUSAL_INTERVAL)
 from . import user_rhs  # noqa: F401
 from .user_rhs import expression_rhs, UserRhs  # noqa: F401
-from .models import (CustomDerivatives, NODE, MultiNODE, MultiCustomDerivatives, SimpleNeuralNetwork, CudaRK4, CudaTsit5,  # noqa: F401
+from .models import (one_hot_series_covariates, CustomDerivatives, NODE, MultiNODE, MultiCustomDerivatives, SimpleNeuralNetwork, CudaRK4, CudaTsit5,  # noqa: F401
                      LV_UDE, LV_UDE_X, LV_UDE_ABS, FISHERY, node_rhs, node_time_rhs, nn_decay_rhs, series_growth_rhs, UDE)
 from .training import (train_, adam_multi_gpu, gradient_descent_, marginal_likelihood_, marginal_likelihood_many_, spline_gradient_matching_, SplineGradientMatching, neural_gradient_matching_, NeuralGradientMatching, kalman_filter_, save_model_parameters, load_model_parameters_, conditional_likelihood, default_loss, multiple_shooting_loss, shooting_loss,  # noqa: F401
                        derivative_matching_loss, errors_to_matrix, build_problem, predictions, forecast, adam_host)

@@ -158,6 +158,27 @@ def interpolate_covariates(X: pd.DataFrame, time_column_name, series_column_name
     return n_cov, off, t_long[order], x_long[order]
 
 
+def one_hot_series_covariates(data: pd.DataFrame, time_column_name="time", series_column_name="series", distance=1.0) -> pd.DataFrame:
+    """Covariate frame that hands the network a one-hot encoding of the series (scaled by `distance`): the reference's
+    `MultiTimeSeriesNetwork` (src/NeuralNetworkConstructors.jl:60-82) and the `vcat(u, one_hot)` model of
+    docs/src/MultipleTimeSeries.md:72-92.  One row per series: a single knot is a constant covariate (flat extrapolation,
+    src/covariates.jl:45-48), so `NN([u; X(t, i)])` IS `NN([u; distance * onehot(i)])`.  Use with
+
+        X = one_hot_series_covariates(data)
+        rhs = expression_rhs(d=2, n_cov=X.shape[1] - 2, nn_out=2, du=["y1", "y2"])        # any m: kernels are generated on demand
+        model = MultiCustomDerivatives(data, rhs, {"NN": SimpleNeuralNetwork(2 + m, 2)[1]}, X=X)
+
+    (for m <= 2 series the catalog's `MultiNODE(data, X=X)` has pre-compiled kernels)."""
+    labels = sorted(pd.unique(data[series_column_name]))
+    t0 = data.groupby(series_column_name)[time_column_name].min()
+    rows = []
+    for i, lab in enumerate(labels):
+        row = {time_column_name: float(t0[lab]), series_column_name: lab}
+        row.update({f"series_is_{l2}": (float(distance) if j == i else 0.0) for j, l2 in enumerate(labels)})
+        rows.append(row)
+    return pd.DataFrame(rows)
+
+
 # ---- model objects ---------------------------------------------------------------------------------------------------
 @dataclass
 class UDE:
