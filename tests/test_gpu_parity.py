@@ -476,3 +476,17 @@ def test_no_device_memory_leak_over_handle_lifetimes(ude):
     torch.cuda.synchronize()
     free1 = torch.cuda.mem_get_info()[0]
     assert free0 - free1 < 64 * 2 ** 20, (free0, free1)      # the driver's own pools may keep a little
+
+
+@pytest.mark.parametrize("rhs,hidden,n_models", [("lv_ude", 20, 1), ("node_time_d3", 24, 3), ("fishery", 32, 1), ("lv_ude_abs", 16, 2),
+                                                 ("series_growth_d1", 16, 1), ("node_d4", 100, 2), ("node_d2x2", 32, 1)])
+def test_catalog_shapes_compiled_on_demand(ude, rhs, hidden, n_models):
+    """Hidden widths / models per handle without a pre-compiled instance (the parametric UDEs above 12 hidden units, NODE shapes
+    above 12 units on a many-model handle): Engine compiles the same hand-written trait for that geometry on first use
+    (user_rhs.ensure_catalog_kernels) instead of answering UNSUPPORTED; parity bar unchanged.  tools/fuzz_parity.py draws 800
+    random (right-hand side, loss, solver, width, lengths, models) cases through the same path: profiles/fuzz_r02.log."""
+    for loss, solver in (("cond_lik", 0), ("multi_shoot", 0), ("deriv_match", 0)):
+        prob, theta = cases.make_case(rhs, loss, solver, hidden=hidden, lengths=(6, 3, 1, 5, 4, 2), n_models=n_models, skip=(loss == "cond_lik"))
+        with ude.Engine(prob) as eng:
+            assert eng.kernel_name().endswith("_jit")
+        _check(prob, theta, ude)

@@ -1,0 +1,83 @@
+"""Randomised differential test: CUDA (through the C ABI) against the C oracle on random small problems -- right-hand side,
+loss form, solver, hidden width (so: kernel family and geometry), substeps, ragged series lengths, models per handle, skip
+masks, prediction-block length.  usage (under gpurun): python tools/fuzz_parity.py [--n 300] [--seed 0]
+Prints one line per failure and a summary; exit code 1 if anything failed."""
+import argparse
+import os
+import sys
+import traceback
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, default=300)
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--prebuild", action="store_true", help="no GPU: only compile the on-demand kernel plugins the same random cases may need")
+    a = ap.parse_args()
+    import ude_b200 as ude
+    import cases
+    from oracle import oracle
+    rng = np.random.default_rng(a.seed)
+    names = list(cases.RHS_SPECS)
+    fails, kernels, unsup = 0, {}, set()
+    for it in range(a.n):
+        rhs = names[int(rng.integers(len(names)))]
+        loss = cases.LOSSES[int(rng.integers(len(cases.LOSSES)))]
+        solver = int(rng.integers(2))
+        d = cases.RHS_SPECS[rhs][1]
+        hmax = 128 if rhs in ("node_d8", "node_d4x1", "node_d4", "node_d2") else 32
+        hidden = int(rng.choice([1, 2, 3, 5, 7, 8, 10, 12, 16, 17, 24, 31, 32] + ([33, 64, 100, 128] if hmax == 128 else [])))
+        n_models = int(rng.choice([1, 1, 1, 2, 3]))
+        n_series = n_models * int(rng.integers(1, 5))
+        lengths = tuple(int(x) for x in rng.choice([1, 2, 3, 4, 5, 6, 9, 11, 17, 30], size=n_series))
+        substeps = int(rng.choice([1, 2, 3, 4]))
+        pl = int(rng.choice([1, 2, 5, 7]))
+        kw = dict(hidden=hidden, lengths=lengths, n_models=n_models, seed=int(rng.integers(1 << 30)), substeps=substeps,
+                  skip=bool(rng.integers(2)) and loss in ("cond_lik", "mse"), pred_length=pl)
+        if cases.RHS_SPECS[rhs][6] and n_models > 1 and n_series % n_models:
+            continue
+        if a.prebuild:
+            if hidden >= 13:
+                prob, theta = cases.make_case(rhs, loss, solver, **kw)
+                ude.user_rhs.ensure_catalog_kernels(prob, 0)
+            continue
+        try:
+            prob, theta = cases.make_case(rhs, loss, solver, **kw)
+            L_ref, g_ref = oracle.loss_grad(prob, theta)
+            with ude.Engine(prob) as eng:
+                kn = eng.kernel_name()
+                L, g = eng.loss_grad(theta)
+                ok_steps = eng.steps_per_eval() == oracle.count_steps(prob)
+            kernels[kn] = kernels.get(kn, 0) + 1
+            el = float(np.max(np.abs(L - L_ref) / np.abs(L_ref)))
+            worst = cases.grad_mismatch(prob, g, g_ref, rtol=1e-10)
+            zeros_ok = bool(np.all(g[g_ref == 0.0] == 0.0))
+            if not (np.all(np.isfinite(g)) and el < 1e-10 and worst[0] <= 1.0 and zeros_ok and ok_steps):
+                fails += 1
+                print("FAIL", it, rhs, loss, solver, kw, kn, "loss err", el, "grad", worst, "zeros", zeros_ok, "steps", ok_steps, flush=True)
+        except ude.UdeError as ex:
+            if ex.code == -2:                      # no compiled kernel for this shape: a documented refusal, not a failure
+                kernels["unsupported"] = kernels.get("unsupported", 0) + 1
+                unsup.add((rhs, hidden, n_models > 1))
+                continue
+            fails += 1
+            print("ERROR", it, rhs, loss, solver, kw, repr(ex), flush=True)
+        except Exception:
+            fails += 1
+            print("EXC", it, rhs, loss, solver, kw, flush=True)
+            traceback.print_exc()
+    print("cases", a.n, "failures", fails)
+    for k, v in sorted(kernels.items(), key=lambda kv: -kv[1]):
+        print(f"  {v:4d}  {k}")
+    print("unsupported (rhs, hidden, many-model):", sorted(unsup))
+    sys.exit(1 if fails else 0)
+
+
+if __name__ == "__main__":
+    main()

@@ -238,6 +238,19 @@ class Engine:
             n = int(self.lib.ude_n_theta(self.handle))
             if n != p.n_theta:
                 raise RuntimeError(f"theta layout mismatch: library {n}, host {p.n_theta}")
+            # a catalog right-hand side at a shape (hidden width, many models) without a pre-compiled kernel: compile the same
+            # hand-written trait for that geometry now and register it (user_rhs.ensure_catalog_kernels), then plan again
+            if not self.lib.ude_kernel_name(self.handle) and p.rhs_kind < 1000 and lanes_per_segment == 0 and hidden_per_lane == 0 \
+                    and weights_in_smem == 0 and os.environ.get("UDE_JIT", "1") != "0" and not os.environ.get("UDE_KERNEL"):
+                msg = self.lib.ude_last_error(self.handle).decode()
+                if "no compiled sm_100a kernel" in msg:
+                    from . import user_rhs
+                    try:
+                        user_rhs.ensure_catalog_kernels(p, dtype)
+                    except ValueError as ex:
+                        raise UdeError(-2, f"{msg} [{ex}]")
+                    if not self.lib.ude_kernel_name(self.handle):
+                        raise UdeError(-2, self.lib.ude_last_error(self.handle).decode())
         except Exception:
             self.close()
             raise

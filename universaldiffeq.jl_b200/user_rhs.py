@@ -275,3 +275,63 @@ def ensure_kernels(rhs: UserRhs, hidden: int, solver: int, verbose: bool = False
         os.replace(so + tmp, so)
     _loaded[so] = ctypes.CDLL(so, mode=ctypes.RTLD_GLOBAL)
     return so
+
+
+# ---- catalog right-hand sides at shapes without a pre-compiled instance ------------------------------------------------------
+def _catalog_trait(p) -> Optional[str]:
+    """C++ name of the hand-written trait (csrc/ude_kernel_body.inc) for a catalog problem"""
+    k, d, nx, do = p.rhs_kind, p.d, p.n_cov, p.nn_out
+    if k == P.RHS_NODE and p.nn_in == d + nx and do == d:
+        return f"RhsNode<{d}, {nx}>"
+    if k == P.RHS_NODE_TIME and p.nn_in == d + nx + 1:
+        return f"RhsNodeTime<{d}, {nx}, {do}>"
+    if k == P.RHS_LV_UDE and d == 2 and nx in (0, 1):
+        return f"RhsLvUde<{nx}>"
+    if k == P.RHS_LV_UDE_ABS and d == 2 and nx == 0:
+        return "RhsLvUdeAbs"
+    if k == P.RHS_FISHERY and d == 2 and nx == 1:
+        return "RhsFishery"
+    if k == P.RHS_NN_DECAY and nx == 0:
+        return f"RhsNnDecay<{d}>"
+    if k == P.RHS_SERIES_GROWTH and nx == 0:
+        return f"RhsSeriesGrowth<{d}>"
+    return None
+
+
+def ensure_catalog_kernels(p, dtype: int = 0, verbose: bool = False) -> str:
+    """The library ships the catalog right-hand sides at the shapes of the BASELINE configurations, the reference's tests and
+    docs (hidden width <= 12 for the parametric UDEs, the NODE shapes of csrc/ude_inst_*.cu).  Any other hidden width up to 128,
+    with one or many models per handle, is compiled here on first use -- the same hand-written trait, instantiated for the
+    geometry `geometry(hidden)` picks -- and registered like a user right-hand side.  Raises ValueError if the problem is not a
+    catalog shape."""
+    trait = _catalog_trait(p)
+    if trait is None:
+        raise ValueError("not a catalog right-hand side")
+    G, HPL, minb = geometry(p.nn_hidden)
+    ns, tns = ("F64", "f64") if dtype == 0 else ("F32", "f32")
+    tag = hashlib.sha1(f"{trait}|{ns}|{G}|{HPL}|{minb}|{p.solver}|{_lib_stamp()}".encode()).hexdigest()[:16]
+    so = os.path.join(_CACHE, f"ude_cat_{tag}.so")
+    if so in _loaded:
+        return so
+    if not os.path.exists(so):
+        os.makedirs(_CACHE, exist_ok=True)
+        src = os.path.join(_CACHE, f"ude_cat_{tag}.cu")
+        tmp = f".{os.getpid()}.tmp"
+        label = "".join(ch if ch.isalnum() else "_" for ch in trait).strip("_").lower() + f"_{tns}_g{G}h{HPL}_jit"
+        regs = "\n".join(f'  register_one<{ns}, {tns}::{trait}, {G}, {HPL}, {minb}, {p.solver}, {lk}, false>("{label}", 5);'
+                         for lk in (("LK_STATE",) if p.solver == P.EULER else ("LK_STATE", "LK_TRAJ", "LK_DM")))
+        with open(src + tmp, "w") as fh:
+            fh.write("// generated by universaldiffeq.jl_b200/user_rhs.py: a catalog right-hand side at a shape without a pre-compiled instance\n"
+                     '#include "ude_inst.cuh"\nnamespace {\nusing namespace ude;\nRegisterKernels reg([] {\n' + regs + "\n});\n}  // namespace\n")
+        os.replace(src + tmp, src)
+        _build.build()
+        cmd = [_build.NVCC, *_build.FLAGS, "-I", _build.CSRC, "-shared", "-o", so + tmp, src, "-L", _build.CSRC, "-lude_cuda", "-lcudart",
+               "-Xlinker", "-rpath", "-Xlinker", _build.CSRC]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
+        if verbose and r.stderr:
+            print(r.stderr)
+        os.replace(so + tmp, so)
+    _loaded[so] = ctypes.CDLL(so, mode=ctypes.RTLD_GLOBAL)
+    return so
