@@ -373,6 +373,20 @@ class Engine:
                 o.Peta[i + d * j] = Pe[i, j]
         return o
 
+    def _ukf_call(self, fn):
+        """The filter's auxiliary handle is a many-model one (a model per filter step): a shape whose only pre-compiled kernel
+        is a single-model tensor-core kernel needs the lane-per-hidden-unit kernels compiled on demand (user_rhs)."""
+        rc = fn()
+        if rc == -2 and self.problem.rhs_kind < 1000 and os.environ.get("UDE_JIT", "1") != "0" \
+                and "auxiliary handle: no compiled sm_100a kernel" in self.lib.ude_last_error(self.handle).decode():
+            from . import user_rhs
+            try:
+                user_rhs.ensure_catalog_kernels(self.problem, 0)
+            except ValueError:
+                return rc
+            rc = fn()
+        return rc
+
     def _ukf_factor(self, pnu_factor):
         """(M, d, d) process-noise factors as column-major bytes per model; a single (d, d) factor is shared by every model"""
         d, M = self.problem.d, self.problem.n_models
@@ -394,8 +408,8 @@ class Engine:
         loss = np.zeros(M)
         g = np.zeros_like(th) if want_grad else None
         gF = np.zeros((M, d, d)) if want_grad else None
-        rc = self.lib.ude_ukf_loss_grad(self.handle, C.byref(o), th.ctypes.data, th.shape[0], F.ctypes.data, loss.ctypes.data,
-                                        g.ctypes.data if want_grad else None, gF.ctypes.data if want_grad else None)
+        rc = self._ukf_call(lambda: self.lib.ude_ukf_loss_grad(self.handle, C.byref(o), th.ctypes.data, th.shape[0], F.ctypes.data, loss.ctypes.data,
+                                                               g.ctypes.data if want_grad else None, gF.ctypes.data if want_grad else None))
         if rc != UDE_OK and rc != UDE_NONFINITE:
             self._check(rc)
         if want_grad:
@@ -413,7 +427,8 @@ class Engine:
         o = self._ukf_opts(Peta, alpha, beta, kappa, 0.0)
         xs = np.zeros((d, self.problem.n_cols), order="F")
         Ps = np.zeros((d, d, self.problem.n_cols), order="F")
-        rc = self.lib.ude_ukf_filter(self.handle, C.byref(o), th.ctypes.data, th.shape[0], F.ctypes.data, xs.ctypes.data, Ps.ctypes.data)
+        rc = self._ukf_call(lambda: self.lib.ude_ukf_filter(self.handle, C.byref(o), th.ctypes.data, th.shape[0], F.ctypes.data, xs.ctypes.data,
+                                                            Ps.ctypes.data))
         if rc != UDE_OK and rc != UDE_NONFINITE:
             self._check(rc)
         return xs, Ps
