@@ -18,6 +18,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--n", type=int, default=300)
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--dtype", default="f64", help="f64 (bar 1e-10, per gradient leaf) or f32 (the optional FP32 mode: bar 1e-4, norm-wise)")
+    ap.add_argument("--forward", action="store_true", help="also compare ude_forward trajectories with the oracle's")
     ap.add_argument("--prebuild", action="store_true", help="no GPU: only compile the on-demand kernel plugins the same random cases may need")
     a = ap.parse_args()
     import ude_b200 as ude
@@ -45,22 +47,30 @@ def main():
         if a.prebuild:
             if hidden >= 13:
                 prob, theta = cases.make_case(rhs, loss, solver, **kw)
-                ude.user_rhs.ensure_catalog_kernels(prob, 0)
+                ude.user_rhs.ensure_catalog_kernels(prob, 1 if a.dtype == "f32" else 0)
             continue
         try:
             prob, theta = cases.make_case(rhs, loss, solver, **kw)
             L_ref, g_ref = oracle.loss_grad(prob, theta)
-            with ude.Engine(prob) as eng:
+            f32 = a.dtype == "f32"
+            tol = 1e-4 if f32 else 1e-10
+            fwd_err = 0.0
+            with ude.Engine(prob, dtype=1 if f32 else 0) as eng:
                 kn = eng.kernel_name()
                 L, g = eng.loss_grad(theta)
                 ok_steps = eng.steps_per_eval() == oracle.count_steps(prob)
+                if a.forward and loss != "deriv_match":
+                    out = eng.forward(theta)
+                    ref = oracle.forward(prob, theta)
+                    msk = np.isfinite(ref)
+                    fwd_err = float(np.max(np.abs(out[msk] - ref[msk])) / max(float(np.max(np.abs(ref[msk]))), 1e-300)) if msk.any() else 0.0
             kernels[kn] = kernels.get(kn, 0) + 1
             el = float(np.max(np.abs(L - L_ref) / np.abs(L_ref)))
-            worst = cases.grad_mismatch(prob, g, g_ref, rtol=1e-10)
+            worst = (cases.relerr(g, g_ref) / tol, -1, "all") if f32 else cases.grad_mismatch(prob, g, g_ref, rtol=tol)
             zeros_ok = bool(np.all(g[g_ref == 0.0] == 0.0))
-            if not (np.all(np.isfinite(g)) and el < 1e-10 and worst[0] <= 1.0 and zeros_ok and ok_steps):
+            if not (np.all(np.isfinite(g)) and el < tol and worst[0] <= 1.0 and zeros_ok and ok_steps and fwd_err < tol):
                 fails += 1
-                print("FAIL", it, rhs, loss, solver, kw, kn, "loss err", el, "grad", worst, "zeros", zeros_ok, "steps", ok_steps, flush=True)
+                print("FAIL", it, rhs, loss, solver, kw, kn, "loss err", el, "grad", worst, "zeros", zeros_ok, "steps", ok_steps, "forward", fwd_err, flush=True)
         except ude.UdeError as ex:
             if ex.code == -2:                      # no compiled kernel for this shape: a documented refusal, not a failure
                 kernels["unsupported"] = kernels.get("unsupported", 0) + 1
