@@ -20,6 +20,8 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--dtype", default="f64", help="f64 (bar 1e-10, per gradient leaf) or f32 (the optional FP32 mode: bar 1e-4, norm-wise)")
     ap.add_argument("--forward", action="store_true", help="also compare ude_forward trajectories with the oracle's")
+    ap.add_argument("--sparse", action="store_true", help="also run the zero-copy host path (UDE_OPT_SPARSE_UHAT_IO, page-locked buffers): the bench's e2e path")
+    ap.add_argument("--adam", action="store_true", help="also compare 5 device-resident Adam iterations (ude_adam) with a host loop on the oracle's gradients")
     ap.add_argument("--prebuild", action="store_true", help="no GPU: only compile the on-demand kernel plugins the same random cases may need")
     a = ap.parse_args()
     import ude_b200 as ude
@@ -64,13 +66,38 @@ def main():
                     ref = oracle.forward(prob, theta)
                     msk = np.isfinite(ref)
                     fwd_err = float(np.max(np.abs(out[msk] - ref[msk])) / max(float(np.max(np.abs(ref[msk]))), 1e-300)) if msk.any() else 0.0
+                extra_ok = True
+                if a.sparse and n_models == 1 and not f32:
+                    import torch
+                    eng.set_option(ude.OPT_SPARSE_UHAT_IO, 1)
+                    h_theta = torch.from_numpy(theta.copy()).pin_memory()
+                    h_grad = torch.zeros(prob.n_theta, dtype=torch.float64).pin_memory()
+                    h_loss = torch.zeros(1, dtype=torch.float64).pin_memory()
+                    for rep in range(2):
+                        eng.loss_grad_ptr(h_theta.data_ptr(), prob.n_theta, h_loss.data_ptr(), h_grad.data_ptr())
+                        gs = h_grad.numpy()
+                        extra_ok = extra_ok and abs(h_loss[0].item() - L_ref[0]) < tol * abs(L_ref[0]) \
+                            and cases.grad_mismatch(prob, gs, g_ref, rtol=tol)[0] <= 1.0 and bool(np.all(gs[g_ref == 0.0] == 0.0))
+                    eng.set_option(ude.OPT_SPARSE_UHAT_IO, 0)
+                if a.adam and not f32:
+                    th_d, tr_d = eng.adam(theta, 1e-3, 5)
+                    th_h = theta.copy(); mm = np.zeros_like(th_h); vv = np.zeros_like(th_h); tr_h = []
+                    for k in range(1, 6):
+                        Lh, gh = oracle.loss_grad(prob, th_h)
+                        tr_h.append(Lh.copy())
+                        mm = 0.9 * mm + 0.1 * gh; vv = 0.999 * vv + 0.001 * gh * gh
+                        th_h -= 1e-3 * (mm / (1 - 0.9 ** k)) / (np.sqrt(vv / (1 - 0.999 ** k)) + 1e-8)
+                    # Adam divides by sqrt(v): entries whose gradient is ~0 amplify round-off, so compare the traces tightly
+                    # and the iterates at the step size's scale
+                    extra_ok = extra_ok and float(np.max(np.abs(tr_d - np.array(tr_h)) / np.abs(np.array(tr_h)))) < 1e-9 \
+                        and float(np.max(np.abs(th_d - th_h))) < 1e-3 * 5 * 1e-4
             kernels[kn] = kernels.get(kn, 0) + 1
             el = float(np.max(np.abs(L - L_ref) / np.abs(L_ref)))
             worst = (cases.relerr(g, g_ref) / tol, -1, "all") if f32 else cases.grad_mismatch(prob, g, g_ref, rtol=tol)
             zeros_ok = bool(np.all(g[g_ref == 0.0] == 0.0))
-            if not (np.all(np.isfinite(g)) and el < tol and worst[0] <= 1.0 and zeros_ok and ok_steps and fwd_err < tol):
+            if not (np.all(np.isfinite(g)) and el < tol and worst[0] <= 1.0 and zeros_ok and ok_steps and fwd_err < tol and extra_ok):
                 fails += 1
-                print("FAIL", it, rhs, loss, solver, kw, kn, "loss err", el, "grad", worst, "zeros", zeros_ok, "steps", ok_steps, "forward", fwd_err, flush=True)
+                print("FAIL", it, rhs, loss, solver, kw, kn, "loss err", el, "grad", worst, "zeros", zeros_ok, "steps", ok_steps, "forward", fwd_err, "sparse/adam", extra_ok, flush=True)
         except ude.UdeError as ex:
             if ex.code == -2:                      # no compiled kernel for this shape: a documented refusal, not a failure
                 kernels["unsupported"] = kernels.get("unsupported", 0) + 1
