@@ -23,7 +23,7 @@ def main():
     from oracle import ukf_oracle_np as ukf
     rng = np.random.default_rng(a.seed)
     names = [n for n, v in cases.RHS_SPECS.items() if not v[6] and v[1] <= 4]
-    fails = 0
+    fails, refused = 0, 0
     for it in range(a.n):
         rhs = names[int(rng.integers(len(names)))]
         d = cases.RHS_SPECS[rhs][1]
@@ -64,11 +64,17 @@ def main():
             if not (worst < tol):
                 fails += 1
                 print("FAIL", it, rhs, solver, kw, "causal", causal, "alpha", alpha, "worst", worst, flush=True)
+        except ude.UdeError as ex:
+            if ex.code == -2:                      # UDE_JIT=0 and no shipped kernel for the shape: a documented refusal
+                refused += 1
+                continue
+            fails += 1
+            print("ERROR", it, rhs, solver, kw, repr(ex), flush=True)
         except Exception:
             fails += 1
             print("EXC", it, rhs, solver, kw, flush=True)
             traceback.print_exc()
-    print("ukf cases", a.n, "failures", fails)
+    print("ukf cases", a.n, "refused", refused, "failures", fails)
     sys.exit(1 if fails else 0)
 
 
