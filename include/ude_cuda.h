@@ -68,7 +68,7 @@ enum {
    * this library: the host side writes the parametric part as expressions, generates the input / combine / combine_vjp trait
    * of csrc/ude_kernel_body.inc from them, compiles it with nvcc into a PLUGIN shared library linked against libude_cuda.so
    * and dlopens it (RTLD_GLOBAL) -- the plugin's static initialiser registers its kernels under this rhs_kind, after which
-   * every entry point below accepts it (universaldiffeq.jl_b200/user_rhs.py).  FP64 only. */
+   * every entry point below accepts it (universaldiffeq.jl_b200/user_rhs.py). */
   UDE_RHS_USER0 = 1000
 };
 

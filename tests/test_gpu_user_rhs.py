@@ -116,3 +116,22 @@ def test_one_hot_series_network_on_the_gpu(ude, m, hidden):
     assert worst[0] <= 1.0, worst
     ude.train_(model, "conditional likelihood", verbose=False, optim_options=dict(maxiter=40, step_size=0.02))
     assert np.all(np.isfinite(model.parameters))
+
+
+def test_user_rhs_fp32_mode(ude):
+    """the optional FP32 mode on generated kernels (the same trait text compiled in the float copy of the kernel family): bar 1e-4"""
+    rhs = urc.lv_twin(ude)
+    for loss, solver in (("cond_lik", 0), ("multi_shoot", 0)):
+        prob_u, theta = urc.make(ude, "user_lv", rhs, (1.0, 0.5, 0.5), loss, solver, hidden=10, lengths=(9, 1, 14, 2, 6))
+        prob_c, _ = cases.make_case("lv_ude", loss, solver, hidden=10, lengths=(9, 1, 14, 2, 6))
+        L_ref, g_ref = oracle.loss_grad(prob_c, theta)
+        with ude.Engine(prob_u, dtype=1) as eng:
+            assert eng.kernel_name().startswith("f32_user")
+            L, g = eng.loss_grad(theta)
+        assert abs(L[0] - L_ref[0]) < 1e-4 * abs(L_ref[0]) and cases.relerr(g, g_ref) < 1e-4
+    ep = urc.epidemic(ude)
+    prob, theta = urc.make(ude, "user_epi", ep, (0.9, 0.4, 2.0), "multi_shoot", 0, hidden=6, lengths=(5, 3, 1, 4), substeps=2)
+    L_ref, g_ref = urc.numpy_loss_grad(prob, theta)
+    with ude.Engine(prob, dtype=1) as eng:
+        L, g = eng.loss_grad(theta)
+    assert abs(L[0] - L_ref[0]) < 1e-4 * abs(L_ref[0]) and cases.relerr(g, g_ref) < 1e-4

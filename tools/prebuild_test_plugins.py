@@ -23,6 +23,7 @@ def main():
     lv, ep, gr = urc.lv_twin(ude), urc.epidemic(ude), urc.growth_twin(ude)
     for r, h, s in [(lv, 10, 0), (lv, 10, 1), (lv, 6, 0), (ep, 6, 0), (ep, 6, 1), (ep, 12, 0), (ep, 20, 1), (gr, 4, 0), (gr, 4, 1)]:
         U.ensure_kernels(r, h, s)                                            # tests/test_gpu_user_rhs.py, bench.py user_rhs_lv
+    U.ensure_kernels(lv, 10, 0, dtype=1); U.ensure_kernels(ep, 6, 0, dtype=1)     # test_user_rhs_fp32_mode
     for m, h in ((3, 6), (10, 10)):
         model, _, _ = urc.one_hot_model(ude, m=m, n_pts=6, hidden=h)
         U.ensure_kernels(model.rhs, h, 0)

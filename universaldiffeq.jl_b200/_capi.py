@@ -216,9 +216,7 @@ class Engine:
             rhs = p.user_rhs if getattr(p, "user_rhs", None) is not None else user_rhs.lookup(p.rhs_kind)
             if rhs is None:
                 raise UdeError(-2, f"rhs_kind {p.rhs_kind} is not a catalog entry and no expression_rhs with that id exists in this process")
-            if dtype != 0:
-                raise UdeError(-2, "user-written right-hand sides are compiled for FP64 only")
-            user_rhs.ensure_kernels(rhs, p.nn_hidden, p.solver)
+            user_rhs.ensure_kernels(rhs, p.nn_hidden, p.solver, dtype=dtype)
         desc = make_desc(p, device, lanes_per_segment, hidden_per_lane, weights_in_smem, dtype)
         rc = self.lib.ude_create(C.byref(desc), C.byref(self.handle))
         if rc != UDE_OK:

@@ -15,7 +15,7 @@ kernel family is templated on (csrc/ude_kernel_body.inc: the same interface the 
 that ONE trait into the fused RK + loss + discrete-adjoint kernels with nvcc for sm_100a, and loads the result as a plugin of
 libude_cuda.so: the plugin's static initialiser adds its kernels to the library's registry under a fresh `rhs_kind`, and from
 there on `ude_create` / `ude_loss_grad` / `ude_adam` / `ude_forward` / the UKF treat it like any catalog entry.  The network
-sees every state (the kernels return the input gradient straight into the state adjoint); FP64 only.
+sees every state (the kernels return the input gradient straight into the state adjoint); FP64, or the optional FP32 mode.
 
 The plugin cache (`csrc/user_rhs/`) is keyed by the generated source, the kernel geometry and the library headers.
 """
@@ -244,11 +244,13 @@ def _lib_stamp() -> str:
     return h.hexdigest()[:10]
 
 
-def ensure_kernels(rhs: UserRhs, hidden: int, solver: int, verbose: bool = False) -> str:
+def ensure_kernels(rhs: UserRhs, hidden: int, solver: int, verbose: bool = False, dtype: int = 0) -> str:
     """Compile (once) and load the plugin that holds this trait's kernels for one hidden width and solver: the three loss
-    families, each with and without the reverse sweep.  Returns the plugin path."""
+    families, each with and without the reverse sweep.  dtype = 1: the optional FP32 mode (the same trait text compiled in the
+    float copy of the kernel family).  Returns the plugin path."""
     G, HPL, minb = geometry(hidden)
-    tag = hashlib.sha1((rhs.cuda_trait + f"|{G}|{HPL}|{minb}|{solver}|" + _lib_stamp()).encode()).hexdigest()[:16]
+    ns, tns = ("F64", "f64") if dtype == 0 else ("F32", "f32")
+    tag = hashlib.sha1((rhs.cuda_trait + f"|{ns}|{G}|{HPL}|{minb}|{solver}|" + _lib_stamp()).encode()).hexdigest()[:16]
     so = os.path.join(_CACHE, f"ude_user_{tag}.so")
     if so in _loaded:
         return so
@@ -256,15 +258,16 @@ def ensure_kernels(rhs: UserRhs, hidden: int, solver: int, verbose: bool = False
         os.makedirs(_CACHE, exist_ok=True)
         src = os.path.join(_CACHE, f"ude_user_{tag}.cu")
         tmp = f".{os.getpid()}.tmp"                   # several ranks may build the same plugin at once: private files, atomic renames
-        label = f"user{rhs.kind}_g{G}h{HPL}"
-        regs = "\n".join(f'  register_one<F64, RhsUser{rhs.kind}, {G}, {HPL}, {minb}, {solver}, {lk}, false>("{label}", 0);'
+        label = ("f32_" if dtype else "") + f"user{rhs.kind}_g{G}h{HPL}"
+        regs = "\n".join(f'  register_one<{ns}, RhsUser{rhs.kind}, {G}, {HPL}, {minb}, {solver}, {lk}, false>("{label}", 0);'
                          for lk in (("LK_STATE",) if solver == P.EULER else ("LK_STATE", "LK_TRAJ", "LK_DM")))
         with open(src + tmp, "w") as fh:
             fh.write("// generated by universaldiffeq.jl_b200/user_rhs.py from the expressions of a user right-hand side -- do not edit\n"
-                     '#include "ude_inst.cuh"\nnamespace ude {\nnamespace f64 {\n' + rhs.cuda_trait + "}  // namespace f64\n}  // namespace ude\n"
-                     f"namespace {{\nusing namespace ude;\nusing ude::f64::RhsUser{rhs.kind};\nRegisterKernels reg([] {{\n" + regs + "\n});\n}  // namespace\n")
+                     f'#include "ude_inst.cuh"\nnamespace ude {{\nnamespace {tns} {{\n' + rhs.cuda_trait + f"}}  // namespace {tns}\n}}  // namespace ude\n"
+                     f"namespace {{\nusing namespace ude;\nusing ude::{tns}::RhsUser{rhs.kind};\nRegisterKernels reg([] {{\n" + regs + "\n});\n}  // namespace\n")
         os.replace(src + tmp, src)
-        _build.build()
+        if not os.path.exists(_build.SO):           # never rebuild here: the library may already be loaded in this process
+            raise RuntimeError("libude_cuda.so is not built (python -c 'import __graft_entry__ as g; g.build()')")
         cmd = [_build.NVCC, *_build.FLAGS, "-I", _build.CSRC, "-shared", "-o", so + tmp, src, "-L", _build.CSRC, "-lude_cuda", "-lcudart",
                "-Xlinker", "-rpath", "-Xlinker", _build.CSRC]
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -324,7 +327,8 @@ def ensure_catalog_kernels(p, dtype: int = 0, verbose: bool = False) -> str:
             fh.write("// generated by universaldiffeq.jl_b200/user_rhs.py: a catalog right-hand side at a shape without a pre-compiled instance\n"
                      '#include "ude_inst.cuh"\nnamespace {\nusing namespace ude;\nRegisterKernels reg([] {\n' + regs + "\n});\n}  // namespace\n")
         os.replace(src + tmp, src)
-        _build.build()
+        if not os.path.exists(_build.SO):           # never rebuild here: the library may already be loaded in this process
+            raise RuntimeError("libude_cuda.so is not built (python -c 'import __graft_entry__ as g; g.build()')")
         cmd = [_build.NVCC, *_build.FLAGS, "-I", _build.CSRC, "-shared", "-o", so + tmp, src, "-L", _build.CSRC, "-lude_cuda", "-lcudart",
                "-Xlinker", "-rpath", "-Xlinker", _build.CSRC]
         r = subprocess.run(cmd, capture_output=True, text=True)
