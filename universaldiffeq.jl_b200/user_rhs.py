@@ -25,6 +25,7 @@ import ctypes
 import hashlib
 import os
 import subprocess
+import threading
 from dataclasses import dataclass, field
 from typing import Callable, Optional, Sequence
 
@@ -37,6 +38,7 @@ USER_KIND0 = 1000                      # rhs_kind values from here on are genera
 _CACHE = os.path.join(_build.CSRC, "user_rhs")
 _loaded: dict = {}                     # plugin path -> ctypes handle (kept alive: the registry points into it)
 _by_kind: dict = {}                    # rhs_kind -> UserRhs
+_lock = threading.RLock()              # one plugin build / load at a time per process (training.adam_multi_gpu: a thread per GPU)
 
 
 def _sympy():
@@ -244,7 +246,7 @@ def _lib_stamp() -> str:
     return h.hexdigest()[:10]
 
 
-def ensure_kernels(rhs: UserRhs, hidden: int, solver: int, verbose: bool = False, dtype: int = 0) -> str:
+def _ensure_kernels(rhs: UserRhs, hidden: int, solver: int, verbose: bool = False, dtype: int = 0) -> str:
     """Compile (once) and load the plugin that holds this trait's kernels for one hidden width and solver: the three loss
     families, each with and without the reverse sweep.  dtype = 1: the optional FP32 mode (the same trait text compiled in the
     float copy of the kernel family).  Returns the plugin path."""
@@ -301,7 +303,7 @@ def _catalog_trait(p) -> Optional[str]:
     return None
 
 
-def ensure_catalog_kernels(p, dtype: int = 0, verbose: bool = False) -> str:
+def _ensure_catalog_kernels(p, dtype: int = 0, verbose: bool = False) -> str:
     """The library ships the catalog right-hand sides at the shapes of the BASELINE configurations, the reference's tests and
     docs (hidden width <= 12 for the parametric UDEs, the NODE shapes of csrc/ude_inst_*.cu).  Any other hidden width up to 128,
     with one or many models per handle, is compiled here on first use -- the same hand-written trait, instantiated for the
@@ -339,3 +341,17 @@ def ensure_catalog_kernels(p, dtype: int = 0, verbose: bool = False) -> str:
         os.replace(so + tmp, so)
     _loaded[so] = ctypes.CDLL(so, mode=ctypes.RTLD_GLOBAL)
     return so
+
+
+def ensure_kernels(rhs: UserRhs, hidden: int, solver: int, verbose: bool = False, dtype: int = 0) -> str:
+    with _lock:
+        return _ensure_kernels(rhs, hidden, solver, verbose, dtype)
+
+
+def ensure_catalog_kernels(p, dtype: int = 0, verbose: bool = False) -> str:
+    with _lock:
+        return _ensure_catalog_kernels(p, dtype, verbose)
+
+
+ensure_kernels.__doc__ = _ensure_kernels.__doc__
+ensure_catalog_kernels.__doc__ = _ensure_catalog_kernels.__doc__
