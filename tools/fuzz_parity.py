@@ -54,6 +54,9 @@ def main():
         try:
             prob, theta = cases.make_case(rhs, loss, solver, **kw)
             L_ref, g_ref = oracle.loss_grad(prob, theta)
+            if not (np.all(np.isfinite(L_ref)) and np.all(np.isfinite(g_ref))):
+                kernels["diverged in the oracle too (open-loop trajectory blows up): skipped"] = kernels.get("diverged in the oracle too (open-loop trajectory blows up): skipped", 0) + 1
+                continue
             f32 = a.dtype == "f32"
             tol = 1e-4 if f32 else 1e-10
             fwd_err = 0.0
