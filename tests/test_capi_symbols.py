@@ -58,3 +58,33 @@ def test_product_path_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "ude_oracle" not in txt and "from oracle" not in txt and "import oracle" not in txt, f
+
+
+def test_julia_desc_mirror_matches_the_header():
+    """julia/UDECuda.jl cannot be executed here (no Julia): at least its `Desc` struct must list the fields of `ude_desc` in the
+    header's order with matching widths, and every function it ccalls must be an exported symbol."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "ude_cuda.h")).read()
+    body = hdr[hdr.index("typedef struct ude_desc {"):hdr.index("} ude_desc;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    c_fields = []
+    for ty, names in re.findall(r"\b(int32_t|int64_t|double)\s+([^;]+);", body):
+        for nm in names.split(","):
+            nm = nm.strip()
+            m = re.match(r"(\w+)\[(.+)\]", nm)
+            n = 1
+            if m:
+                nm, dim = m.group(1), m.group(2)
+                n = eval(dim.replace("UDE_MAX_SCALARS", "8").replace("UDE_MAX_D", "8"))
+            c_fields.append((nm, {"int32_t": "Int32", "int64_t": "Int64", "double": "Float64"}[ty], n))
+    jl = open(os.path.join(root, "julia", "UDECuda.jl")).read()
+    sb = jl[jl.index("struct Desc"):]
+    sb = sb[:sb.index("\nend")]
+    j_fields = []
+    for nm, ty in re.findall(r"(\w+)::((?:NTuple\{\d+,\s*\w+\})|\w+)", sb):
+        m = re.match(r"NTuple\{(\d+),\s*(\w+)\}", ty)
+        j_fields.append((nm, m.group(2), int(m.group(1))) if m else (nm, ty, 1))
+    assert j_fields == c_fields, (j_fields, c_fields)
+    called = set(re.findall(r"ccall\(\(:(\w+),", jl))
+    assert called and called <= set(_declared()), called - set(_declared())
