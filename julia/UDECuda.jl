@@ -161,6 +161,44 @@ function cuda_objective(UDE, loss_function, loss_options, regularization_weight;
     return f, g!, h
 end
 
+# ---- unscented-Kalman-filter marginal likelihood (src/UnscentedKalmanFilter.jl:76-87, :59-72; LFC.jl:103-127, :427-476) --------------
+# mirror of `ude_ukf_opts` (include/ude_cuda.h)
+struct UkfOpts
+    alpha::Float64; beta::Float64; kappa::Float64; reg::Float64
+    Peta::NTuple{64,Float64}
+end
+UkfOpts(Pη::AbstractMatrix; α = 1e-3, β = 2.0, κ = 0.0, reg = 0.0) = UkfOpts(α, β, κ, reg, pad64(Matrix{Float64}(Pη)))
+
+# F: d×d factor of the process noise (Pν = F F'), or d×d×n_models on a many-model handle (folds × ensemble members);
+# returns (loss per model, ∇θ, ∇F).  `train!(…; loss_function = "marginal likelihood")` optimises (process_model, F) with these.
+function ukf_loss_grad(h, opts::UkfOpts, θ::Vector{Float64}, F::Array{Float64}, n_models = 1)
+    L = zeros(n_models); Gθ = zeros(length(θ)); GF = zeros(size(F))
+    check(h, ccall((:ude_ukf_loss_grad, lib), Cint,
+                   (Ptr{Cvoid}, Ref{UkfOpts}, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                   h.ptr, Ref(opts), θ, length(θ), F, L, Gθ, GF))
+    L, Gθ, GF
+end
+# ukf_smoothing: filtered states d×N and covariances d×d×N
+function ukf_filter(h, opts::UkfOpts, θ::Vector{Float64}, F::Array{Float64}, d, N)
+    xs = zeros(d, N); Ps = zeros(d, d, N)
+    check(h, ccall((:ude_ukf_filter, lib), Cint,
+                   (Ptr{Cvoid}, Ref{UkfOpts}, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                   h.ptr, Ref(opts), θ, length(θ), F, xs, Ps))
+    xs, Ps
+end
+
+# ---- derivative-matching pre-step (LFC.jl:161-171, :510-522): RegularizationSmooth(u, t, d; alg = :gcv_svd) for all rows at once --
+# U: rows×n (row-major on the C side: pass permutedims of an n×rows Julia matrix), Vt (r×n), s (r), M (n×n) from the time grid
+function reg_smooth(Ut::Matrix{Float64}, Vt_t::Matrix{Float64}, s::Vector{Float64}, Mt::Matrix{Float64}; device = 0, λlo = 1e-4, λhi = 1e3)
+    n, rows = size(Ut); r = length(s)
+    u = zeros(n, rows); du = zeros(n, rows); λ = zeros(rows)
+    rc = ccall((:ude_reg_smooth, lib), Cint,
+               (Int32, Int32, Int32, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Float64, Float64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+               device, n, r, rows, Vt_t, s, Mt, Ut, λlo, λhi, u, du, λ)
+    rc == 0 || error("ude_reg_smooth failed with status $rc")
+    u, du, λ
+end
+
 end # module
 
 # ---- the hook in train! (src/Optimizers.jl:473-478), verbatim --------------------------------------------------------------
