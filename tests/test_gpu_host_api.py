@@ -97,6 +97,37 @@ def test_forecast_and_predictions_match_oracle(ude):
         assert np.max(np.abs(fc[j, 1:] - x)) < 1e-9 and fc[j, 0] == t1
 
 
+def test_forecast_with_a_per_series_parameter(ude):
+    """MultiCustomDerivatives with `p.r[i]` (docs/src/MultipleTimeSeries.md:27-61): forecast() and the leave-future-out forecasts
+    chain one-interval mini-series; each of them must carry the growth rate of the series being forecast."""
+    from oracle import ude_oracle_np as onp
+    rng = np.random.default_rng(3)
+    ts = np.linspace(0.0, 3.0, 12)
+    dfm = pd.concat([pd.DataFrame({"time": ts, "series": s, "x": 0.3 + 0.2 * s + 0.1 * np.sin(ts + s) + 0.01 * rng.normal(size=12)}) for s in (1, 2, 3)],
+                    ignore_index=True)
+    _, nn = ude.SimpleNeuralNetwork(1, 1, hidden=5, seed=2)
+    m = ude.MultiCustomDerivatives(dfm, ude.series_growth_rhs(1), {"NN": nn, "r": np.array([0.3, -0.2, 0.5])})
+    m.parameters[: m.data.shape[1]] = m.data.reshape(-1, order="F")
+    prob = ude.default_loss(m)
+    for j in range(3):
+        s0, ln = int(m.starts[j]), int(m.lengths[j])
+        uh = m.uhat[:, s0:s0 + ln]
+        t_new = m.times[s0 + ln - 1] + np.array([0.2, 0.5, 0.9])
+        fc = ude.forecast(m, uh[:, -1], m.times[s0 + ln - 1], t_new, series=j)
+        x = uh[:, -1].copy(); t0 = m.times[s0 + ln - 1]
+        umax, umin, umean = uh.max(axis=1), uh.min(axis=1), uh.mean(axis=1)
+        l, rho = m.extra.get("l", 0.25), m.extra.get("extrap_rho", 0.1)
+        for k, t1 in enumerate(t_new):
+            p1 = np.real(onp.flow(prob, m.process_model, j, j, x, t0, t1))
+            du = p1 - x
+            w = np.exp(-0.5 / l ** 2 * ((x - umax) / (umax - umin)) ** 2); du = np.where(x > umax, w * du - rho * (1 - w) * (x - umean), du)
+            w = np.exp(-0.5 / l ** 2 * ((x - umin) / (umax - umin)) ** 2); du = np.where(x < umin, w * du - (1 - w) * rho * (x - umean), du)
+            x = x + du; t0 = t1
+            assert np.max(np.abs(fc[k, 1:] - x)) < 1e-9, (j, k)
+    models, tr, te, fc, trace = ude.leave_future_out_batched(m, k=2, skip=1, loss_function="conditional likelihood", optim_options=dict(maxiter=3))
+    assert len(fc) == 2 and np.all(np.isfinite(fc[0][["x"]].to_numpy()))
+
+
 def test_multinode_leave_future_out_and_kfold(ude):
     df = _lv_frame(ude, n=14)
     dfm = pd.concat([df.assign(series="a"), df.iloc[:12].assign(series="b")])

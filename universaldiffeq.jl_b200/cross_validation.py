@@ -212,7 +212,7 @@ def predict(model: UDE, test_data: pd.DataFrame, device=0) -> pd.DataFrame:
     predictions between consecutive rows of `test_data`, started from the observed values; for multi-series models each
     series of the test frame is predicted with the covariates of the TRAINED series that carries the same label.  All
     intervals of a series are one batch of segments on the GPU.  Returns [series,] time, variables at the interval ends."""
-    from .training import _interval_problem
+    from .training import _interval_problem, _interval_pm
     tcol, scol = model.time_column_name, model.series_column_name
     frames = []
     groups = [(None, test_data)] if not model.multi else [(lab, test_data[test_data[scol] == lab]) for lab in sorted(pd.unique(test_data[scol]))]
@@ -227,7 +227,7 @@ def predict(model: UDE, test_data: pd.DataFrame, device=0) -> pd.DataFrame:
         cols = np.zeros((model.d, 2 * (tt.shape[0] - 1)), order="F")
         cols[:, 0::2] = Y[:, :-1]
         with Engine(pr, device=device) as eng:
-            pred = eng.forward(np.concatenate([cols.reshape(-1, order="F"), model.process_model]))[:, 1::2]
+            pred = eng.forward(np.concatenate([cols.reshape(-1, order="F"), _interval_pm(model, pr, j)]))[:, 1::2]
         out = pd.DataFrame(pred.T, columns=list(model.varnames))
         out.insert(0, tcol, tt[1:])
         if lab is not None:

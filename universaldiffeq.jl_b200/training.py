@@ -211,9 +211,18 @@ def _interval_problem(model: UDE, t_from, t_to, series=0) -> P.Problem:
         m2.cov = (nc, np.concatenate([[0], np.tile(np.diff(o), n).cumsum()]).astype(np.int64), np.tile(seg_t, n), np.tile(seg_x, n))
     pr = m2.base_problem()
     pr.loss_kind = P.LOSS_STATE_SPACE
-    if pr.has_series_param:
-        raise NotImplementedError("per-series parameters are not supported on mini-series problems")
     return pr
+
+
+def _interval_pm(model: UDE, pr: P.Problem, series=0) -> np.ndarray:
+    """process_model for a mini-series problem of `_interval_problem`: the model's own, except that a per-series parameter
+    vector (MultiCustomDerivatives' p.r[i]) becomes one entry per MINI-series, all equal to the entry of `series`."""
+    pm = np.asarray(model.process_model, dtype=np.float64)
+    if not pr.has_series_param:
+        return pm
+    n_own = 1 if not model.multi else len(model.starts)
+    off = pm.shape[0] - n_own                    # the per-series vector is the tail of process_model (problem.default_layout)
+    return np.concatenate([pm[:off], np.full(pr.n_series, pm[off + (series if model.multi else 0)])])
 
 
 class NeuralGradientMatching:
@@ -739,7 +748,7 @@ def forecast(model: UDE, u0, t0, times, series=0, device=0):
     tt = np.concatenate([[t0], times])
     pr = _interval_problem(model, tt[:-1], tt[1:], series)
     pr.finalize()
-    theta = np.concatenate([np.zeros(d * 2 * n), model.process_model])
+    theta = np.concatenate([np.zeros(d * 2 * n), _interval_pm(model, pr, series)])
     out = np.zeros((n, d + 1))
     with Engine(pr, device=device) as eng:     # the chain (predict, damp, next start) never leaves the device
         out[:, 1:] = eng.forecast_chain(theta, np.asarray(u0, dtype=np.float64), umax, umin, umean, l, rho).T
