@@ -135,3 +135,41 @@ def test_user_rhs_fp32_mode(ude):
     with ude.Engine(prob, dtype=1) as eng:
         L, g = eng.loss_grad(theta)
     assert abs(L[0] - L_ref[0]) < 1e-4 * abs(L_ref[0]) and cases.relerr(g, g_ref) < 1e-4
+
+
+def test_every_training_route_accepts_a_generated_right_hand_side(ude, tmp_path):
+    """train!'s loss functions and optimisers, the CV drivers and parameter I/O with an expression right-hand side: each route
+    must run on the generated kernels and agree with the same model on the hand-written catalog kernel"""
+    import pandas as pd
+    df = ude.LotkaVolterra(plot=False, datasize=18)
+    rhs = urc.lv_twin(ude)
+    _, nn = ude.SimpleNeuralNetwork(2, 1, hidden=6, seed=4)
+    init = {"NN": nn, "r": 0.5, "m": 0.4, "theta": 0.6}
+    routes = [("spline gradient matching", "ADAM", dict(maxiter=15)), ("neural gradient matching", "ADAM", dict(maxiter=10)),
+              ("derivative matching", "BFGS", dict(maxiter=5)), ("shooting", "ADAM", dict(maxiter=8, step_size=0.01)),
+              ("multiple shooting", "ADAM", dict(maxiter=8, step_size=0.01)), ("conditional likelihood", "BFGS", dict(maxiter=4)),
+              ("marginal likelihood", "ADAM", dict(maxiter=5))]
+    for loss, opt, oo in routes:
+        a = ude.CustomDerivatives(df, rhs, init)
+        b = ude.CustomDerivatives(df, ude.LV_UDE, init)
+        lo = dict(alpha=1.0) if loss == "marginal likelihood" else None
+        ude.train_(a, loss, optimizer=opt, verbose=False, loss_options=lo, optim_options=oo)
+        ude.train_(b, loss, optimizer=opt, verbose=False, loss_options=lo, optim_options=oo)
+        assert np.all(np.isfinite(a.parameters)), loss
+        assert cases.relerr(a.parameters, b.parameters) < 1e-7, (loss, cases.relerr(a.parameters, b.parameters))
+    f = tmp_path / "pm.json"
+    ude.save_model_parameters(a, str(f))
+    c = ude.CustomDerivatives(df, rhs, init)
+    ude.load_model_parameters_(c, str(f))
+    assert np.array_equal(c.process_model, a.process_model)
+    tr, te, fc = ude.leave_future_out(a, lambda mi: ude.train_(mi, "conditional likelihood", verbose=False, optim_options=dict(maxiter=3)), 2)
+    assert len(fc) == 2 and np.all(np.isfinite(fc[0][["x1", "x2"]].to_numpy()))
+    # multi-series model with a per-series parameter: leave-site-out refits on the other sites
+    rng = np.random.default_rng(2)
+    ts = np.linspace(0.0, 3.0, 10)
+    dfm = pd.concat([pd.DataFrame({"time": ts, "series": s, "x": 0.4 + 0.1 * s + 0.05 * np.sin(ts) + 0.01 * rng.normal(size=10)}) for s in (1, 2, 3)],
+                    ignore_index=True)
+    _, nn1 = ude.SimpleNeuralNetwork(1, 1, hidden=4, seed=1)
+    mm = ude.MultiCustomDerivatives(dfm, urc.growth_twin(ude), {"NN": nn1, "r": np.array([0.1, 0.2, 0.3])})
+    score = ude.leave_site_out(mm, lambda mi: ude.train_(mi, "conditional likelihood", verbose=False, optim_options=dict(maxiter=3)))
+    assert np.isfinite(score)

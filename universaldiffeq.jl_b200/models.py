@@ -265,9 +265,11 @@ def _pack_pm(prob: P.Problem, rhs: Rhs, initial_parameters: dict, n_series: int)
             pm[o] = float(initial_parameters[nm])
     if rhs.series_param is not None:
         v = np.asarray(initial_parameters[rhs.series_param], dtype=np.float64)
-        if v.shape[0] != n_series:
+        if v.shape[0] < n_series:
             raise ValueError("per-series parameter vector must have one entry per series")
-        pm[prob.off_series_param:prob.off_series_param + n_series] = v
+        # a longer vector is indexed by the position of the series among those present, as `p.r[round(Int, i)]` is in the
+        # reference when a CV driver rebuilds the model on fewer series (src/CrossValidation.jl:463-474)
+        pm[prob.off_series_param:prob.off_series_param + n_series] = v[:n_series]
     return pm
 
 
