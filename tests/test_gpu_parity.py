@@ -248,6 +248,32 @@ def test_pipelined_host_path_whole_rounds(ude, monkeypatch):
     assert cases.relerr(res[0][1], res[1][1]) < 1e-12
 
 
+@pytest.mark.parametrize("loss", ["cond_lik", "multi_shoot", "shoot_theta", "deriv_match"])
+@pytest.mark.parametrize("chunks", [2, 3, 5])
+def test_pipelined_host_path_many_models(ude, loss, chunks, monkeypatch):
+    """Many-model handles (folds x members, src/CrossValidation.jl:17-45): ude_loss_grad moves theta up and gradient + losses
+    down in runs of whole models while the neighbouring run is on the SMs; every run is finalised behind its own kernel."""
+    monkeypatch.setenv("UDE_HOST_CHUNKS", str(chunks))
+    monkeypatch.setenv("UDE_HOST_CHUNK_ROUNDS", "0")
+    prob, theta = cases.make_case("node_time_d3", loss, 0, lengths=(9, 8, 7, 6, 5, 4, 11, 3, 2, 12, 6, 6, 3, 20), n_models=7, skip=(loss == "cond_lik"))
+    _check(prob, theta, ude)
+    prob, theta = cases.make_case("node_d4x1", loss, 1, hidden=32, lengths=(9, 3, 7, 6, 5, 4), n_models=3)
+    _check(prob, theta, ude)
+
+
+def test_pipelined_host_path_many_models_whole_rounds(ude, monkeypatch):
+    """default plan (chunk borders at model boundaries just below whole rounds of the persistent grid) on a C4-shaped handle
+    big enough to be split: per-model losses and gradients equal the single-chunk evaluation."""
+    prob, theta = ude.synthetic.config_c4(n_members=300, n_folds=10)
+    res = []
+    for k in ("4", "1"):
+        monkeypatch.setenv("UDE_HOST_CHUNKS", k)
+        with ude.Engine(prob) as eng:
+            res.append(eng.loss_grad(theta))
+    assert res[0][0].shape == res[1][0].shape and np.max(np.abs(res[0][0] - res[1][0]) / np.abs(res[1][0])) < 1e-12
+    assert cases.relerr(res[0][1], res[1][1]) < 1e-12
+
+
 @pytest.mark.parametrize("rhs,hidden", [("node_d1", 32), ("node_d2", 29), ("node_d3", 32), ("node_d1x1", 20), ("node_d2x1", 32),
                                         ("node_d3x1", 17), ("node_d4", 32), ("node_d4x1", 128), ("node_d4", 100), ("node_d2", 128)])
 def test_parity_dmma_shapes(ude, rhs, hidden, monkeypatch):

@@ -132,7 +132,9 @@ struct ude_handle {
   bool x_opened[UDE_MAX_PEERS] = {};    // mapped with cudaIpcOpenMemHandle (to be closed)
   bool x_attached = false;
   // host-buffer path: series chunks whose H2D / kernel / D2H overlap (built with the plan)
-  struct Chunk { int64_t task_begin, task_end, up_lo, up_hi, dn_lo, dn_hi; };
+  // single model: up_* / dn_* are uhat COLUMN ranges.  Many models: a chunk is a run of whole models [m_lo, m_hi) and
+  // up_* / dn_* are the (identical) ranges of theta / gradient ENTRIES of those models.
+  struct Chunk { int64_t task_begin, task_end, up_lo, up_hi, dn_lo, dn_hi, m_lo = 0, m_hi = 0; };
   std::vector<Chunk> chunks;
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
   std::vector<cudaEvent_t> ev_up, ev_done;
@@ -596,6 +598,53 @@ int build_plan(ude_handle* h) {
       h->chunks.push_back(c);
     }
   }
+  // ---- many-model handles (folds x ensemble members, every model its own theta block): the same three-stream overlap with
+  // chunks that are runs of WHOLE models -- theta / gradient of a run are one contiguous range, nothing is shared between
+  // chunks.  A warp takes a contiguous ceil(tasks / warps) run of the chunk's tasks, so a chunk boundary is the last model
+  // boundary at or below a whole number of rounds of the persistent grid (a chunk of r rounds + a few tasks would cost r + 1).
+  if (h->n_models > 1) {
+    const int64_t NT = h->n_tasks, M = h->n_models;
+    const int64_t Wg = std::max<int64_t>(1, (int64_t)h->grid_grad * (wpb / best_g->warps_per_task));
+    const char* env = getenv("UDE_HOST_CHUNKS");
+    const char* wenv = getenv("UDE_HOST_CHUNK_ROUNDS");
+    const bool whole_rounds = !(wenv && atoi(wenv) == 0);
+    const int64_t rounds_total = (NT + Wg - 1) / Wg;
+    int64_t K = env ? atoi(env) : std::min<int64_t>(6, rounds_total / 4);      // >= 4 rounds per chunk: small problems stay whole
+    K = std::max<int64_t>(1, std::min<int64_t>(K, M));
+    if (K > 1) {
+      std::vector<int64_t> mb(1, 0);                                            // model boundaries of the chunks
+      // the first upload and the last download are the only transfers nothing overlaps: one-round chunks at both ends
+      const char* eenv = getenv("UDE_HOST_CHUNK_EDGE");
+      const bool edge = whole_rounds && !(eenv && atoi(eenv) == 0) && rounds_total >= 3 * K && M >= K + 2;
+      const int64_t KK = edge ? K + 2 : K;
+      for (int64_t k = 1; k < KK; ++k) {
+        const int64_t t_prev = h->model_task0[(size_t)mb.back()];
+        int64_t left = KK - k + 1;                                              // chunks still to cut, this one included
+        int64_t rounds_left = (NT - t_prev + Wg - 1) / Wg;
+        int64_t want = 1;
+        if (!(edge && k == 1)) {
+          if (edge) { left -= 1; rounds_left -= 1; }                            // the one-round chunk at the far end
+          want = std::max<int64_t>(1, (rounds_left + left / 2) / left);
+        }
+        const int64_t target = whole_rounds ? t_prev + want * Wg : NT * k / K;
+        // last model boundary with model_task0[m] <= target
+        int64_t m = (int64_t)(std::upper_bound(h->model_task0.begin(), h->model_task0.end(), target) - h->model_task0.begin()) - 1;
+        m = std::min<int64_t>(std::max<int64_t>(m, mb.back() + 1), M - (KK - k));
+        if (m > mb.back() && m < M) mb.push_back(m);
+      }
+      mb.push_back(M);
+      auto th_end = [&](int64_t m) { return m < M ? h->theta_base[(size_t)m] : h->n_theta; };
+      if (mb.size() > 2) h->chunks.clear();                                     // replaces the single whole-problem chunk
+      if (mb.size() > 2)
+        for (size_t k = 0; k + 1 < mb.size(); ++k) {
+          ude_handle::Chunk c;
+          c.m_lo = mb[k]; c.m_hi = mb[k + 1];
+          c.task_begin = h->model_task0[(size_t)c.m_lo]; c.task_end = h->model_task0[(size_t)c.m_hi];
+          c.up_lo = c.dn_lo = th_end(c.m_lo); c.up_hi = c.dn_hi = th_end(c.m_hi);
+          h->chunks.push_back(c);
+        }
+    }
+  }
   UDE_CUDA_TRY(h, h->d_block_part.reserve((size_t)std::max(h->grid_grad, h->grid_fwd) * (size_t)(D.n_pm + 1) * std::max<size_t>(1, h->chunks.size())));
   if (h->chunks.size() > 1 && !h->s_h2d) {
     UDE_CUDA_TRY(h, cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
@@ -1029,6 +1078,38 @@ int ude_loss_grad(ude_handle* h, const double* theta, int64_t n_theta, double* l
     const int64_t cols = reads_uhat ? h->n_segments : 0;
     h->last_h2d = 8 * ((int64_t)d * cols + (int64_t)npm);
     h->last_d2h = 8 * ((int64_t)d * cols + (int64_t)npm + 1);
+  } else
+  if (K > 1 && grad && h->n_models > 1) {
+    // ---- pipelined host path, many-model handle: chunk = run of whole models; theta of run k+1 goes up and the gradient
+    // and losses of run k-1 come down while run k is on the SMs.  Each run is finalised (regulariser) right behind its kernel.
+    const ude_desc& D = h->desc;
+    const long long n_w1 = (long long)D.nn_hidden * D.nn_in, n_w2 = (long long)D.nn_out * D.nn_hidden;
+    double* dth = h->d_theta.p; double* dg = h->d_grad.p;
+    UDE_CUDA_TRY(h, cudaEventRecord(h->ev_start, s));
+    UDE_CUDA_TRY(h, cudaStreamWaitEvent(h->s_h2d, h->ev_start, 0));
+    UDE_CUDA_TRY(h, cudaStreamWaitEvent(h->s_d2h, h->ev_start, 0));
+    UDE_CUDA_TRY(h, cudaMemsetAsync(dg, 0, (size_t)n_theta * sizeof(double), s));
+    UDE_CUDA_TRY(h, cudaMemsetAsync(h->d_model_loss.p, 0, (size_t)h->n_models * sizeof(double), s));
+    for (size_t k = 0; k < K; ++k) {
+      const ude_handle::Chunk& c = h->chunks[k];
+      const size_t nb = (size_t)(c.up_hi - c.up_lo) * sizeof(double);
+      UDE_CUDA_TRY(h, cudaMemcpyAsync(dth + c.up_lo, theta + c.up_lo, nb, cudaMemcpyHostToDevice, h->s_h2d));
+      UDE_CUDA_TRY(h, cudaEventRecord(h->ev_up[k], h->s_h2d));
+      UDE_CUDA_TRY(h, cudaStreamWaitEvent(s, h->ev_up[k], 0));
+      int rc = launch_segments(h, dth, dg, nullptr, c.task_begin, c.task_end, 0, s);
+      if (rc != UDE_OK) return rc;
+      ude_finalize_multi<<<(int)(c.m_hi - c.m_lo), 128, 0, s>>>(dth, dg, h->d_model_loss.p + c.m_lo, h->d_theta_base.p + c.m_lo,
+                                                               h->d_model_col0.p + c.m_lo, D.d, D.off_w1, n_w1, D.off_w2, n_w2,
+                                                               h->d_reg_weight.p ? h->d_reg_weight.p + c.m_lo : nullptr, h->d_loss.p + c.m_lo);
+      UDE_CUDA_TRY(h, cudaGetLastError());
+      UDE_CUDA_TRY(h, cudaEventRecord(h->ev_done[k], s));
+      UDE_CUDA_TRY(h, cudaStreamWaitEvent(h->s_d2h, h->ev_done[k], 0));
+      UDE_CUDA_TRY(h, cudaMemcpyAsync(grad + c.dn_lo, dg + c.dn_lo, nb, cudaMemcpyDeviceToHost, h->s_d2h));
+      UDE_CUDA_TRY(h, cudaMemcpyAsync(loss + c.m_lo, h->d_loss.p + c.m_lo, (size_t)(c.m_hi - c.m_lo) * sizeof(double), cudaMemcpyDeviceToHost, h->s_d2h));
+    }
+    UDE_CUDA_TRY(h, cudaStreamSynchronize(s));
+    UDE_CUDA_TRY(h, cudaStreamSynchronize(h->s_d2h));
+    h->last_h2d = 8 * n_theta; h->last_d2h = 8 * (n_theta + h->n_models);
   } else
   if (K > 1 && grad) {
     // ---- pipelined host path: chunk k+1's uhat columns are uploaded and chunk k-1's gradient columns downloaded while
