@@ -374,7 +374,9 @@ def time_e2e(cx, eng, prob, theta0, steps, sparse=True):
     dense = h2d == 8 * n
     return {"value": eng.steps_per_eval() * cx.world * steps / el, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
             "ms_per_step": 1e3 * el / steps,
-            "api": ("ude_loss_grad (page-locked host theta in, loss + gradient out; dense copies of theta and gradient)" if dense else
+            "api": (("ude_loss_grad (page-locked host theta in, per-model losses + gradient out; dense copies of theta and gradient, "
+                     "pipelined in runs of whole models: H2D / kernel + finalize / D2H overlap)") if dense and prob.n_models > 1 else
+                    "ude_loss_grad (page-locked host theta in, loss + gradient out; dense copies of theta and gradient)" if dense else
                     "ude_loss_grad with UDE_OPT_SPARSE_UHAT_IO (page-locked host theta in, loss + gradient out; the block-start uhat "
                     "columns are read / their gradient written zero-copy by the kernels, process model copied; gradient buffer "
                     "zeroed once by the caller, structurally-zero entries never rewritten)"),
@@ -479,7 +481,7 @@ def main():
             todo += [("c3_tsit5", "c3", 100_000, "tsit5", 0), ("c3_f32_mode", "c3", 100_000, args.solver, 1)]
         for key, cfg, n, solver2, dt2k in todo:
             try:
-                others[key] = side_config(cx, key, cfg, n, solver2, dt2k, e2e=(key in ("c2", "c4") and not args.no_e2e))
+                others[key] = side_config(cx, key, cfg, n, solver2, dt2k, e2e=(key in ("c2", "c4", "c5") and not args.no_e2e))
             except Exception as ex:        # a side measurement must never take the headline down
                 others[key] = {"error": str(ex)[:200]}
                 cx.barrier()

@@ -6,6 +6,6 @@
 namespace {
 using namespace ude;
 RegisterKernels reg([] {
-  register_mma2_combo<4, 0, 4, 1, 3, MMA2_PARK_GW | MMA2_TAB16 | MMA2_AFFINE>("node_d4_mma2_h32_nt1", 0);
+  register_mma2_combo<4, 0, 4, 1, 3, MMA2_PARK_GW | MMA2_TAB16 | MMA2_AFFINE | MMA2_TANH3>("node_d4_mma2_h32_nt1", 0);
 });
 }  // namespace

@@ -156,7 +156,7 @@ __device__ __forceinline__ void mma_stage_forward(const double* __restrict__ s_w
   // completely but needs ~40 more live registers)
   if constexpr (MG::TB == 8 && MG::HT == 4) {
     double zi[8] = {z[0][0], z[0][1], z[1][0], z[1][1], z[2][0], z[2][1], z[3][0], z[3][1]}, ho[8];
-    ude_tanh_tab_vec<8>(zi, ho, s_tab);
+    ude_tanh_vec<8>(zi, ho, s_tab);
 #pragma unroll
     for (int t = 0; t < 4; ++t) { h[t][0] = ho[2 * t]; h[t][1] = ho[2 * t + 1]; }
   } else
@@ -164,11 +164,11 @@ __device__ __forceinline__ void mma_stage_forward(const double* __restrict__ s_w
   for (int t = 0; t < MG::HT; t += 2) {
     if (t + 1 < MG::HT) {
       double zi[4] = {z[t][0], z[t][1], z[t + 1][0], z[t + 1][1]}, ho[4];
-      ude_tanh_tab_vec<4>(zi, ho, s_tab);
+      ude_tanh_vec<4>(zi, ho, s_tab);
       h[t][0] = ho[0]; h[t][1] = ho[1]; h[t + 1][0] = ho[2]; h[t + 1][1] = ho[3];
     } else {
       double zi[2] = {z[t][0], z[t][1]}, ho[2];
-      ude_tanh_tab_vec<2>(zi, ho, s_tab);
+      ude_tanh_vec<2>(zi, ho, s_tab);
       h[t][0] = ho[0]; h[t][1] = ho[1];
     }
   }
@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) ude_mma_kernel(const DevP
   // stash: one record per RK stage
   double* __restrict__ stash = GRAD ? reinterpret_cast<double*>(P.stash) + warp_global * P.stash_rows_per_warp * 32 : nullptr;
 
-  ude_load_exp2_tab(s_tab);
+  ude_load_tanh_tab(s_tab);
   if constexpr (!RA) for (long long k = threadIdx.x; k <= P.n_pm; k += blockDim.x) s_red[k] = 0.0;
   const double* __restrict__ pm = P.theta + (long long)D * P.model_col0[1];        // single model: [uhat | pm]
   build_frags<MG>(P, pm, s_w);

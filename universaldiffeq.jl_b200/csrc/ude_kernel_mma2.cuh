@@ -41,6 +41,8 @@ enum { MMA2_PARK_GW = 1,      // park the weight-gradient accumulators in shared
                               // address of the stage loop "lane base + immediate": the rotation costs two integer
                               // instructions per access (~60 of the ~590 issued per stage and tile)
        // ablation bits for timing diagnosis ONLY (results are wrong): registered by ude_inst_mma2v_probe.cu
+       MMA2_TANH2 = 8192,     // 13-instruction tanh (ude_tanh_fast2_vec)
+       MMA2_TANH3 = 16384,    // + signed argument, integer clamp, biased table (ude_tanh_fast3_vec): ~4 fewer non-FP64 instructions
        MMA2_ABL_NO_TMA = 256, MMA2_ABL_NO_TANH = 512, MMA2_ABL_NO_GW = 1024, MMA2_ABL_NO_REC = 2048, MMA2_ABL_NO_COV = 4096 };      // 16 interleaved copies of the 2^(j/64) table: lane l of a half-warp reads bank pair l, so the
                               // table lookups of tanh are conflict-free (8 KB per block instead of 512 B)
 
@@ -156,7 +158,14 @@ __device__ __forceinline__ double cov_value(const DevProblem& P, CovLin& c, doub
   return fma(t - c.vhi, c.slope, c.xhi);
 }
 
-template <int N, int TB, int TS>
+template <int NV, int TS, int V2>
+__device__ __forceinline__ void tanh_vec_sel(const double (&zi)[NV], double (&ho)[NV], const double* s_tab, int toff) {
+  if constexpr (V2 == 3) ude_tanh_fast3_vec<NV, TS>(zi, ho, s_tab, toff);
+  else if constexpr (V2 == 2) ude_tanh_fast2_vec<NV, TS>(zi, ho, s_tab, toff);
+  else ude_tanh_fast_vec<NV, TS>(zi, ho, s_tab, toff);
+}
+
+template <int N, int TB, int TS, int V2 = 1>
 __device__ __forceinline__ void tanh_batches(double (&v)[N], const double* s_tab, int toff) {
   static_assert(N % 2 == 0 && (TB == 2 || TB == 4 || TB == 8), "batches of 2, 4 or 8 interleaved chains");
 #pragma unroll
@@ -166,7 +175,7 @@ __device__ __forceinline__ void tanh_batches(double (&v)[N], const double* s_tab
         double zi[8], ho[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) zi[q] = v[b + q < N ? b + q : 0];
-        ude_tanh_fast_vec<8, TS>(zi, ho, s_tab, toff);
+        tanh_vec_sel<8, TS, V2>(zi, ho, s_tab, toff);
 #pragma unroll
         for (int q = 0; q < 8; ++q) if (b + q < N) v[b + q] = ho[q];
         continue;
@@ -178,7 +187,7 @@ __device__ __forceinline__ void tanh_batches(double (&v)[N], const double* s_tab
         double zi[4], ho[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) zi[q] = v[b2 + q < N ? b2 + q : 0];
-        ude_tanh_fast_vec<4, TS>(zi, ho, s_tab, toff);
+        tanh_vec_sel<4, TS, V2>(zi, ho, s_tab, toff);
 #pragma unroll
         for (int q = 0; q < 4; ++q) if (b2 + q < N) v[b2 + q] = ho[q];
       }
@@ -186,7 +195,7 @@ __device__ __forceinline__ void tanh_batches(double (&v)[N], const double* s_tab
 #pragma unroll
       for (int b2 = b; b2 < (b + TB < N ? b + TB : N); b2 += 2) {
         double zi[2] = {v[b2], v[b2 + 1 < N ? b2 + 1 : 0]}, ho[2];
-        ude_tanh_fast_vec<2, TS>(zi, ho, s_tab, toff);
+        tanh_vec_sel<2, TS, V2>(zi, ho, s_tab, toff);
         v[b2] = ho[0];
         if (b2 + 1 < N) v[b2 + 1] = ho[1];
       }
@@ -241,7 +250,7 @@ __device__ __forceinline__ void mma2_stage_forward(const double* __restrict__ s_
 #pragma unroll
       for (int i = 0; i < NT * HT * 2; ++i) v[i] = fma(v[i], 0.125, 0.25);
     } else
-    tanh_batches<NT * HT * 2, MG::TB, (MG::OPT & MMA2_TAB16) ? 16 : 1>(v, s_tab, (MG::OPT & MMA2_TAB16) ? (lane & 15) : 0);
+    tanh_batches<NT * HT * 2, MG::TB, (MG::OPT & MMA2_TAB16) ? 16 : 1, ((MG::OPT & MMA2_TANH3) ? 3 : (MG::OPT & MMA2_TANH2) ? 2 : 1)>(v, s_tab, (MG::OPT & MMA2_TAB16) ? (lane & 15) : 0);
 #pragma unroll
     for (int tl = 0; tl < NT; ++tl)
 #pragma unroll
@@ -303,7 +312,8 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) ude_mma2_kernel(const Dev
   constexpr uint32_t kRecBytes = MG::RECW * 8;
   double* __restrict__ stash = GRAD ? reinterpret_cast<double*>(P.stash) + warp_global * P.stash_rows_per_warp * 32 : nullptr;
 
-  if constexpr (OPT & MMA2_TAB16) ude_load_exp2_tab_n<16>(s_tab); else ude_load_exp2_tab(s_tab);
+  if constexpr ((OPT & MMA2_TANH3) != 0) { if constexpr (OPT & MMA2_TAB16) ude_load_exp2_tabb_n<16>(s_tab); else ude_load_exp2_tabb_n<1>(s_tab); }
+  else if constexpr (OPT & MMA2_TAB16) ude_load_exp2_tab_n<16>(s_tab); else ude_load_exp2_tab(s_tab);
   for (long long k = threadIdx.x; k <= P.n_pm; k += blockDim.x) s_red[k] = 0.0;
   const double* __restrict__ pm = P.theta + (long long)D * P.model_col0[1];        // single model: [uhat | pm]
   build_frags<typename MG::Base>(P, pm, s_w);

@@ -231,13 +231,151 @@ __device__ __forceinline__ void ude_tanh_fast_vec(const double (&x)[N], double (
   for (int i = 0; i < N; ++i) out[i] = copysign(fma(-2.0, y[i], 1.0), x[i]);
 }
 
-// type-dispatched front end used by the typed kernel body
-#ifndef UDE_TANH_FAST
-#define UDE_TANH_FAST 1
+// Variant with 13 FP64-pipe instructions: since the result is formed as 1 - 2/(w + 1), w = exp(2|x|) needs no expm1-style
+// care, so the polynomial is a plain Horner form of E = exp(2 rh) (degree 5, |2 rh| <= ln2/128: the r^6/720 term is 3.4e-17)
+// and  w + 1 = fma(s, E, 1)  -- one FMA fewer than P / s2 / s + 1, and no second exponent patch in the integer pipe.
+// The rounding of E and of the fma put <= 2.5e-16 relative on w + 1, i.e. <= 2.5e-16 * 2w/(w+1)^2 <= 1.3e-16 absolute on
+// the result, on top of the same reciprocal / final-fma roundings as ude_tanh_fast_vec (tools/tanh_check.cu measures it).
+template <int N, int TS = 1>
+__device__ __forceinline__ void ude_tanh_fast2_vec(const double (&x)[N], double (&out)[N], const double* __restrict__ s_tab, int toff = 0) {
+  const double INV   = 184.6649652337873;              // 128 / ln 2
+  const double CH    = 0x1.62e42fefa39efp-8;           // (ln 2)/128
+  const double SHIFT = 6755399441055744.0;
+  double ax[N], kf[N], rh[N], q[N], T[N], s[N], den[N], y[N], e[N];
+  int Nn[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    int hi = __double2hiint(x[i]) & 0x7fffffff;
+    hi = min(hi, 0x40340000);                          // |x| <= 20
+    ax[i] = __hiloint2double(hi, __double2loint(x[i]));
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) kf[i] = fma(ax[i], INV, SHIFT);
+#pragma unroll
+  for (int i = 0; i < N; ++i) { Nn[i] = __double2loint(kf[i]); kf[i] -= SHIFT; }
+#pragma unroll
+  for (int i = 0; i < N; ++i) T[i] = s_tab[(Nn[i] & 63) * TS + toff];
+#pragma unroll
+  for (int i = 0; i < N; ++i) rh[i] = fma(kf[i], -CH, ax[i]);
+#pragma unroll
+  for (int i = 0; i < N; ++i) q[i] = fma(rh[i], 2.6666666666666666e-01, 6.6666666666666663e-01);   // 4/15, 2/3
+#pragma unroll
+  for (int i = 0; i < N; ++i) q[i] = fma(q[i], rh[i], 1.3333333333333333);                          // 4/3
+#pragma unroll
+  for (int i = 0; i < N; ++i) q[i] = fma(q[i], rh[i], 2.0);
+#pragma unroll
+  for (int i = 0; i < N; ++i) q[i] = fma(q[i], rh[i], 2.0);
+#pragma unroll
+  for (int i = 0; i < N; ++i) q[i] = fma(q[i], rh[i], 1.0);                                         // exp(2 rh)
+#pragma unroll
+  for (int i = 0; i < N; ++i) s[i] = __hiloint2double(__double2hiint(T[i]) + ((Nn[i] >> 6) << 20), __double2loint(T[i]));   // 2^n T_j
+#pragma unroll
+  for (int i = 0; i < N; ++i) den[i] = fma(s[i], q[i], 1.0);                                        // w + 1
+#pragma unroll
+  for (int i = 0; i < N; ++i) asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y[i]) : "d"(den[i]));
+#pragma unroll
+  for (int i = 0; i < N; ++i) e[i] = fma(-den[i], y[i], 1.0);
+#pragma unroll
+  for (int i = 0; i < N; ++i) e[i] = fma(e[i], e[i], e[i]);
+#pragma unroll
+  for (int i = 0; i < N; ++i) y[i] = fma(y[i], e[i], y[i]);
+#pragma unroll
+  for (int i = 0; i < N; ++i) out[i] = copysign(fma(-2.0, y[i], 1.0), x[i]);
+}
+
+// Variant 3: the same 13 FP64-pipe instructions with ~4 fewer integer / move instructions around them (the tanh phases
+// of the kernels are ISSUE-bound, DESIGN.md 4.0, so every instruction counts, not only the FP64 ones):
+//   * SIGNED argument: w = exp(2x), tanh x = 1 - 2/(w + 1) holds for either sign, so |x| and copysign go;
+//   * the clamp |x| <= 20 (beyond which the result is exactly +-1) is two integer min on the high word, in place: a signed
+//     min against hi(20) bounds the positive arguments (negative ones are negative integers), an unsigned min against
+//     hi(-20) bounds the negative ones (positive ones have the top bit clear).  +-inf saturate to +-1; a NaN becomes 1
+//     (as in the other variants: a diverged state shows up as a non-finite loss through the state itself);
+//   * BIASED table (ude_load_exp2_tabb*): entry j carries hi(T_j) - (j << 14), so the exponent patch is the single
+//     integer operation hi + (N << 14) = hi(T_j) + (n << 20), N = 64 n + j (no masking of j, no second shift).
+// Not exactly odd (tanh(-x) and -tanh(x) may differ in the last bit); absolute error as variant 2 (tools/tanh_check.cu).
+template <int N, int TS = 1>
+__device__ __forceinline__ void ude_tanh_fast3_vec(const double (&x)[N], double (&out)[N], const double* __restrict__ s_tabb, int toff = 0) {
+  const double INV   = 184.6649652337873;              // 128 / ln 2
+  const double CH    = 0x1.62e42fefa39efp-8;           // (ln 2)/128
+  const double SHIFT = 6755399441055744.0;
+  double xc[N], kf[N], rh[N], q[N], T[N], s[N], den[N], y[N], e[N];
+  int Nn[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    int hi = min(__double2hiint(x[i]), 0x40340000);
+    hi = (int)min((unsigned)hi, 0xc0340000u);
+    xc[i] = __hiloint2double(hi, __double2loint(x[i]));
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) kf[i] = fma(xc[i], INV, SHIFT);
+#pragma unroll
+  for (int i = 0; i < N; ++i) { Nn[i] = __double2loint(kf[i]); kf[i] -= SHIFT; }
+#pragma unroll
+  for (int i = 0; i < N; ++i) T[i] = s_tabb[(Nn[i] & 63) * TS + toff];
+#pragma unroll
+  for (int i = 0; i < N; ++i) rh[i] = fma(kf[i], -CH, xc[i]);
+#pragma unroll
+  for (int i = 0; i < N; ++i) q[i] = fma(rh[i], 2.6666666666666666e-01, 6.6666666666666663e-01);   // 4/15, 2/3
+#pragma unroll
+  for (int i = 0; i < N; ++i) q[i] = fma(q[i], rh[i], 1.3333333333333333);                          // 4/3
+#pragma unroll
+  for (int i = 0; i < N; ++i) q[i] = fma(q[i], rh[i], 2.0);
+#pragma unroll
+  for (int i = 0; i < N; ++i) q[i] = fma(q[i], rh[i], 2.0);
+#pragma unroll
+  for (int i = 0; i < N; ++i) q[i] = fma(q[i], rh[i], 1.0);                                         // exp(2 rh)
+#pragma unroll
+  for (int i = 0; i < N; ++i) s[i] = __hiloint2double(__double2hiint(T[i]) + (int)((unsigned)Nn[i] << 14), __double2loint(T[i]));   // 2^n T_j
+#pragma unroll
+  for (int i = 0; i < N; ++i) den[i] = fma(s[i], q[i], 1.0);                                        // w + 1
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    // MUFU.RCP64H produces the high word only; the seed (~2^-20) does not care about the low one, so it borrows the low word
+    // of s (dead from here on) instead of paying a move for a zero
+    double y0;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(den[i]));
+    y[i] = __hiloint2double(__double2hiint(y0), __double2loint(s[i]));
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) e[i] = fma(-den[i], y[i], 1.0);
+#pragma unroll
+  for (int i = 0; i < N; ++i) e[i] = fma(e[i], e[i], e[i]);
+#pragma unroll
+  for (int i = 0; i < N; ++i) y[i] = fma(y[i], e[i], y[i]);
+#pragma unroll
+  for (int i = 0; i < N; ++i) out[i] = fma(-2.0, y[i], 1.0);
+}
+
+// biased 2^(j/64) table for ude_tanh_fast3_vec: COPIES interleaved copies, entry j of copy q at [j * COPIES + q]
+template <int COPIES>
+__device__ __forceinline__ void ude_load_exp2_tabb_n(double* s_tab /* shared, 64 * COPIES doubles */) {
+  for (int i = threadIdx.x; i < 64 * COPIES; i += blockDim.x) {
+    const int j = i / COPIES;
+    const double T = c_ude_exp2_tab[j];
+    s_tab[i] = __hiloint2double(__double2hiint(T) - (j << 14), __double2loint(T));
+  }
+}
+
+// type-dispatched front end used by the kernels (lane-per-hidden-unit family and the round-1 DMMA family; the round-2 DMMA
+// kernel picks its variant by option flag).  UDE_TANH_V: 3 = ude_tanh_fast3_vec (default), 2 = fast2, 1 = fast, 0 = tab.
+// The table a kernel stages in shared memory must match: ude_load_tanh_tab (biased for variant 3).
+#ifndef UDE_TANH_V
+#define UDE_TANH_V 3
 #endif
+__device__ __forceinline__ void ude_load_tanh_tab(double* s_tab /* shared, 64 doubles */) {
+#if UDE_TANH_V == 3
+  ude_load_exp2_tabb_n<1>(s_tab);
+#else
+  ude_load_exp2_tab(s_tab);
+#endif
+}
 template <int N>
 __device__ __forceinline__ void ude_tanh_vec(const double (&x)[N], double (&out)[N], const double* __restrict__ s_tab) {
-#if UDE_TANH_FAST
+#if UDE_TANH_V == 3
+  ude_tanh_fast3_vec<N>(x, out, s_tab);
+#elif UDE_TANH_V == 2
+  ude_tanh_fast2_vec<N>(x, out, s_tab);
+#elif UDE_TANH_V == 1
   ude_tanh_fast_vec<N>(x, out, s_tab);
 #else
   ude_tanh_tab_vec<N>(x, out, s_tab);
