@@ -42,6 +42,8 @@ enum { MMA2_PARK_GW = 1,      // park the weight-gradient accumulators in shared
                               // instructions per access (~60 of the ~590 issued per stage and tile)
        // ablation bits for timing diagnosis ONLY (results are wrong): registered by ude_inst_mma2v_probe.cu
        MMA2_TANH2 = 8192,     // 13-instruction tanh (ude_tanh_fast2_vec)
+       MMA2_RING3 = 32768,    // reverse sweep: three-slot record ring, the record TWO stages ahead is in flight (one stage of lead is about
+                              // one HBM round trip with three warps per scheduler: the mbarrier waits showed up as long_sb stalls)
        MMA2_TANH3 = 16384,    // + signed argument, integer clamp, biased table (ude_tanh_fast3_vec): ~4 fewer non-FP64 instructions
        MMA2_ABL_NO_TMA = 256, MMA2_ABL_NO_TANH = 512, MMA2_ABL_NO_GW = 1024, MMA2_ABL_NO_REC = 2048, MMA2_ABL_NO_COV = 4096 };      // 16 interleaved copies of the 2^(j/64) table: lane l of a half-warp reads bank pair l, so the
                               // table lookups of tanh are conflict-free (8 KB per block instead of 512 B)
@@ -70,7 +72,8 @@ struct Mma2Geo : MmaGeo<D_, NX_, HT_, 1, 4> {
   static constexpr int PFL = 1 + KSU + 3 * Base::NX;       // prefetch slots (doubles) per lane and tile: time, data, 3 per covariate
   static constexpr int PFW = (OPT_ & 32) ? NT_ * 32 * PFL : 0;   // per warp
   static constexpr int WARP_FWD = PFW;
-  static constexpr int WARP_GRAD = 2 * RECW + NT_ * SCR1 + PARK + PFW;
+  static constexpr int RB = (OPT_ & MMA2_RING3) ? 3 : 2;   // stage-record slots per warp
+  static constexpr int WARP_GRAD = RB * RECW + NT_ * SCR1 + PARK + PFW;
   static constexpr int NA = (NT_ == 1) ? HT_ : (HT_ >= 2 ? 2 : 1);   // accumulators per tile for K-long products
   static constexpr int TABN = (OPT_ & MMA2_TAB16) ? 64 * 16 : 64;
   static constexpr bool AFF = (OPT_ & 64) != 0 && D_ == 4 * KSU && KSU < Base::KS;
@@ -286,7 +289,7 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) ude_mma2_kernel(const Dev
   static_assert(LK == LK_STATE || LK == LK_TRAJ, "derivative matching stays with ude_mma_kernel");
   constexpr int D = D_, NX = NX_, HT = HT_, NT = NT_, KS = MG::KS, KSU = MG::KSU, NXA = MG::NXA, NA = MG::NA;
   __shared__ double s_tab[MG::TABN];
-  __shared__ __align__(8) uint64_t s_bar[kBlockThreads / 32][2];
+  __shared__ __align__(8) uint64_t s_bar[kBlockThreads / 32][MG::RB];
   __shared__ __align__(16) double s_aff[MG::NAFF];
   extern __shared__ __align__(16) double s_dyn[];
   // [n_pm + 1 (block partial) padded even][weight fragments][per warp: 2 stage records (NT tiles each) | NT scratch tiles (+ park)]
@@ -296,9 +299,9 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) ude_mma2_kernel(const Dev
   constexpr bool SPF = (OPT & MMA2_SMEM_PF) != 0;
   double* s_warp = s_w + MG::NFRAG * 32 + (size_t)(threadIdx.x >> 5) * kPerWarp;
   double* s_stage = s_warp;
-  double* s_scr = s_warp + (GRAD ? 2 * MG::RECW : 0);
+  double* s_scr = s_warp + (GRAD ? MG::RB * MG::RECW : 0);
   // MMA2_SMEM_PF: this lane's prefetch slots, [tile][lane][time | data (KSU) | 3 per covariate]
-  const uint32_t s_pf = SPF ? smem_u32(s_warp + (GRAD ? 2 * MG::RECW + NT * MG::SCR1 + MG::PARK : 0)) + (uint32_t)((threadIdx.x & 31) * MG::PFL * 8) : 0u;
+  const uint32_t s_pf = SPF ? smem_u32(s_warp + (GRAD ? MG::RB * MG::RECW + NT * MG::SCR1 + MG::PARK : 0)) + (uint32_t)((threadIdx.x & 31) * MG::PFL * 8) : 0u;
   auto pf_slot = [&](int tl, int k) -> uint32_t { return s_pf + (uint32_t)((tl * 32 * MG::PFL + k) * 8); };
   uint64_t* bar = s_bar[threadIdx.x >> 5];
 
@@ -322,7 +325,7 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) ude_mma2_kernel(const Dev
       const int q = k / (8 * HT), j = k % (8 * HT);             // q = 0: b1 (slot D + NX), q >= 1: covariate q - 1 (slot D + q - 1)
       s_aff[k] = w1_slot<typename MG::Base>(P, pm, j, q == 0 ? D + NX : D + q - 1);
     }
-  if (GRAD && lane == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); }
+  if (GRAD && lane == 0) { for (int b = 0; b < MG::RB; ++b) mbar_init(&bar[b], 1); }
   uint32_t bar_phase = 0;
   __syncthreads();
 
@@ -595,9 +598,13 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) ude_mma2_kernel(const Dev
         if (lane == 0) {
           if constexpr (!(OPT & MMA2_DIRECT_ST)) bulk_wait_all<0>();
           if (nsteps > 0) {
-            const int rec = nsteps * T::S - 1, b = rec & 1;
+            const int rec = nsteps * T::S - 1, b = (MG::RB == 3) ? 0 : (rec & 1);      // three slots: the reverse sweep starts in slot 0
             mbar_expect_tx(&bar[b], kRecBytes);
             bulk_load(s_stage + b * MG::RECW, stash + (long long)rec * MG::RECW, kRecBytes, &bar[b]);
+            if (MG::RB == 3 && rec > 0) {
+              mbar_expect_tx(&bar[1], kRecBytes);
+              bulk_load(s_stage + MG::RECW, stash + (long long)(rec - 1) * MG::RECW, kRecBytes, &bar[1]);
+            }
           }
         }
         __syncwarp();
@@ -683,6 +690,7 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) ude_mma2_kernel(const Dev
       double hs[NT];
 #pragma unroll
       for (int tl = 0; tl < NT; ++tl) hs[tl] = 0.0;
+      [[maybe_unused]] int rb3 = 0;            // MMA2_RING3: slot of the record being reversed (0, 1, 2, 0, ...)
       for (int k = nsteps - 1; k >= 0; --k) {
         if (k >= pre) {
           if (n == S - 1) {
@@ -720,8 +728,17 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) ude_mma2_kernel(const Dev
 #pragma unroll
         for (int ii = 0; ii < T::S; ++ii) {
           const int st = T::S - 1 - ii;
-          const int rec = k * T::S + st, b = rec & 1;
+          const int rec = k * T::S + st;
+          int b;
+          if constexpr (MG::RB == 3) { b = rb3; rb3 = (rb3 == 2) ? 0 : rb3 + 1; } else b = rec & 1;
           if constexpr (!(OPT & MMA2_ABL_NO_TMA)) {
+          if constexpr (MG::RB == 3) {
+            if (rec > 1 && lane == 0) {        // the record two stages ahead goes into the slot the previous stage has just released
+              const int b2 = (b == 0) ? 2 : b - 1;
+              mbar_expect_tx(&bar[b2], kRecBytes);
+              bulk_load(s_stage + b2 * MG::RECW, stash + (long long)(rec - 2) * MG::RECW, kRecBytes, &bar[b2]);
+            }
+          } else
           if (rec > 0 && lane == 0) {          // prefetch the next record to be reversed into the other buffer
             mbar_expect_tx(&bar[b ^ 1], kRecBytes);
             bulk_load(s_stage + (b ^ 1) * MG::RECW, stash + (long long)(rec - 1) * MG::RECW, kRecBytes, &bar[b ^ 1]);
