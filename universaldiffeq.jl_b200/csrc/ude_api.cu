@@ -691,6 +691,7 @@ DevProblem make_dev_problem(const ude_handle* h, const double* d_theta, double* 
   P.knot_off = h->d_knot_off.p; P.knot_t = h->d_knot_t.p; P.knot_x = h->d_knot_x.p; P.knot_inv = h->d_knot_inv.p;
   P.dm_u = h->d_dm_u.p; P.dm_dudt = h->d_dm_dudt.p;
   P.segs = h->d_segs.p; P.task_begin = 0; P.n_tasks = h->n_tasks; P.n_models = (int)h->n_models;
+  P.n_cols_total = h->n_cols;
   P.theta = d_theta; P.grad = d_grad; P.traj_out = d_traj;
   P.uhat_x = nullptr; P.guhat_x = nullptr;
   P.block_part = h->d_block_part.p; P.model_loss = h->d_model_loss.p;

@@ -45,6 +45,7 @@ struct DevProblem {
   const double* dm_u; const double* dm_dudt;
   // work
   const Seg* segs; long long task_begin, n_tasks; int n_models;   // this launch covers tasks [task_begin, n_tasks)
+  long long n_cols_total;     // columns of data / uhat over all models (bounds the next-task prefetch guesses)
   // io
   const double* theta; double* grad; double* traj_out;
   // Single-model trajectory losses read only the block-start columns of uhat and each of those columns receives exactly
@@ -111,6 +112,12 @@ __host__ __device__ constexpr int ilog2(int n) { int l = 0; while (n > 1) { n >>
 template <int G, int N, class TV>
 __device__ __forceinline__ void group_allreduce(TV (&v)[N], int lane) {
   if constexpr (G == 1) { return; }
+  else if constexpr (G == 2) {
+    // two lanes: the plain exchange is N double shuffles and ONE shuffle latency; reduce-scatter + gather would be
+    // NP/2 + N shuffles, 2 NP selects and two dependent shuffle latencies (measured on the ten-unit kernels)
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], 1);
+  }
   else {
     constexpr int NP = next_pow2(N);
     TV w[NP];
@@ -161,6 +168,8 @@ __device__ __forceinline__ void group_allreduce(TV (&v)[N], int lane) {
 // ------------------------------------------------------------------------------------------------
 // TMA bulk copies (cp.async.bulk, SASS UBLKCP) between a warp's shared-memory staging buffers and its stash in global
 // memory, completion through an mbarrier (loads) or a bulk async-group (stores).  One lane issues, the warp consumes.
+// hint only: pull the line holding p towards L1 (the next task's inputs while this task's reverse sweep runs)
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

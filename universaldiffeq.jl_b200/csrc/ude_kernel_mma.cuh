@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) ude_mma_kernel(const DevP
   static_assert(HW == 1 || HW == kBlockThreads / 32, "a task is shared by one warp or by the whole block");
   using T = Tab<SOLVER>;
   constexpr int D = D_, NX = NX_, HT = HT_, KS = MG::KS;
-  __shared__ double s_tab[64];
+  __shared__ double s_tab[UDE_TANH_TAB_N];
   __shared__ __align__(8) uint64_t s_bar[kBlockThreads / 32][2];
   __shared__ __align__(16) double s_b1[MG::BX ? 8 * MG::HTT : 2];
   extern __shared__ __align__(16) double s_dyn[];

@@ -356,14 +356,79 @@ __device__ __forceinline__ void ude_load_exp2_tabb_n(double* s_tab /* shared, 64
   }
 }
 
+// Variant 4 (kernels whose table is a single copy): a 256-entry table, |rh| <= ln2/1024, so exp(2 rh) needs degree 4 only
+// (the (2 rh)^5/120 term is 3.8e-17): 12 FP64-pipe instructions and a dependent chain one FMA shorter.  Same structure as
+// variant 3: k = round(x 512/ln2) = 256 n + j, biased entry hi(T_j) - (j << 12), exponent patch hi + (N << 12).  The single
+// reduction constant ln2/512 has the same relative rounding as ln2/128, so the damping argument of ude_tanh_fast_vec holds.
+__constant__ double c_ude_exp2_tab256[256] = {
+#include "ude_exp2_table256.inc"
+};
+__device__ __forceinline__ void ude_load_exp2_tabb256(double* s_tab /* shared, 256 doubles */) {
+  for (int j = threadIdx.x; j < 256; j += blockDim.x) {
+    const double T = c_ude_exp2_tab256[j];
+    s_tab[j] = __hiloint2double(__double2hiint(T) - (j << 12), __double2loint(T));
+  }
+}
+template <int N>
+__device__ __forceinline__ void ude_tanh_fast4_vec(const double (&x)[N], double (&out)[N], const double* __restrict__ s_tabb) {
+  const double INV   = 738.6598609351493;               // 512 / ln 2
+  const double CH    = 0x1.62e42fefa39efp-10;           // (ln 2)/512
+  const double SHIFT = 6755399441055744.0;
+  double xc[N], kf[N], rh[N], q[N], T[N], s[N], den[N], y[N], e[N];
+  int Nn[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    int hi = min(__double2hiint(x[i]), 0x40340000);
+    hi = (int)min((unsigned)hi, 0xc0340000u);
+    xc[i] = __hiloint2double(hi, __double2loint(x[i]));
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) kf[i] = fma(xc[i], INV, SHIFT);
+#pragma unroll
+  for (int i = 0; i < N; ++i) { Nn[i] = __double2loint(kf[i]); kf[i] -= SHIFT; }
+#pragma unroll
+  for (int i = 0; i < N; ++i) T[i] = s_tabb[Nn[i] & 255];
+#pragma unroll
+  for (int i = 0; i < N; ++i) rh[i] = fma(kf[i], -CH, xc[i]);
+#pragma unroll
+  for (int i = 0; i < N; ++i) q[i] = fma(rh[i], 6.6666666666666663e-01, 1.3333333333333333);       // 2/3, 4/3
+#pragma unroll
+  for (int i = 0; i < N; ++i) q[i] = fma(q[i], rh[i], 2.0);
+#pragma unroll
+  for (int i = 0; i < N; ++i) q[i] = fma(q[i], rh[i], 2.0);
+#pragma unroll
+  for (int i = 0; i < N; ++i) q[i] = fma(q[i], rh[i], 1.0);                                         // exp(2 rh)
+#pragma unroll
+  for (int i = 0; i < N; ++i) s[i] = __hiloint2double(__double2hiint(T[i]) + (int)((unsigned)Nn[i] << 12), __double2loint(T[i]));   // 2^n T_j
+#pragma unroll
+  for (int i = 0; i < N; ++i) den[i] = fma(s[i], q[i], 1.0);                                        // w + 1
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    double y0;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(den[i]));
+    y[i] = __hiloint2double(__double2hiint(y0), __double2loint(s[i]));
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) e[i] = fma(-den[i], y[i], 1.0);
+#pragma unroll
+  for (int i = 0; i < N; ++i) e[i] = fma(e[i], e[i], e[i]);
+#pragma unroll
+  for (int i = 0; i < N; ++i) y[i] = fma(y[i], e[i], y[i]);
+#pragma unroll
+  for (int i = 0; i < N; ++i) out[i] = fma(-2.0, y[i], 1.0);
+}
+
 // type-dispatched front end used by the kernels (lane-per-hidden-unit family and the round-1 DMMA family; the round-2 DMMA
-// kernel picks its variant by option flag).  UDE_TANH_V: 3 = ude_tanh_fast3_vec (default), 2 = fast2, 1 = fast, 0 = tab.
-// The table a kernel stages in shared memory must match: ude_load_tanh_tab (biased for variant 3).
+// kernel picks its variant by option flag).  UDE_TANH_V: 4 = ude_tanh_fast4_vec (default), 3 = fast3, 2 = fast2, 1 = fast,
+// 0 = tab.  The table a kernel stages in shared memory must match: UDE_TANH_TAB_N doubles filled by ude_load_tanh_tab.
 #ifndef UDE_TANH_V
-#define UDE_TANH_V 3
+#define UDE_TANH_V 4
 #endif
-__device__ __forceinline__ void ude_load_tanh_tab(double* s_tab /* shared, 64 doubles */) {
-#if UDE_TANH_V == 3
+#define UDE_TANH_TAB_N (UDE_TANH_V == 4 ? 256 : 64)
+__device__ __forceinline__ void ude_load_tanh_tab(double* s_tab /* shared, UDE_TANH_TAB_N doubles */) {
+#if UDE_TANH_V == 4
+  ude_load_exp2_tabb256(s_tab);
+#elif UDE_TANH_V == 3
   ude_load_exp2_tabb_n<1>(s_tab);
 #else
   ude_load_exp2_tab(s_tab);
@@ -371,7 +436,9 @@ __device__ __forceinline__ void ude_load_tanh_tab(double* s_tab /* shared, 64 do
 }
 template <int N>
 __device__ __forceinline__ void ude_tanh_vec(const double (&x)[N], double (&out)[N], const double* __restrict__ s_tab) {
-#if UDE_TANH_V == 3
+#if UDE_TANH_V == 4
+  ude_tanh_fast4_vec<N>(x, out, s_tab);
+#elif UDE_TANH_V == 3
   ude_tanh_fast3_vec<N>(x, out, s_tab);
 #elif UDE_TANH_V == 2
   ude_tanh_fast2_vec<N>(x, out, s_tab);
