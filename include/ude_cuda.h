@@ -153,7 +153,12 @@ const char* ude_kernel_name(ude_handle* h);
 int32_t ude_launches_per_eval(const ude_handle* h);
 
 /* loss[n_models] and grad[n_theta] (grad may be NULL: loss only). Synchronous, host buffers:
- * H2D(theta) -> kernels (-> allreduce) -> D2H(loss, grad). */
+ * H2D(theta) -> kernels (-> allreduce) -> D2H(loss, grad).  Large problems are pipelined inside the call (page-locked
+ * buffers make the copies asynchronous): a single-model handle in chunks of series, a many-model handle in runs of whole
+ * models (theta of run k+1 up, gradient and losses of run k-1 down, while run k is on the SMs); with
+ * UDE_OPT_SPARSE_UHAT_IO the trajectory losses of a single-model handle move only the block-start columns (zero-copy).
+ * Tuning aids (environment, read when the plan is built): UDE_HOST_CHUNKS=<n> (1 = no pipeline), UDE_HOST_CHUNK_ROUNDS=0,
+ * UDE_HOST_CHUNK_EDGE=0, UDE_KERNEL=<substring of a kernel name>. */
 int ude_loss_grad(ude_handle* h, const double* theta, int64_t n_theta, double* loss, double* grad);
 /* Same with device-resident theta / loss / grad on `stream` (a cudaStream_t; NULL = the handle's stream).
  * Asynchronous: returns after enqueueing. No nonfinite check. */
