@@ -11,7 +11,7 @@
 //   (b) NT = 2 M-tiles (16 segments) per warp: every weight B fragment read from shared memory (LDS.64) feeds two DMMAs,
 //       and a warp carries twice the independent DMMA / tanh chains, so two resident warps per scheduler keep the FP64
 //       pipe fed where three were not.
-//   (c) fewer FP64-pipe instructions around the MMAs: tanh in 14 instead of 19 (ude_tanh_fast_vec), b2 rides in the
+//   (c) fewer FP64-pipe instructions around the MMAs: tanh in 14 instead of 19 (ude_tanh_fast_vec; MMA2_TANH3: 13 + 8 other), b2 rides in the
 //       accumulator of the first layer-2 DMMA, step sizes are formed with a multiply by 1/substeps.
 // Loss families LK_STATE and LK_TRAJ (derivative matching has no time stepping: ude_kernel_mma.cuh keeps it).
 // Reference semantics: src/MultiProcessModel.jl:215-218 (RHS), src/covariates.jl:46-48 (interpolation),
